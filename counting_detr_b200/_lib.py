@@ -1,0 +1,101 @@
+"""ctypes loader for libcdetr_sm100a.so (the C ABI declared in include/cdetr.h).
+
+The product path has no fallback: if the library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcdetr_sm100a.so")
+_lib = None
+
+
+class CdetrError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CdetrError(
+                f"{LIB_PATH} not built: run `python __graft_entry__.py` (nvcc, sm_100a). "
+                "There is no CPU/eager fallback for the hot path.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.cdetr_last_error.restype = C.c_char_p
+        _lib.cdetr_version.restype = C.c_int
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise CdetrError(f"{what} failed ({rc}): {lib().cdetr_last_error().decode()}")
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class SplitT(C.Structure):
+    """cdetr_split_t"""
+    _fields_ = [("base", C.c_void_p), ("ld", C.c_int64), ("plane", C.c_int64)]
+
+
+def split_view(t):
+    """t: bf16 tensor [2, rows, ld] (planes hi, lo), possibly a row/column slice of a bigger one."""
+    if t is None:
+        return SplitT(None, 0, 0)
+    assert t.dtype == torch.bfloat16 and t.dim() == 3 and t.shape[0] == 2 and t.stride(2) == 1, (t.shape, t.stride())
+    return SplitT(t.data_ptr(), t.stride(1), t.stride(0))
+
+
+class GemmT(C.Structure):
+    """cdetr_gemm_t"""
+    _fields_ = [
+        ("mode", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("a", SplitT), ("b", SplitT),
+        ("block_n", C.c_int32), ("split_k", C.c_int32),
+        ("row_scale", C.c_void_p), ("bias", C.c_void_p),
+        ("add_split", SplitT),
+        ("add_f32", C.c_void_p), ("ld_add_f32", C.c_int64),
+        ("mask", SplitT),
+        ("relu", C.c_int32), ("accumulate", C.c_int32),
+        ("out_f32", C.c_void_p), ("ld_out_f32", C.c_int64),
+        ("out_split", SplitT),
+    ]
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def gemm(a, b, M, N, K, mode=0, out_f32=None, out_split=None, bias=None, row_scale=None,
+         add_split=None, add_f32=None, mask=None, relu=False, accumulate=False, block_n=0, split_k=1):
+    """cdetr_gemm: see include/cdetr.h. a, b, add_split, mask, out_split are split tensors [2, rows, ld]."""
+    g = GemmT()
+    g.mode, g.M, g.N, g.K = mode, M, N, K
+    g.a, g.b = split_view(a), split_view(b)
+    g.block_n, g.split_k = block_n, split_k
+    g.row_scale, g.bias = _ptr(row_scale), _ptr(bias)
+    g.add_split = split_view(add_split)
+    g.add_f32 = _ptr(add_f32)
+    g.ld_add_f32 = add_f32.stride(0) if add_f32 is not None else 0
+    g.mask = split_view(mask)
+    g.relu, g.accumulate = int(relu), int(accumulate)
+    g.out_f32 = _ptr(out_f32)
+    g.ld_out_f32 = out_f32.stride(0) if out_f32 is not None else 0
+    g.out_split = split_view(out_split)
+    check(lib().cdetr_gemm(C.byref(g), stream_ptr()), "cdetr_gemm")
+
+
+def to_split(x):
+    """torch restatement of the split-bf16 format (used by tests; the product path packs on device)."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo])
+
+
+def from_split(s):
+    return s[0].float() + s[1].float()

@@ -1,0 +1,448 @@
+// tcgen05 / TMA / TMEM GEMM for split-bf16 operands (see common.cuh for the number format).
+//
+//   mode 0 (TN): D[M,N] = A[M,K] * B[N,K]^T    both operands K-major   (forward / dgrad)
+//   mode 1 (NT): D[M,N] = A[K,M]^T * B[K,N]    both operands MN-major  (wgrad)
+//
+// One CTA computes one 128 x BN output tile (optionally one K-split of it):
+//   warp 0     TMA producer  : cp.async.bulk.tensor (SWIZZLE_128B) of the hi+lo planes of A and B
+//   warp 1     MMA issuer    : per 64-wide k block, 4 k-steps x 3 tcgen05.mma (hi*lo, lo*hi, hi*hi)
+//   warps 2-5  epilogue      : tcgen05.ld of the fp32 accumulator (one TMEM lane = one row per thread)
+//                              -> row-scale / bias / residual / ReLU / ReLU-mask -> fp32 and/or split-bf16
+// smem stages are recycled through full/empty mbarriers; the accumulator lives in TMEM.
+//
+// Replaces the ATen GEMM call sites listed in include/cdetr.h (cdetr_gemm).
+#include "common.cuh"
+#include "../../include/cdetr.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 6;
+
+struct EpilogueArgs {
+  const float* row_scale;
+  const float* bias;
+  const __nv_bfloat16* add_hi;
+  const __nv_bfloat16* add_lo;
+  int64_t ld_add;
+  const float* add_f32;
+  int64_t ld_add_f32;
+  const __nv_bfloat16* mask_hi;
+  int64_t ld_mask;
+  int relu;
+  int atomic;
+  float* out_f32;
+  int64_t ld_out_f32;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  int64_t ld_out_split;
+};
+
+struct KernelArgs {
+  int M, N, K;
+  int block_n;
+  int stages;
+  int kb_per_split;  // k blocks (of 64) handled by one blockIdx.z
+  int num_kb;
+  uint32_t idesc;
+  uint32_t tmem_cols;
+  EpilogueArgs ep;
+};
+
+template <bool NT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const KernelArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // SWIZZLE_128B atoms need 1024-byte alignment of every tile base.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  const int BN = args.block_n;
+  const uint32_t a_bytes = 2u * BM * 128u;               // hi+lo planes, 128 B per row/k-row
+  const uint32_t b_bytes = NT ? (uint32_t)((BN + 63) / 64) * 16384u : 2u * (uint32_t)BN * 128u;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)args.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int kb_begin = blockIdx.z * args.kb_per_split;
+  const int kb_end = min(args.num_kb, kb_begin + args.kb_per_split);
+  const int stages = args.stages;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_holder, args.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int it = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* a_s = smem + (size_t)s * stage_bytes;
+        uint8_t* b_s = a_s + a_bytes;
+        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        if (!NT) {
+          tma_load_3d(a_s, &tmA, &full_bar[s], kb * BK, m0, 0);  // box {64, BM, 2}
+          tma_load_3d(b_s, &tmB, &full_bar[s], kb * BK, n0, 0);  // box {64, BN, 2}
+        } else {
+          for (int c = 0; c < BM / 64; ++c)                       // box {64(mn), 64(k), 2}
+            tma_load_3d(a_s + c * 16384, &tmA, &full_bar[s], m0 + 64 * c, kb * BK, 0);
+          for (int c = 0; c < (BN + 63) / 64; ++c)
+            tma_load_3d(b_s + c * 16384, &tmB, &full_bar[s], n0 + 64 * c, kb * BK, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      int it = 0;
+      uint32_t acc = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_base = a_base + a_bytes;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          uint64_t a_hi, a_lo, b_hi, b_lo;
+          if (!NT) {
+            // K-major SW128: rows at 128 B pitch, 8-row groups 1024 B apart, k-step = +32 B.
+            a_hi = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
+            a_lo = make_smem_desc_sw128(a_base + BM * 128 + k * 32, 16, 1024);
+            b_hi = make_smem_desc_sw128(b_base + k * 32, 16, 1024);
+            b_lo = make_smem_desc_sw128(b_base + BN * 128 + k * 32, 16, 1024);
+          } else {
+            // MN-major SW128: 64-wide MN chunks 16 KB apart (LBO), 8-k groups 1024 B apart (SBO),
+            // one k-step (16) = two k groups = +2048 B; lo plane 8 KB after hi inside a chunk.
+            a_hi = make_smem_desc_sw128(a_base + k * 2048, 16384, 1024);
+            a_lo = make_smem_desc_sw128(a_base + 8192 + k * 2048, 16384, 1024);
+            b_hi = make_smem_desc_sw128(b_base + k * 2048, 16384, 1024);
+            b_lo = make_smem_desc_sw128(b_base + 8192 + k * 2048, 16384, 1024);
+          }
+          umma_bf16_ss(tmem_base, a_hi, b_lo, args.idesc, acc);
+          acc = 1;
+          umma_bf16_ss(tmem_base, a_lo, b_hi, args.idesc, 1);
+          umma_bf16_ss(tmem_base, a_hi, b_hi, args.idesc, 1);
+        }
+        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ------------------------------ epilogue ----------------------------------
+    const EpilogueArgs& ep = args.ep;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < args.M;
+    const float rs = (ep.row_scale != nullptr && row_ok) ? ep.row_scale[row] : 1.0f;
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool vec_ok = ((ep.ld_out_f32 & 3) == 0) && ((ep.ld_out_split & 7) == 0) &&
+                        ((ep.ld_add & 7) == 0) && ((ep.ld_add_f32 & 3) == 0) &&
+                        ((ep.ld_mask & 7) == 0);
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r);
+      tmem_ld_wait();
+      const int nb = n0 + c0;
+      if (!row_ok || nb >= args.N) continue;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * rs;
+      const bool full = vec_ok && (nb + 16 <= args.N);
+      if (ep.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nb + j < args.N) v[j] += __ldg(ep.bias + nb + j);
+      }
+      if (ep.add_hi != nullptr) {
+        const __nv_bfloat16* ph = ep.add_hi + (int64_t)row * ep.ld_add + nb;
+        const __nv_bfloat16* pl = ep.add_lo + (int64_t)row * ep.ld_add + nb;
+        if (full) {
+          uint4 h[2], l[2];
+          h[0] = __ldg(reinterpret_cast<const uint4*>(ph));
+          h[1] = __ldg(reinterpret_cast<const uint4*>(ph) + 1);
+          l[0] = __ldg(reinterpret_cast<const uint4*>(pl));
+          l[1] = __ldg(reinterpret_cast<const uint4*>(pl) + 1);
+          const uint32_t* hw = reinterpret_cast<const uint32_t*>(h);
+          const uint32_t* lw = reinterpret_cast<const uint32_t*>(l);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[2 * j] += bf16_bits_to_float(hw[j] & 0xffffu) + bf16_bits_to_float(lw[j] & 0xffffu);
+            v[2 * j + 1] += bf16_bits_to_float(hw[j] >> 16) + bf16_bits_to_float(lw[j] >> 16);
+          }
+        } else {
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < args.N) v[j] += join_bf16(ph[j], pl[j]);
+        }
+      }
+      if (ep.add_f32 != nullptr) {
+        const float* pa = ep.add_f32 + (int64_t)row * ep.ld_add_f32 + nb;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(pa) + j);
+            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+          }
+        } else {
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < args.N) v[j] += pa[j];
+        }
+      }
+      if (ep.relu) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+      }
+      if (ep.mask_hi != nullptr) {
+        const __nv_bfloat16* pm = ep.mask_hi + (int64_t)row * ep.ld_mask + nb;
+        if (full) {
+          uint4 h[2];
+          h[0] = __ldg(reinterpret_cast<const uint4*>(pm));
+          h[1] = __ldg(reinterpret_cast<const uint4*>(pm) + 1);
+          const uint32_t* hw = reinterpret_cast<const uint32_t*>(h);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (!(bf16_bits_to_float(hw[j] & 0xffffu) > 0.0f)) v[2 * j] = 0.0f;
+            if (!(bf16_bits_to_float(hw[j] >> 16) > 0.0f)) v[2 * j + 1] = 0.0f;
+          }
+        } else {
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < args.N && !(__bfloat162float(pm[j]) > 0.0f)) v[j] = 0.0f;
+        }
+      }
+      if (ep.out_f32 != nullptr) {
+        float* po = ep.out_f32 + (int64_t)row * ep.ld_out_f32 + nb;
+        if (ep.atomic) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              atomicAdd(reinterpret_cast<float4*>(po) + j,
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          } else {
+            for (int j = 0; j < 16; ++j)
+              if (nb + j < args.N) atomicAdd(po + j, v[j]);
+          }
+        } else if (full) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            reinterpret_cast<float4*>(po)[j] =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < args.N) po[j] = v[j];
+        }
+      }
+      if (ep.out_hi != nullptr) {
+        __nv_bfloat16* ph = ep.out_hi + (int64_t)row * ep.ld_out_split + nb;
+        __nv_bfloat16* pl = ep.out_lo + (int64_t)row * ep.ld_out_split + nb;
+        if (full) {
+          uint32_t hw[8], lw[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[2 * j], h0, l0);
+            split_bf16(v[2 * j + 1], h1, l1);
+            hw[j] = pack_bf16x2(h0, h1);
+            lw[j] = pack_bf16x2(l0, l1);
+          }
+          reinterpret_cast<uint4*>(ph)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          reinterpret_cast<uint4*>(ph)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+          reinterpret_cast<uint4*>(pl)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          reinterpret_cast<uint4*>(pl)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+        } else {
+          for (int j = 0; j < 16; ++j)
+            if (nb + j < args.N) split_bf16(v[j], ph[j], pl[j]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, args.tmem_cols);
+  }
+}
+
+// -------------------------------- host side ---------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 3-D map over a split matrix: dim0 = contiguous index (extent inner), dim1 = rows, dim2 = plane.
+int make_split_map(CUtensorMap* map, const cdetr_split_t& t, int64_t inner, int64_t rows,
+                   int box_inner, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    cdetr_set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return CDETR_ERR_CUDA;
+  }
+  CDETR_CHECK_ARG(t.base != nullptr, "gemm: null operand");
+  CDETR_CHECK_ARG((reinterpret_cast<uintptr_t>(t.base) & 15) == 0, "gemm: operand not 16B aligned");
+  CDETR_CHECK_ARG(t.ld % 8 == 0 && t.plane % 8 == 0 && t.ld >= inner && t.plane > 0,
+                  "gemm: operand ld/plane must be multiples of 8 elements (ld=%lld plane=%lld)",
+                  (long long)t.ld, (long long)t.plane);
+  cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)rows, 2};
+  cuuint64_t gstride[2] = {(cuuint64_t)t.ld * 2, (cuuint64_t)t.plane * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t.base, gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    cdetr_set_error("cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld ld=%lld box=%dx%d",
+                    (int)r, (long long)inner, (long long)rows, (long long)t.ld, box_inner, box_rows);
+    return CDETR_ERR_CUDA;
+  }
+  return CDETR_OK;
+}
+
+}  // namespace
+
+extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CDETR_CHECK_ARG(g != nullptr, "gemm: null descriptor");
+  CDETR_CHECK_ARG(g->mode == 0 || g->mode == 1, "gemm: bad mode %d", g->mode);
+  CDETR_CHECK_ARG(g->M > 0 && g->N > 0 && g->K > 0, "gemm: bad shape %d %d %d", g->M, g->N, g->K);
+  CDETR_CHECK_ARG(g->out_f32 != nullptr || g->out_split.base != nullptr, "gemm: no output");
+  const bool nt = g->mode == 1;
+
+  int bn = g->block_n;
+  if (bn <= 0) {
+    if (g->N >= 256 && (int64_t)cdiv(g->M, BM) * cdiv(g->N, 256) >= 120) bn = 256;
+    else if (g->N > 64) bn = 128;
+    else if (g->N > 32) bn = 64;
+    else if (g->N > 16) bn = 32;
+    else bn = 16;
+    if (nt && bn < 64) bn = 64;
+  }
+  CDETR_CHECK_ARG(bn >= 16 && bn <= 256 && bn % 16 == 0, "gemm: bad block_n %d", bn);
+  CDETR_CHECK_ARG(!nt || bn % 64 == 0, "gemm: mode 1 needs block_n multiple of 64");
+
+  const int num_kb = cdiv(g->K, BK);
+  int splits = g->split_k > 1 ? g->split_k : 1;
+  if (splits > num_kb) splits = num_kb;
+  int kb_per_split = cdiv(num_kb, splits);
+  splits = cdiv(num_kb, kb_per_split);
+  const bool atomic = g->accumulate != 0 || splits > 1;
+  if (splits > 1)
+    CDETR_CHECK_ARG(g->out_split.base == nullptr && g->bias == nullptr && !g->relu &&
+                        g->add_split.base == nullptr && g->add_f32 == nullptr &&
+                        g->mask.base == nullptr && g->out_f32 != nullptr,
+                    "gemm: split_k only supports (row_scale, atomic out_f32) epilogues");
+  if (g->accumulate) CDETR_CHECK_ARG(g->out_f32 != nullptr, "gemm: accumulate needs out_f32");
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!nt) {
+    if ((rc = make_split_map(&tmA, g->a, g->K, g->M, BK, BM)) != 0) return rc;
+    if ((rc = make_split_map(&tmB, g->b, g->K, g->N, BK, bn)) != 0) return rc;
+  } else {
+    if ((rc = make_split_map(&tmA, g->a, g->M, g->K, 64, BK)) != 0) return rc;
+    if ((rc = make_split_map(&tmB, g->b, g->N, g->K, 64, BK)) != 0) return rc;
+  }
+
+  KernelArgs ka;
+  ka.M = g->M; ka.N = g->N; ka.K = g->K;
+  ka.block_n = bn;
+  ka.kb_per_split = kb_per_split;
+  ka.num_kb = num_kb;
+  ka.idesc = make_idesc_bf16_f32(BM, bn, nt ? 1 : 0, nt ? 1 : 0);
+  uint32_t cols = 32;
+  while ((int)cols < bn) cols <<= 1;
+  ka.tmem_cols = cols;
+  const uint32_t a_bytes = 2u * BM * 128u;
+  const uint32_t b_bytes = nt ? (uint32_t)((bn + 63) / 64) * 16384u : 2u * (uint32_t)bn * 128u;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t tail_bytes = (2 * MAX_STAGES + 1) * 8 + 16;
+  const uint32_t smem_budget = 227u * 1024u - 1024u - tail_bytes;
+  int stages = (int)(smem_budget / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > kb_per_split) stages = kb_per_split < 2 ? 2 : kb_per_split;
+  if ((uint32_t)stages * stage_bytes > smem_budget) stages = (int)(smem_budget / stage_bytes);
+  CDETR_CHECK_ARG(stages >= 1, "gemm: tile does not fit shared memory");
+  ka.stages = stages;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + tail_bytes + 1024;
+
+  EpilogueArgs& ep = ka.ep;
+  ep.row_scale = g->row_scale;
+  ep.bias = g->bias;
+  ep.add_hi = reinterpret_cast<const __nv_bfloat16*>(g->add_split.base);
+  ep.add_lo = ep.add_hi ? ep.add_hi + g->add_split.plane : nullptr;
+  ep.ld_add = ep.add_hi ? g->add_split.ld : 0;
+  ep.add_f32 = g->add_f32;
+  ep.ld_add_f32 = g->add_f32 ? g->ld_add_f32 : 0;
+  ep.mask_hi = reinterpret_cast<const __nv_bfloat16*>(g->mask.base);
+  ep.ld_mask = ep.mask_hi ? g->mask.ld : 0;
+  ep.relu = g->relu;
+  ep.atomic = atomic ? 1 : 0;
+  ep.out_f32 = g->out_f32;
+  ep.ld_out_f32 = g->out_f32 ? g->ld_out_f32 : 0;
+  ep.out_hi = reinterpret_cast<__nv_bfloat16*>(g->out_split.base);
+  ep.out_lo = ep.out_hi ? ep.out_hi + g->out_split.plane : nullptr;
+  ep.ld_out_split = ep.out_hi ? g->out_split.ld : 0;
+  // vector paths need 16-byte aligned bases
+  auto mis = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
+  if (mis(ep.add_hi) || mis(ep.add_lo) || mis(ep.add_f32) || mis(ep.mask_hi) || mis(ep.out_f32) ||
+      mis(ep.out_hi) || mis(ep.out_lo)) {
+    cdetr_set_error("gemm: epilogue tensors must be 16-byte aligned");
+    return CDETR_ERR_ARG;
+  }
+
+  dim3 grid(cdiv(g->N, bn), cdiv(g->M, BM), splits);
+  auto kern = nt ? gemm_split_kernel<true> : gemm_split_kernel<false>;
+  static size_t configured[2] = {0, 0};
+  if (configured[nt] < smem_bytes) {
+    CDETR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          227 * 1024));
+    configured[nt] = 227 * 1024;
+  }
+  kern<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, ka);
+  CDETR_CHECK_LAUNCH();
+  return CDETR_OK;
+}

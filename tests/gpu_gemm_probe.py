@@ -1,0 +1,103 @@
+"""First-contact probe of the tcgen05 GEMM on a B200: many shapes/epilogues against an fp64 product."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from counting_detr_b200 import _lib as L
+
+torch.manual_seed(0)
+dev = "cuda"
+fails = 0
+
+
+def report(name, got, ref):
+    global fails
+    err = (got.double() - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-30
+    rel = err / scale
+    ok = rel < 2e-5
+    fails += (not ok)
+    print(f"{'OK  ' if ok else 'FAIL'} {name}: max_abs_err={err:.3e} rel={rel:.3e}", flush=True)
+    return ok
+
+
+def run_tn(M, N, K, block_n=0, **kw):
+    A = torch.randn(M, K, device=dev)
+    B = torch.randn(N, K, device=dev)
+    ref = A.double() @ B.double().t()
+    out = torch.full((M, N), float("nan"), device=dev)
+    L.gemm(L.to_split(A), L.to_split(B), M, N, K, mode=0, out_f32=out, block_n=block_n, **kw)
+    torch.cuda.synchronize()
+    return report(f"TN M={M} N={N} K={K} bn={block_n} {kw}", out, ref)
+
+
+def run_nt(M, N, K, block_n=0, split_k=1):
+    A = torch.randn(K, M, device=dev)
+    B = torch.randn(K, N, device=dev)
+    ref = A.double().t() @ B.double()
+    out = torch.zeros((M, N), device=dev)
+    L.gemm(L.to_split(A), L.to_split(B), M, N, K, mode=1, out_f32=out, block_n=block_n, split_k=split_k,
+           accumulate=True)
+    torch.cuda.synchronize()
+    return report(f"NT M={M} N={N} K={K} bn={block_n} split_k={split_k}", out, ref)
+
+
+print("lib version", L.lib().cdetr_version(), torch.cuda.get_device_name(0), flush=True)
+run_tn(128, 128, 64)
+run_tn(128, 128, 256)
+run_tn(256, 256, 512)
+run_tn(128, 16, 64, block_n=16)
+run_tn(128, 64, 128, block_n=64)
+run_tn(128, 256, 128, block_n=256)
+run_tn(300, 200, 200)          # ragged everything (K tail by TMA zero fill)
+run_tn(1000, 2, 256)           # head-like N=2
+run_tn(4800, 4, 256)
+run_tn(16384, 256, 2048)
+run_tn(16384, 1024, 256)
+run_tn(4096, 2304, 256)
+run_nt(128, 128, 64)
+run_nt(128, 128, 1024)
+run_nt(256, 2304, 4096, split_k=8)
+run_nt(256, 256, 16384, split_k=16)
+run_nt(200, 72, 1000, split_k=3)  # ragged
+run_nt(64, 192, 512)
+
+# epilogue: bias + residual(split) + relu + split output; relu-mask; row_scale
+M, N, K = 512, 256, 320
+A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev)
+bias = torch.randn(N, device=dev); res = torch.randn(M, N, device=dev)
+ref = torch.relu(A.double() @ B.double().t() + bias.double() + L.from_split(L.to_split(res)).double())
+out = torch.empty(M, N, device=dev); outs = torch.zeros(2, M, N, device=dev, dtype=torch.bfloat16)
+L.gemm(L.to_split(A), L.to_split(B), M, N, K, out_f32=out, out_split=outs, bias=bias, add_split=L.to_split(res), relu=True)
+torch.cuda.synchronize()
+report("epilogue bias+res+relu f32", out, ref)
+report("epilogue bias+res+relu split", L.from_split(outs), ref)
+mask = torch.randn(M, N, device=dev)
+rs = torch.randn(M, device=dev)
+addf = torch.randn(M, N, device=dev)
+ref = ((A.double() @ B.double().t()) * rs.double()[:, None] + addf.double()) * (mask > 0).double()
+L.gemm(L.to_split(A), L.to_split(B), M, N, K, out_f32=out, row_scale=rs, add_f32=addf, mask=L.to_split(torch.relu(mask)))
+torch.cuda.synchronize()
+report("epilogue row_scale+add_f32+mask", out, ref)
+
+# sub-view operands (row slice of a bigger weight, column slice of an activation)
+Wbig = torch.randn(1280, 256, device=dev); X = torch.randn(700, 512, device=dev)
+Ws = L.to_split(Wbig); Xs = L.to_split(X)
+out = torch.empty(700, 256, device=dev)
+L.gemm(Xs[:, :, 256:], Ws[:, 512:768], 700, 256, 256, out_f32=out)
+torch.cuda.synchronize()
+report("subview", out, X[:, 256:].double() @ Wbig[512:768].double().t())
+
+# timing (rough): big TN GEMM
+for (M, N, K, bn) in [(16384, 2048, 512, 128), (16384, 2048, 512, 256), (16384, 512, 4608, 128), (16384, 512, 4608, 256), (65536, 256, 256, 128), (16384, 1024, 256, 256)]:
+    A = L.to_split(torch.randn(M, K, device=dev)); B = L.to_split(torch.randn(N, K, device=dev))
+    outs = torch.empty(2, M, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        L.gemm(A, B, M, N, K, out_split=outs, block_n=bn)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        L.gemm(A, B, M, N, K, out_split=outs, block_n=bn)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    print(f"time TN M={M} N={N} K={K} bn={bn}: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s(fp32-equiv) {3*2*M*N*K/ms/1e9:.1f} TFLOP/s(bf16 issued)", flush=True)
+print("FAILS", fails)
