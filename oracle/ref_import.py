@@ -42,6 +42,8 @@ def load(stage):
         for name in ("models.anchor_center", "models.centerness"):
             stub = types.ModuleType(name)
             stub.build = lambda args: None
+            stub.build_anchor_center = lambda args: None
+            stub.build_centerness = lambda args: None
             sys.modules[name] = stub
     # skip pretrained download/load: patch before models.backbone binds it
     misc = importlib.import_module("util.misc")
