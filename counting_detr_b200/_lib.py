@@ -99,3 +99,79 @@ def to_split(x):
 
 def from_split(s):
     return s[0].float() + s[1].float()
+
+
+# ---------------------------------------------------------------------------------------------
+# Generic typed call layer for the rest of the C ABI (include/cdetr.h).
+#   p = device pointer (torch tensor or None), i = int32, l = int64, f = float, S = cdetr_split_t
+# ---------------------------------------------------------------------------------------------
+_SIGS = {
+    "cdetr_bn_fold": "ppppfipp",
+    "cdetr_pack_weight": "piiipSS",
+    "cdetr_unpack_conv_grad": "piiip",
+    "cdetr_to_split": "plilS",
+    "cdetr_from_split": "Slipl",
+    "cdetr_stem_im2col": "piiiS",
+    "cdetr_im2col3x3": "SiiiiiiS",
+    "cdetr_col2im3x3": "SiiiiiiSS",
+    "cdetr_maxpool3x3s2": "SiiiiS",
+    "cdetr_subsample2": "SiiiiS",
+    "cdetr_upsample2_zero": "SiiiiS",
+    "cdetr_exemplar_concat": "SiiiipipS",
+    "cdetr_exemplar_concat_bwd": "SSpiiiipipSS",
+    "cdetr_groupnorm_fwd": "piiiippfpSp",
+    "cdetr_groupnorm_bwd": "ppiiiipppSpp",
+    "cdetr_layernorm_fwd": "pplippfppSp",
+    "cdetr_layernorm_bwd": "pppplippSpp",
+    "cdetr_sine_embed": "pliiiip",
+    "cdetr_sine_embed_bwd": "pliiiipp",
+    "cdetr_add_bcast": "ppliiiilpS",
+    "cdetr_reduce_axis": "piiiiifpipS",
+    "cdetr_combine_bcast": "ppppfpfliiip",
+    "cdetr_colsum": "pSllip",
+    "cdetr_box_head_fwd": "pplp",
+    "cdetr_box_head_bwd": "ppplpSp",
+    "cdetr_scale": "plf",
+    "cdetr_rcda_fwd": "iiiiiipppppppppS",
+    "cdetr_rcda_bwd": "iiiiiippppppppppSSSSS",
+    "cdetr_mha_fwd": "iiiippplSp",
+    "cdetr_mha_bwd": "iiiippplSpppSSS",
+    "cdetr_match_cost": "pipppiiifffp",
+    "cdetr_lsap": "ppiiipppp",
+    "cdetr_set_loss_fwd": "ppppppppiiiffppppppp",
+    "cdetr_set_loss_bwd": "pppppplppp",
+    "cdetr_bbox_loss_fwd": "ppplppp",
+    "cdetr_bbox_loss_bwd": "ppplp",
+}
+_CT = {"p": C.c_void_p, "i": C.c_int32, "l": C.c_int64, "f": C.c_float, "S": SplitT}
+_bound = {}
+
+
+def _bind(name):
+    fn = _bound.get(name)
+    if fn is None:
+        fn = getattr(lib(), name)
+        fn.argtypes = [_CT[c] for c in _SIGS[name]] + [C.c_void_p]
+        fn.restype = C.c_int
+        _bound[name] = fn
+    return fn
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point on torch's current stream; tensors become raw device pointers."""
+    sig = _SIGS[name]
+    assert len(args) == len(sig), (name, len(args), len(sig))
+    conv = []
+    for a, c in zip(args, sig):
+        if c == "p":
+            conv.append(None if a is None else (a.data_ptr() if isinstance(a, torch.Tensor) else a))
+        elif c == "S":
+            conv.append(a if isinstance(a, SplitT) else split_view(a))
+        elif c == "f":
+            conv.append(float(a))
+        else:
+            conv.append(int(a))
+    check(_bind(name)(*conv, torch.cuda.current_stream().cuda_stream), name)
+
+
+EXPORTED = ["cdetr_version", "cdetr_last_error", "cdetr_gemm"] + list(_SIGS)

@@ -1,0 +1,292 @@
+// Hungarian set matching on the device: per-image cost block + exact linear-sum-assignment.
+//
+//  cost (A2/models/matcher.py:221-242; box ops A2/util/box_ops.py:17-67): fp32, same operation order
+//  as the reference (explicit __f*_rn intrinsics so nvcc cannot contract into FMAs); only the diagonal
+//  [Q x T_b] block of each image is computed (the reference builds the full cross-batch matrix).
+//
+//  assignment (A2/models/matcher.py:243-247 -> scipy.optimize.linear_sum_assignment): one CTA per image
+//  runs scipy's shortest-augmenting-path solver (Crouse 2016) in fp64 with scipy's exact scan order,
+//  tie rule and output ordering (C restatement in oracle/lsap.c), so the indices are
+//  bit-identical to the reference's host call while removing the per-step D2H copy + host solve.
+//  The column scan of one step is spread over the CTA's threads and the arg-min is a lexicographic
+//  reduction on (value, assigned?, scan position) which reproduces the sequential tie rule.
+#include "common.cuh"
+#include "../../include/cdetr.h"
+#include <math.h>
+
+namespace {
+
+__device__ __forceinline__ float giou_rn(float ax0, float ay0, float ax1, float ay1, float bx0, float by0,
+                                         float bx1, float by1) {
+  const float area_a = __fmul_rn(__fsub_rn(ax1, ax0), __fsub_rn(ay1, ay0));
+  const float area_b = __fmul_rn(__fsub_rn(bx1, bx0), __fsub_rn(by1, by0));
+  const float iw = fmaxf(__fsub_rn(fminf(ax1, bx1), fmaxf(ax0, bx0)), 0.0f);
+  const float ih = fmaxf(__fsub_rn(fminf(ay1, by1), fmaxf(ay0, by0)), 0.0f);
+  const float inter = __fmul_rn(iw, ih);
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  const float iou = __fdiv_rn(inter, uni);
+  const float cw = fmaxf(__fsub_rn(fmaxf(ax1, bx1), fminf(ax0, bx0)), 0.0f);
+  const float ch = fmaxf(__fsub_rn(fmaxf(ay1, by1), fminf(ay0, by0)), 0.0f);
+  const float hull = __fmul_rn(cw, ch);
+  return __fsub_rn(iou, __fdiv_rn(__fsub_rn(hull, uni), hull));
+}
+
+// cost[b] is [T_b, Q] (transposed, when T_b < Q: rows of the LSAP = targets) or [Q, T_b] otherwise;
+// each image owns a slab of Q*Tmax floats.
+__global__ void match_cost_kernel(const float* __restrict__ logits, int num_logits,
+                                  const float* __restrict__ boxes, const float* __restrict__ tgt,
+                                  const int* __restrict__ tgt_off, int Q, int Tmax, float w_class,
+                                  float w_bbox, float w_giou, float* __restrict__ cost) {
+  const int b = blockIdx.y;
+  const int t0 = tgt_off[b], T = tgt_off[b + 1] - t0;
+  float* cb = cost + (int64_t)b * Q * Tmax;
+  const bool transposed = T < Q;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Q * T; i += gridDim.x * blockDim.x) {
+    // iterate with q fastest so that both the box reads and (transposed) cost writes coalesce
+    const int q = i % Q, t = i / Q;
+    const float x = logits[((int64_t)b * Q + q) * num_logits];
+    const float p = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+    const float neg = __fmul_rn(__fmul_rn(0.75f, __fmul_rn(p, p)),
+                                -logf(__fadd_rn(__fsub_rn(1.0f, p), 1e-8f)));
+    const float omp = __fsub_rn(1.0f, p);
+    const float pos = __fmul_rn(__fmul_rn(0.25f, __fmul_rn(omp, omp)), -logf(__fadd_rn(p, 1e-8f)));
+    const float c_class = __fsub_rn(pos, neg);
+    const float4 pb = *reinterpret_cast<const float4*>(boxes + ((int64_t)b * Q + q) * 4);
+    const float4 tb = *reinterpret_cast<const float4*>(tgt + (int64_t)(t0 + t) * 4);
+    float c_bbox = fabsf(__fsub_rn(pb.x, tb.x));
+    c_bbox = __fadd_rn(c_bbox, fabsf(__fsub_rn(pb.y, tb.y)));
+    c_bbox = __fadd_rn(c_bbox, fabsf(__fsub_rn(pb.z, tb.z)));
+    c_bbox = __fadd_rn(c_bbox, fabsf(__fsub_rn(pb.w, tb.w)));
+    const float hwp = __fmul_rn(0.5f, pb.z), hhp = __fmul_rn(0.5f, pb.w);
+    const float hwt = __fmul_rn(0.5f, tb.z), hht = __fmul_rn(0.5f, tb.w);
+    const float g = giou_rn(__fsub_rn(pb.x, hwp), __fsub_rn(pb.y, hhp), __fadd_rn(pb.x, hwp),
+                            __fadd_rn(pb.y, hhp), __fsub_rn(tb.x, hwt), __fsub_rn(tb.y, hht),
+                            __fadd_rn(tb.x, hwt), __fadd_rn(tb.y, hht));
+    const float c = __fadd_rn(__fadd_rn(__fmul_rn(w_bbox, c_bbox), __fmul_rn(w_class, c_class)),
+                              __fmul_rn(w_giou, -g));
+    if (transposed) cb[(int64_t)t * Q + q] = c; else cb[(int64_t)q * T + t] = c;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Key {  // lexicographic (val, pri, pos): smaller wins
+  double val;
+  int pri;  // 0: column unassigned (preferred among ties), 1: assigned
+  int pos;  // unassigned: -scan position (so the LAST wins); assigned: +scan position (FIRST wins)
+};
+__device__ __forceinline__ bool key_less(const Key& a, const Key& b) {
+  if (a.val != b.val) return a.val < b.val;
+  if (a.pri != b.pri) return a.pri < b.pri;
+  return a.pos < b.pos;
+}
+__device__ __forceinline__ Key key_shfl_xor(const Key& k, int o) {
+  Key r;
+  r.val = __shfl_xor_sync(0xffffffffu, k.val, o);
+  r.pri = __shfl_xor_sync(0xffffffffu, k.pri, o);
+  r.pos = __shfl_xor_sync(0xffffffffu, k.pos, o);
+  return r;
+}
+
+template <bool ONE_WARP>
+__device__ __forceinline__ void bsync() {
+  if (ONE_WARP) __syncwarp(); else __syncthreads();
+}
+
+// One CTA per image.  Shared layout (nr <= nc): u[nr] v[nc] spc[nc] (double) | path col4row row4col
+// remaining (int) | SR[nr] SC[nc] (uint8) | reduction scratch.
+template <bool ONE_WARP>
+__global__ void lsap_kernel(const float* __restrict__ cost_all, const int* __restrict__ tgt_off, int Q,
+                            int Tmax, int64_t* __restrict__ out_q, int64_t* __restrict__ out_t,
+                            int* __restrict__ out_n, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int b = blockIdx.x;
+  const int T = tgt_off[b + 1] - tgt_off[b];
+  const bool transposed = T < Q;  // rows = targets (scipy transposes iff nr > nc)
+  const int nr = transposed ? T : Q, nc = transposed ? Q : T;
+  const int ncap = max(Q, Tmax);
+  const float* cost = cost_all + (int64_t)b * Q * Tmax;  // [nr, nc] row-major
+  double* u = reinterpret_cast<double*>(smraw);
+  double* v = u + ncap;
+  double* spc = v + ncap;
+  int* path = reinterpret_cast<int*>(spc + ncap);
+  int* col4row = path + ncap;
+  int* row4col = col4row + ncap;
+  int* remaining = row4col + ncap;
+  unsigned char* SR = reinterpret_cast<unsigned char*>(remaining + ncap);
+  unsigned char* SC = SR + ncap;
+  Key* red = reinterpret_cast<Key*>(SC + ncap + ((16 - (2 * ncap) % 16) % 16));
+  __shared__ int s_i, s_sink, s_nrem, s_fail;
+  __shared__ double s_minval;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  int64_t* oq = out_q + (int64_t)b * min(Q, Tmax);
+  int64_t* ot = out_t + (int64_t)b * min(Q, Tmax);
+  if (nr == 0) {
+    if (tid == 0) out_n[b] = 0;
+    return;
+  }
+  for (int i = tid; i < nr; i += nt) { u[i] = 0.0; col4row[i] = -1; }
+  for (int j = tid; j < nc; j += nt) { v[j] = 0.0; row4col[j] = -1; }
+  if (tid == 0) s_fail = 0;
+  bsync<ONE_WARP>();
+
+  for (int cur = 0; cur < nr; ++cur) {
+    for (int j = tid; j < nc; j += nt) {
+      remaining[j] = nc - j - 1;  // reverse fill, as scipy
+      spc[j] = INFINITY;
+      SC[j] = 0;
+    }
+    for (int i = tid; i < nr; i += nt) SR[i] = 0;
+    if (tid == 0) { s_i = cur; s_sink = -1; s_nrem = nc; s_minval = 0.0; }
+    bsync<ONE_WARP>();
+    while (true) {
+      const int i = s_i;
+      const int nrem = s_nrem;
+      const double minval = s_minval;
+      const double ui = u[i];
+      const float* crow = cost + (int64_t)i * nc;
+      Key best;
+      best.val = INFINITY; best.pri = 2; best.pos = 0x7fffffff;
+      for (int it = tid; it < nrem; it += nt) {
+        const int j = remaining[it];
+        const double r = __dsub_rn(__dsub_rn(__dadd_rn(minval, (double)__ldg(crow + j)), ui), v[j]);
+        double sj = spc[j];
+        if (r < sj) {
+          sj = r;
+          spc[j] = r;
+          path[j] = i;
+        }
+        Key k;
+        k.val = sj;
+        const bool unassigned = row4col[j] == -1;
+        k.pri = unassigned ? 0 : 1;
+        k.pos = unassigned ? -it : it;
+        if (key_less(k, best)) best = k;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const Key other = key_shfl_xor(best, o);
+        if (key_less(other, best)) best = other;
+      }
+      if (!ONE_WARP) {
+        if (lane == 0) red[warp] = best;
+        __syncthreads();
+        if (warp == 0) {
+          Key k2;
+          k2.val = INFINITY; k2.pri = 2; k2.pos = 0x7fffffff;
+          if (lane < (nt >> 5)) k2 = red[lane];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const Key other = key_shfl_xor(k2, o);
+            if (key_less(other, k2)) k2 = other;
+          }
+          best = k2;
+        }
+      }
+      if (tid == 0) {
+        SR[i] = 1;
+        if (best.val == INFINITY) {  // infeasible (cannot happen for finite costs)
+          s_fail = 1;
+          s_sink = -2;
+        } else {
+          const int index = best.pri == 0 ? -best.pos : best.pos;
+          const int j = remaining[index];
+          s_minval = best.val;
+          if (row4col[j] == -1) s_sink = j; else s_i = row4col[j];
+          SC[j] = 1;
+          remaining[index] = remaining[nrem - 1];
+          s_nrem = nrem - 1;
+        }
+      }
+      bsync<ONE_WARP>();
+      if (s_sink != -1) break;
+    }
+    if (s_fail) break;
+    // dual update (scipy order of arithmetic), then augment along the alternating path
+    const double minval = s_minval;
+    for (int i = tid; i < nr; i += nt) {
+      if (i == cur) u[i] = __dadd_rn(u[i], minval);
+      else if (SR[i]) u[i] = __dadd_rn(u[i], __dsub_rn(minval, spc[col4row[i]]));
+    }
+    for (int j = tid; j < nc; j += nt)
+      if (SC[j]) v[j] = __dsub_rn(v[j], __dsub_rn(minval, spc[j]));
+    bsync<ONE_WARP>();
+    if (tid == 0) {
+      int j = s_sink;
+      while (true) {
+        const int i = path[j];
+        row4col[j] = i;
+        const int tmp = col4row[i];
+        col4row[i] = j;
+        j = tmp;
+        if (i == cur) break;
+      }
+    }
+    bsync<ONE_WARP>();
+  }
+  if (s_fail) {
+    if (tid == 0) { out_n[b] = 0; atomicExch(status, 1); }
+    return;
+  }
+  // output: (query, target) pairs with query ascending (scipy ordering, incl. the transposed case)
+  if (!transposed) {
+    for (int i = tid; i < nr; i += nt) { oq[i] = i; ot[i] = col4row[i]; }
+  } else {
+    for (int t = tid; t < nr; t += nt) {
+      const int q = col4row[t];
+      int rank = 0;
+      for (int t2 = 0; t2 < nr; ++t2) rank += col4row[t2] < q;
+      oq[rank] = q;
+      ot[rank] = t;
+    }
+  }
+  if (tid == 0) out_n[b] = nr;
+}
+
+size_t lsap_smem(int ncap, int nthreads) {
+  size_t s = 3 * sizeof(double) * ncap + 4 * sizeof(int) * ncap + 2 * (size_t)ncap;
+  s += (16 - (2 * ncap) % 16) % 16;
+  s += sizeof(Key) * 32;
+  (void)nthreads;
+  return s + 16;
+}
+
+}  // namespace
+
+extern "C" int cdetr_match_cost(const float* logits, int num_logits, const float* boxes, const float* tgt_boxes,
+                                const int* tgt_off, int B, int Q, int Tmax, float w_class, float w_bbox,
+                                float w_giou, float* cost, cdetr_stream_t s) {
+  CDETR_CHECK_ARG(logits && boxes && tgt_boxes && tgt_off && cost && B > 0 && Q > 0 && Tmax >= 0,
+                  "match_cost: bad args");
+  if (Tmax == 0) return 0;
+  dim3 grid(cdiv((int64_t)Q * Tmax, 256), B);
+  if (grid.x > 64) grid.x = 64;
+  match_cost_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(logits, num_logits, boxes, tgt_boxes,
+                                                                       tgt_off, Q, Tmax, w_class, w_bbox,
+                                                                       w_giou, cost);
+  CDETR_CHECK_LAUNCH();
+  return 0;
+}
+
+// out_q/out_t: [B, min(Q,Tmax)] int64 (first out_n[b] entries valid); status: device int set to 1 on failure.
+extern "C" int cdetr_lsap(const float* cost, const int* tgt_off, int B, int Q, int Tmax, int64_t* out_q,
+                          int64_t* out_t, int* out_n, int* status, cdetr_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  CDETR_CHECK_ARG(cost && tgt_off && out_q && out_t && out_n && status && B > 0 && Q > 0, "lsap: bad args");
+  const int ncap = Q > Tmax ? Q : Tmax;
+  if (ncap <= 384) {
+    const size_t smem = lsap_smem(ncap, 32);
+    lsap_kernel<true><<<B, 32, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status);
+  } else {
+    int nt = 256;
+    if (ncap > 768) nt = 512;
+    if (ncap > 2048) nt = 1024;
+    const size_t smem = lsap_smem(ncap, nt);
+    CDETR_CHECK_ARG(smem <= 200 * 1024, "lsap: problem too large for shared memory (n=%d)", ncap);
+    CDETR_CHECK_CUDA(cudaFuncSetAttribute(lsap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
+    lsap_kernel<false><<<B, nt, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status);
+  }
+  CDETR_CHECK_LAUNCH();
+  return 0;
+}

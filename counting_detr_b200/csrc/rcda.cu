@@ -1,0 +1,432 @@
+// Row/column-decoupled attention core (AnchorDETR RCDA), forward and hand-written backward.
+//   A_r = softmax_w(s * q_r K_r^T)  [L,W]     A_c = softmax_h(s * q_c K_c^T)  [L,H]      (s = d^-1/2)
+//   O[q,:] = sum_h sum_w A_c[q,h] A_r[q,w] V[h,w,:]
+// per (sample, head), head dim d = 32.  The reference materialises a [B*heads, L, W, d] intermediate
+// (537 MB per encoder layer at B=16, 512x512) and keeps it for autograd; here the contraction is fused
+// with the two softmaxes, the intermediate never exists, and backward recomputes from A_r/A_c.
+// Reference: A2/models/row_column_decoupled_attention.py:210-291 (core), backward derived in
+// SURVEY.md §8a-4.  Attention maps are stored transposed ([B,heads,W,L] / [B,heads,H,L]) so that
+// per-query threads read/write them coalesced.
+//
+// Round-1 kernels run the contraction on the fp32 FMA pipe (V tile staged in shared memory and
+// broadcast to one-query-per-thread accumulators); the tcgen05 formulation is the next step.
+#include "common.cuh"
+#include "../../include/cdetr.h"
+
+namespace {
+
+constexpr int HD = 32;  // head dim
+
+struct RcdaArgs {
+  int B, L, H, W, E, nh;
+  int Hc;  // V rows per shared-memory chunk
+  const float* qr;  // [B,L,E] projected (bias added, unscaled)
+  const float* qc;
+  const float* kr;  // [B,W,E]
+  const float* kc;  // [B,H,E]
+  const float* v;   // [B,H,W,E]
+  const uint8_t* mask_row;  // [B,W] or null (1 = padded)
+  const uint8_t* mask_col;  // [B,H] or null
+  float* ar;  // [B,nh,W,L]
+  float* ac;  // [B,nh,H,L]
+  __nv_bfloat16* o_hi;  // [B,L,E] split
+  __nv_bfloat16* o_lo;
+  int64_t ld_o;
+  // backward
+  const float* d_o;  // [B,L,E]
+  float* dsr;        // [B,nh,W,L]
+  float* dsc;        // [B,nh,H,L]
+  __nv_bfloat16 *dqr_hi, *dqr_lo, *dqc_hi, *dqc_lo;  // [B,L,E] split
+  __nv_bfloat16 *dkr_hi, *dkr_lo, *dkc_hi, *dkc_lo;  // [B,W,E], [B,H,E] split
+  __nv_bfloat16 *dv_hi, *dv_lo;                      // [B,H,W,E] split
+  int64_t ld_g;  // ld of all gradient split tensors (E)
+};
+
+__device__ __forceinline__ void store_split32(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[g * 8 + 2 * j], h0, l0);
+      split_bf16(v[g * 8 + 2 * j + 1], h1, l1);
+      hw[j] = pack_bf16x2(h0, h1);
+      lw[j] = pack_bf16x2(l0, l1);
+    }
+    reinterpret_cast<uint4*>(hi)[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    reinterpret_cast<uint4*>(lo)[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
+__device__ __forceinline__ void load32(const float* p, float* v) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + j);
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
+
+// one softmax over `n` keys for this thread's query; logits written to s_col[k*T + tid] then normalised
+__device__ __forceinline__ void thread_softmax(const float* q, const float* Ks, int n,
+                                               const uint8_t* mask, float* s_col, int T, int tid) {
+  float mx = -INFINITY;
+  for (int k = 0; k < n; ++k) {
+    float s = 0.0f;
+    const float4* kp = reinterpret_cast<const float4*>(Ks + k * HD);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = kp[j];
+      s += q[4 * j] * t.x + q[4 * j + 1] * t.y + q[4 * j + 2] * t.z + q[4 * j + 3] * t.w;
+    }
+    if (mask && mask[k]) s = -INFINITY;
+    s_col[k * T + tid] = s;
+    mx = fmaxf(mx, s);
+  }
+  float sum = 0.0f;
+  for (int k = 0; k < n; ++k) {
+    const float e = expf(s_col[k * T + tid] - mx);
+    s_col[k * T + tid] = e;
+    sum += e;
+  }
+  const float inv = 1.0f / sum;
+  for (int k = 0; k < n; ++k) s_col[k * T + tid] *= inv;
+}
+
+__device__ __forceinline__ void load_v_chunk(const RcdaArgs& a, int b, int head, int h0, int hc, float* Vs) {
+  const int n4 = hc * a.W * 8;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    const int pos = i >> 3, c4 = i & 7;
+    const int h = h0 + pos / a.W, w = pos % a.W;
+    const float4 t = __ldg(reinterpret_cast<const float4*>(
+        a.v + (((int64_t)b * a.H + h) * a.W + w) * a.E + head * HD + c4 * 4));
+    reinterpret_cast<float4*>(Vs)[i] = t;
+  }
+}
+
+// ------------------------------------------------------------------ forward: grid (ceil(L/T), nh, B)
+__global__ void rcda_fwd_kernel(const RcdaArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int head = blockIdx.y, b = blockIdx.z;
+  float* Ksr = sm;                       // [W][32]
+  float* Ksc = Ksr + a.W * HD;           // [H][32]
+  float* ars = Ksc + a.H * HD;           // [W][T]
+  float* acs = ars + a.W * T;            // [H][T]
+  float* Vs = acs + a.H * T;             // [Hc*W][32]
+  for (int i = tid; i < a.W * HD; i += T)
+    Ksr[i] = a.kr[((int64_t)b * a.W + i / HD) * a.E + head * HD + (i % HD)];
+  for (int i = tid; i < a.H * HD; i += T)
+    Ksc[i] = a.kc[((int64_t)b * a.H + i / HD) * a.E + head * HD + (i % HD)];
+  __syncthreads();
+  const int q = blockIdx.x * T + tid;
+  const bool ok = q < a.L;
+  const float scale = rsqrtf((float)HD);
+  {
+    float qv[HD];
+    if (ok) {
+      load32(a.qr + ((int64_t)b * a.L + q) * a.E + head * HD, qv);
+#pragma unroll
+      for (int j = 0; j < HD; ++j) qv[j] *= scale;
+      thread_softmax(qv, Ksr, a.W, a.mask_row ? a.mask_row + (int64_t)b * a.W : nullptr, ars, T, tid);
+      load32(a.qc + ((int64_t)b * a.L + q) * a.E + head * HD, qv);
+#pragma unroll
+      for (int j = 0; j < HD; ++j) qv[j] *= scale;
+      thread_softmax(qv, Ksc, a.H, a.mask_col ? a.mask_col + (int64_t)b * a.H : nullptr, acs, T, tid);
+      const int64_t bh = (int64_t)b * a.nh + head;
+      for (int w = 0; w < a.W; ++w) a.ar[(bh * a.W + w) * a.L + q] = ars[w * T + tid];
+      for (int h = 0; h < a.H; ++h) a.ac[(bh * a.H + h) * a.L + q] = acs[h * T + tid];
+    } else {
+      for (int w = 0; w < a.W; ++w) ars[w * T + tid] = 0.0f;
+      for (int h = 0; h < a.H; ++h) acs[h * T + tid] = 0.0f;
+    }
+  }
+  float acc[HD];
+#pragma unroll
+  for (int j = 0; j < HD; ++j) acc[j] = 0.0f;
+  for (int h0 = 0; h0 < a.H; h0 += a.Hc) {
+    const int hc = min(a.Hc, a.H - h0);
+    __syncthreads();
+    load_v_chunk(a, b, head, h0, hc, Vs);
+    __syncthreads();
+    for (int hh = 0; hh < hc; ++hh) {
+      const float cc = acs[(h0 + hh) * T + tid];
+      for (int w = 0; w < a.W; ++w) {
+        const float coef = cc * ars[w * T + tid];
+        const float4* vp = reinterpret_cast<const float4*>(Vs + (hh * a.W + w) * HD);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 t = vp[j];
+          acc[4 * j] += coef * t.x; acc[4 * j + 1] += coef * t.y;
+          acc[4 * j + 2] += coef * t.z; acc[4 * j + 3] += coef * t.w;
+        }
+      }
+    }
+  }
+  if (ok) {
+    const int64_t off = ((int64_t)b * a.L + q) * a.ld_o + head * HD;
+    store_split32(a.o_hi + off, a.o_lo + off, acc);
+  }
+}
+
+// ------------------------------------------------------------------ backward 1 (per query): dA -> dS -> dq
+__global__ void rcda_bwd_q_kernel(const RcdaArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int head = blockIdx.y, b = blockIdx.z;
+  float* Ksr = sm;
+  float* Ksc = Ksr + a.W * HD;
+  float* ars = Ksc + a.H * HD;   // [W][T]
+  float* acs = ars + a.W * T;    // [H][T]
+  float* dar = acs + a.H * T;    // [W][T]
+  float* dac = dar + a.W * T;    // [H][T]
+  float* Vs = dac + a.H * T;
+  for (int i = tid; i < a.W * HD; i += T)
+    Ksr[i] = a.kr[((int64_t)b * a.W + i / HD) * a.E + head * HD + (i % HD)];
+  for (int i = tid; i < a.H * HD; i += T)
+    Ksc[i] = a.kc[((int64_t)b * a.H + i / HD) * a.E + head * HD + (i % HD)];
+  const int q = blockIdx.x * T + tid;
+  const bool ok = q < a.L;
+  const int64_t bh = (int64_t)b * a.nh + head;
+  float dov[HD];
+  if (ok) {
+    load32(a.d_o + ((int64_t)b * a.L + q) * a.E + head * HD, dov);
+    for (int w = 0; w < a.W; ++w) ars[w * T + tid] = a.ar[(bh * a.W + w) * a.L + q];
+    for (int h = 0; h < a.H; ++h) acs[h * T + tid] = a.ac[(bh * a.H + h) * a.L + q];
+  } else {
+#pragma unroll
+    for (int j = 0; j < HD; ++j) dov[j] = 0.0f;
+    for (int w = 0; w < a.W; ++w) ars[w * T + tid] = 0.0f;
+    for (int h = 0; h < a.H; ++h) acs[h * T + tid] = 0.0f;
+  }
+  for (int w = 0; w < a.W; ++w) dar[w * T + tid] = 0.0f;
+  for (int h0 = 0; h0 < a.H; h0 += a.Hc) {
+    const int hc = min(a.Hc, a.H - h0);
+    __syncthreads();
+    load_v_chunk(a, b, head, h0, hc, Vs);
+    __syncthreads();
+    for (int hh = 0; hh < hc; ++hh) {
+      const float cc = acs[(h0 + hh) * T + tid];
+      float dcc = 0.0f;
+      for (int w = 0; w < a.W; ++w) {
+        const float4* vp = reinterpret_cast<const float4*>(Vs + (hh * a.W + w) * HD);
+        float g0 = 0.0f, g1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float4 t = vp[j];
+          const float4 u = vp[j + 1];
+          g0 += dov[4 * j] * t.x + dov[4 * j + 1] * t.y + dov[4 * j + 2] * t.z + dov[4 * j + 3] * t.w;
+          g1 += dov[4 * j + 4] * u.x + dov[4 * j + 5] * u.y + dov[4 * j + 6] * u.z + dov[4 * j + 7] * u.w;
+        }
+        const float g = g0 + g1;
+        dcc += ars[w * T + tid] * g;
+        dar[w * T + tid] += cc * g;
+      }
+      dac[(h0 + hh) * T + tid] = dcc;
+    }
+  }
+  if (!ok) return;
+  const float scale = rsqrtf((float)HD);
+  // softmax backward + dq, row then column
+  {
+    float dot = 0.0f;
+    for (int w = 0; w < a.W; ++w) dot += ars[w * T + tid] * dar[w * T + tid];
+    float dq[HD];
+#pragma unroll
+    for (int j = 0; j < HD; ++j) dq[j] = 0.0f;
+    for (int w = 0; w < a.W; ++w) {
+      const float ds = ars[w * T + tid] * (dar[w * T + tid] - dot);
+      a.dsr[(bh * a.W + w) * a.L + q] = ds;
+      const float4* kp = reinterpret_cast<const float4*>(Ksr + w * HD);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = kp[j];
+        dq[4 * j] += ds * t.x; dq[4 * j + 1] += ds * t.y; dq[4 * j + 2] += ds * t.z; dq[4 * j + 3] += ds * t.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < HD; ++j) dq[j] *= scale;
+    const int64_t off = ((int64_t)b * a.L + q) * a.ld_g + head * HD;
+    store_split32(a.dqr_hi + off, a.dqr_lo + off, dq);
+  }
+  {
+    float dot = 0.0f;
+    for (int h = 0; h < a.H; ++h) dot += acs[h * T + tid] * dac[h * T + tid];
+    float dq[HD];
+#pragma unroll
+    for (int j = 0; j < HD; ++j) dq[j] = 0.0f;
+    for (int h = 0; h < a.H; ++h) {
+      const float ds = acs[h * T + tid] * (dac[h * T + tid] - dot);
+      a.dsc[(bh * a.H + h) * a.L + q] = ds;
+      const float4* kp = reinterpret_cast<const float4*>(Ksc + h * HD);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = kp[j];
+        dq[4 * j] += ds * t.x; dq[4 * j + 1] += ds * t.y; dq[4 * j + 2] += ds * t.z; dq[4 * j + 3] += ds * t.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < HD; ++j) dq[j] *= scale;
+    const int64_t off = ((int64_t)b * a.L + q) * a.ld_g + head * HD;
+    store_split32(a.dqc_hi + off, a.dqc_lo + off, dq);
+  }
+}
+
+// ------------------------------------------------------------------ backward 2 (per key position): dV
+// dV[h,w,:] = sum_q A_c[q,h] A_r[q,w] dO[q,:];  grid (ceil(HW/T), nh, B); queries staged in tiles of TQ.
+constexpr int TQ = 64;
+__global__ void rcda_bwd_v_kernel(const RcdaArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int head = blockIdx.y, b = blockIdx.z;
+  float* dos = sm;                          // [TQ][32]
+  float* ars = dos + TQ * HD;               // [W][TQ+1]
+  float* acs = ars + a.W * (TQ + 1);        // [H][TQ+1]
+  const int p = blockIdx.x * T + tid;
+  const bool ok = p < a.H * a.W;
+  const int h = ok ? p / a.W : 0, w = ok ? p % a.W : 0;
+  const int64_t bh = (int64_t)b * a.nh + head;
+  float acc[HD];
+#pragma unroll
+  for (int j = 0; j < HD; ++j) acc[j] = 0.0f;
+  for (int q0 = 0; q0 < a.L; q0 += TQ) {
+    const int nq = min(TQ, a.L - q0);
+    __syncthreads();
+    for (int i = tid; i < TQ * 8; i += T) {
+      const int qq = i >> 3, c4 = i & 7;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (qq < nq)
+        t = __ldg(reinterpret_cast<const float4*>(a.d_o + ((int64_t)b * a.L + q0 + qq) * a.E + head * HD + c4 * 4));
+      reinterpret_cast<float4*>(dos)[i] = t;
+    }
+    for (int i = tid; i < a.W * TQ; i += T) {
+      const int ww = i / TQ, qq = i % TQ;
+      ars[ww * (TQ + 1) + qq] = qq < nq ? a.ar[(bh * a.W + ww) * a.L + q0 + qq] : 0.0f;
+    }
+    for (int i = tid; i < a.H * TQ; i += T) {
+      const int hh = i / TQ, qq = i % TQ;
+      acs[hh * (TQ + 1) + qq] = qq < nq ? a.ac[(bh * a.H + hh) * a.L + q0 + qq] : 0.0f;
+    }
+    __syncthreads();
+    for (int qq = 0; qq < nq; ++qq) {
+      const float coef = acs[h * (TQ + 1) + qq] * ars[w * (TQ + 1) + qq];
+      const float4* dp = reinterpret_cast<const float4*>(dos + qq * HD);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = dp[j];
+        acc[4 * j] += coef * t.x; acc[4 * j + 1] += coef * t.y;
+        acc[4 * j + 2] += coef * t.z; acc[4 * j + 3] += coef * t.w;
+      }
+    }
+  }
+  if (ok) {
+    const int64_t off = (((int64_t)b * a.H + h) * a.W + w) * a.ld_g + head * HD;
+    store_split32(a.dv_hi + off, a.dv_lo + off, acc);
+  }
+}
+
+// ------------------------------------------------------------------ backward 3: dK_r / dK_c
+// dK[k,d] = s * sum_q dS[k,q] * q[q,d];  grid (nh, B, 2), block (32, 32): threadIdx.x = d, y strides keys.
+__global__ void rcda_bwd_k_kernel(const RcdaArgs a) {
+  const int head = blockIdx.x, b = blockIdx.y, which = blockIdx.z;
+  const int n = which == 0 ? a.W : a.H;
+  const float* ds = which == 0 ? a.dsr : a.dsc;
+  const float* qp = which == 0 ? a.qr : a.qc;
+  __nv_bfloat16* ohi = which == 0 ? a.dkr_hi : a.dkc_hi;
+  __nv_bfloat16* olo = which == 0 ? a.dkr_lo : a.dkc_lo;
+  const int64_t bh = (int64_t)b * a.nh + head;
+  const int d = threadIdx.x;
+  const float scale = rsqrtf((float)HD);
+  for (int k = threadIdx.y; k < n; k += blockDim.y) {
+    const float* dsk = ds + (bh * n + k) * a.L;
+    float acc0 = 0.0f, acc1 = 0.0f;
+    int q = 0;
+    for (; q + 1 < a.L; q += 2) {
+      acc0 += __ldg(dsk + q) * __ldg(qp + ((int64_t)b * a.L + q) * a.E + head * HD + d);
+      acc1 += __ldg(dsk + q + 1) * __ldg(qp + ((int64_t)b * a.L + q + 1) * a.E + head * HD + d);
+    }
+    if (q < a.L) acc0 += __ldg(dsk + q) * __ldg(qp + ((int64_t)b * a.L + q) * a.E + head * HD + d);
+    const int64_t off = ((int64_t)b * n + k) * a.ld_g + head * HD + d;
+    split_bf16((acc0 + acc1) * scale, ohi[off], olo[off]);
+  }
+}
+
+size_t fwd_smem(int H, int W, int T, int Hc) {
+  return sizeof(float) * ((size_t)(W + H) * HD + (size_t)(W + H) * T + (size_t)Hc * W * HD);
+}
+size_t bwdq_smem(int H, int W, int T, int Hc) {
+  return sizeof(float) * ((size_t)(W + H) * HD + 2 * (size_t)(W + H) * T + (size_t)Hc * W * HD);
+}
+
+}  // namespace
+
+// C-ABI descriptor mirrors RcdaArgs with split views.
+extern "C" int cdetr_rcda_fwd(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc,
+                              const float* kr, const float* kc, const float* v, const uint8_t* mask_row,
+                              const uint8_t* mask_col, float* ar, float* ac, cdetr_split_t o,
+                              cdetr_stream_t s) {
+  CDETR_CHECK_ARG(E == nh * HD, "rcda_fwd: head dim must be 32 (E=%d nh=%d)", E, nh);
+  CDETR_CHECK_ARG(qr && qc && kr && kc && v && ar && ac && o.base, "rcda_fwd: null pointer");
+  RcdaArgs a = {};
+  a.B = B; a.L = L; a.H = H; a.W = W; a.E = E; a.nh = nh;
+  a.qr = qr; a.qc = qc; a.kr = kr; a.kc = kc; a.v = v; a.mask_row = mask_row; a.mask_col = mask_col;
+  a.ar = ar; a.ac = ac;
+  a.o_hi = reinterpret_cast<__nv_bfloat16*>(o.base); a.o_lo = a.o_hi + o.plane; a.ld_o = o.ld;
+  const size_t budget = 220 * 1024;
+  int T = 256;
+  while (T > 32 && fwd_smem(H, W, T, 1) > budget) T >>= 1;
+  int Hc = H;
+  while (Hc > 1 && fwd_smem(H, W, T, Hc) > budget) --Hc;
+  CDETR_CHECK_ARG(fwd_smem(H, W, T, Hc) <= budget, "rcda_fwd: H=%d W=%d do not fit shared memory", H, W);
+  a.Hc = Hc;
+  const size_t smem = fwd_smem(H, W, T, Hc);
+  CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  dim3 grid(cdiv(L, T), nh, B);
+  rcda_fwd_kernel<<<grid, T, smem, reinterpret_cast<cudaStream_t>(s)>>>(a);
+  CDETR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cdetr_rcda_bwd(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc,
+                              const float* kr, const float* kc, const float* v, const float* ar,
+                              const float* ac, const float* d_o, float* dsr, float* dsc, cdetr_split_t dqr,
+                              cdetr_split_t dqc, cdetr_split_t dkr, cdetr_split_t dkc, cdetr_split_t dv,
+                              cdetr_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  CDETR_CHECK_ARG(E == nh * HD, "rcda_bwd: head dim must be 32");
+  CDETR_CHECK_ARG(qr && qc && kr && kc && v && ar && ac && d_o && dsr && dsc && dqr.base && dqc.base &&
+                      dkr.base && dkc.base && dv.base,
+                  "rcda_bwd: null pointer");
+  CDETR_CHECK_ARG(dqr.ld == dqc.ld && dqr.ld == dkr.ld && dqr.ld == dkc.ld && dqr.ld == dv.ld,
+                  "rcda_bwd: gradient tensors must share ld");
+  RcdaArgs a = {};
+  a.B = B; a.L = L; a.H = H; a.W = W; a.E = E; a.nh = nh;
+  a.qr = qr; a.qc = qc; a.kr = kr; a.kc = kc; a.v = v;
+  a.ar = const_cast<float*>(ar); a.ac = const_cast<float*>(ac);
+  a.d_o = d_o; a.dsr = dsr; a.dsc = dsc;
+  auto hi = [](cdetr_split_t t) { return reinterpret_cast<__nv_bfloat16*>(t.base); };
+  a.dqr_hi = hi(dqr); a.dqr_lo = hi(dqr) + dqr.plane;
+  a.dqc_hi = hi(dqc); a.dqc_lo = hi(dqc) + dqc.plane;
+  a.dkr_hi = hi(dkr); a.dkr_lo = hi(dkr) + dkr.plane;
+  a.dkc_hi = hi(dkc); a.dkc_lo = hi(dkc) + dkc.plane;
+  a.dv_hi = hi(dv); a.dv_lo = hi(dv) + dv.plane;
+  a.ld_g = dqr.ld;
+  const size_t budget = 220 * 1024;
+  int T = 256;
+  while (T > 32 && bwdq_smem(H, W, T, 1) > budget) T >>= 1;
+  int Hc = H;
+  while (Hc > 1 && bwdq_smem(H, W, T, Hc) > budget) --Hc;
+  CDETR_CHECK_ARG(bwdq_smem(H, W, T, Hc) <= budget, "rcda_bwd: H=%d W=%d do not fit shared memory", H, W);
+  a.Hc = Hc;
+  CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  rcda_bwd_q_kernel<<<dim3(cdiv(L, T), nh, B), T, bwdq_smem(H, W, T, Hc), s>>>(a);
+  CDETR_CHECK_LAUNCH();
+  const int TV = 256;
+  const size_t smem_v = sizeof(float) * ((size_t)TQ * HD + (size_t)(W + H) * (TQ + 1));
+  CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  rcda_bwd_v_kernel<<<dim3(cdiv(H * W, TV), nh, B), TV, smem_v, s>>>(a);
+  CDETR_CHECK_LAUNCH();
+  rcda_bwd_k_kernel<<<dim3(nh, B, 2), dim3(32, 32), 0, s>>>(a);
+  CDETR_CHECK_LAUNCH();
+  return 0;
+}

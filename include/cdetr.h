@@ -71,6 +71,117 @@ typedef struct {
 
 int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Backbone layout kernels (split-bf16 NHWC).  Replace, together with cdetr_gemm:
+ *   A2/models/backbone.py:50-60 (FrozenBatchNorm2d -> folded scale/shift),
+ *   A2/models/resnet.py:143-158 (Bottleneck convs), :263-271 (stem conv + max-pool).
+ * --------------------------------------------------------------------------------------------- */
+int cdetr_bn_fold(const float* w, const float* b, const float* rm, const float* rv, float eps, int c,
+                  float* scale, float* shift, cdetr_stream_t s);
+/* w [cout, cin, taps] fp32 -> dst [cout, taps*cin] and/or dst_t [taps*cin, cout] (row_scale folded) */
+int cdetr_pack_weight(const float* w, int cout, int cin, int taps, const float* row_scale,
+                      cdetr_split_t dst, cdetr_split_t dst_t, cdetr_stream_t s);
+/* grad [cout, cin, taps] += g [cout, taps*cin] */
+int cdetr_unpack_conv_grad(const float* g, int cout, int cin, int taps, float* grad, cdetr_stream_t s);
+int cdetr_to_split(const float* x, int64_t rows, int cols, int64_t ld_x, cdetr_split_t dst, cdetr_stream_t s);
+int cdetr_from_split(cdetr_split_t src, int64_t rows, int cols, float* y, int64_t ld_y, cdetr_stream_t s);
+int cdetr_stem_im2col(const float* img_nchw, int B, int H, int W, cdetr_split_t col, cdetr_stream_t s);
+int cdetr_im2col3x3(cdetr_split_t x, int B, int H, int W, int C, int stride, int dil, cdetr_split_t col,
+                    cdetr_stream_t s);
+int cdetr_col2im3x3(cdetr_split_t dcol, int B, int H, int W, int C, int stride, int dil, cdetr_split_t mask,
+                    cdetr_split_t dx, cdetr_stream_t s);
+int cdetr_maxpool3x3s2(cdetr_split_t x, int B, int H, int W, int C, cdetr_split_t y, cdetr_stream_t s);
+int cdetr_subsample2(cdetr_split_t x, int B, int H, int W, int C, cdetr_split_t y, cdetr_stream_t s);
+int cdetr_upsample2_zero(cdetr_split_t dy, int B, int H, int W, int C, cdetr_split_t dx, cdetr_stream_t s);
+
+/* Exemplar feature injection, A2/models/backbone.py:116-136: cat = [x | x * p_b], p_b = mean of x at the
+ * exemplar centres (yx int32 [n_ex, 2], taken from sample 0's rects by the caller, reference quirk). */
+int cdetr_exemplar_concat(cdetr_split_t x, int B, int H, int W, int C, const int* centres_yx, int n_ex,
+                          float* p_out, cdetr_split_t cat, cdetr_stream_t s);
+int cdetr_exemplar_concat_bwd(cdetr_split_t dcat, cdetr_split_t x, const float* p, int B, int H, int W, int C,
+                              const int* centres_yx, int n_ex, float* dp_scratch, cdetr_split_t mask,
+                              cdetr_split_t dx, cdetr_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * Norms: A2/models/anchor_detr.py:81,119 (GroupNorm 32x8), A2/models/transformer.py:233-426 (LayerNorm).
+ * --------------------------------------------------------------------------------------------- */
+int cdetr_groupnorm_fwd(const float* x, int B, int N, int C, int G, const float* gamma, const float* beta,
+                        float eps, float* y, cdetr_split_t y_split, float* stats, cdetr_stream_t s);
+int cdetr_groupnorm_bwd(const float* dy, const float* x, int B, int N, int C, int G, const float* gamma,
+                        const float* stats, float* dx, cdetr_split_t dx_split, float* dgamma, float* dbeta,
+                        cdetr_stream_t s);
+int cdetr_layernorm_fwd(const float* x, const float* res, int64_t M, int C, const float* gamma,
+                        const float* beta, float eps, float* z_out, float* y, cdetr_split_t y_split,
+                        float* stats, cdetr_stream_t s);
+int cdetr_layernorm_bwd(const float* dy, const float* dy2, const float* z, const float* stats, int64_t M, int C,
+                        const float* gamma, float* dz, cdetr_split_t dz_split, float* dgamma, float* dbeta,
+                        cdetr_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * Transformer glue: A2/models/transformer.py:474-503 (sine embeddings, mask2pos), :248-256,:378-392
+ * (position broadcasts), A2/models/row_column_decoupled_attention.py:212-213 (key means),
+ * A2/models/transformer.py:193-202 + A2/util/misc.py:475-479 (box head).
+ * --------------------------------------------------------------------------------------------- */
+int cdetr_sine_embed(const float* pos, int64_t n, int pos_stride, int num_feats, int off, int ld, float* out,
+                     cdetr_stream_t s);
+int cdetr_sine_embed_bwd(const float* pos, int64_t n, int pos_stride, int num_feats, int off, int ld,
+                         const float* demb, float* dpos, cdetr_stream_t s);
+int cdetr_add_bcast(const float* x, const float* y, int64_t M, int E, int mode, int H, int W, int64_t rows_y,
+                    float* out, cdetr_split_t out_split, cdetr_stream_t s);
+int cdetr_reduce_axis(const float* x, int B, int H, int W, int E, int axis, float scale, const float* add,
+                      int accumulate, float* out, cdetr_split_t out_split, cdetr_stream_t s);
+int cdetr_combine_bcast(const float* a, const float* b, const float* c, const float* row, float sr,
+                        const float* col, float sc, int64_t M, int E, int H, int W, float* out, cdetr_stream_t s);
+int cdetr_colsum(const float* x, cdetr_split_t x_split, int64_t ld, int64_t M, int N, float* out, cdetr_stream_t s);
+int cdetr_box_head_fwd(const float* t, const float* ref, int64_t M, float* boxes, cdetr_stream_t s);
+int cdetr_box_head_bwd(const float* dboxes, const float* boxes, const float* ref, int64_t M, float* dt,
+                       cdetr_split_t dt_split, float* dref, cdetr_stream_t s);
+int cdetr_scale(float* x, int64_t n, float a, cdetr_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention cores.  RCDA: A2/models/row_column_decoupled_attention.py:210-291 (q scaling, row/col logits,
+ * padding masks, two softmaxes, decoupled contraction); attention maps stored transposed
+ * ([B,heads,W,L], [B,heads,H,L]).  MHA: decoder self-attention, A2/models/transformer.py:366-372.
+ * --------------------------------------------------------------------------------------------- */
+int cdetr_rcda_fwd(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc, const float* kr,
+                   const float* kc, const float* v, const uint8_t* mask_row, const uint8_t* mask_col, float* ar,
+                   float* ac, cdetr_split_t o, cdetr_stream_t s);
+int cdetr_rcda_bwd(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc, const float* kr,
+                   const float* kc, const float* v, const float* ar, const float* ac, const float* d_o,
+                   float* dsr, float* dsc, cdetr_split_t dqr, cdetr_split_t dqc, cdetr_split_t dkr,
+                   cdetr_split_t dkc, cdetr_split_t dv, cdetr_stream_t s);
+int cdetr_mha_fwd(int B, int L, int E, int nh, const float* q, const float* k, const float* v, int64_t ldq,
+                  cdetr_split_t o, float* lse, cdetr_stream_t s);
+int cdetr_mha_bwd(int B, int L, int E, int nh, const float* q, const float* k, const float* v, int64_t ldq,
+                  cdetr_split_t o, const float* lse, const float* d_o, float* dsum, cdetr_split_t dq,
+                  cdetr_split_t dk, cdetr_split_t dv, cdetr_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * Matcher + criterion.  A2/models/matcher.py:221-247 (cost + scipy linear_sum_assignment per image),
+ * A2/models/anchor_detr.py:166-289 (SetCriterion losses), A1/models/anchor_detr.py:317-337.
+ * tgt_off: int32 [B+1] prefix offsets into the concatenated target boxes [sum T, 4] (cxcywh).
+ * cost: B slabs of Q*Tmax floats, each [T_b, Q] when T_b < Q (LSAP rows = targets) else [Q, T_b].
+ * out_q/out_t: int64 [B, min(Q,Tmax)], first out_n[b] valid, query index ascending (scipy order).
+ * --------------------------------------------------------------------------------------------- */
+int cdetr_match_cost(const float* logits, int num_logits, const float* boxes, const float* tgt_boxes,
+                     const int* tgt_off, int B, int Q, int Tmax, float w_class, float w_bbox, float w_giou,
+                     float* cost, cdetr_stream_t s);
+int cdetr_lsap(const float* cost, const int* tgt_off, int B, int Q, int Tmax, int64_t* out_q, int64_t* out_t,
+               int* out_n, int* status, cdetr_stream_t s);
+/* out6 = loss_ce, class_error, loss_bbox, loss_giou, cardinality_error, loss_variance */
+int cdetr_set_loss_fwd(const float* logits, const float* boxes, const float* vars, const float* tgt_boxes,
+                       const int* tgt_off, const int64_t* idx_q, const int64_t* idx_t, const int* idx_n, int B,
+                       int Q, int Kmax, float num_boxes, float focal_alpha, float* out6, float* g_ce,
+                       float* g_bbox, float* g_giou, float* g_var_box, float* g_var_var, unsigned char* matched,
+                       cdetr_stream_t s);
+int cdetr_set_loss_bwd(const float* upstream4, const float* g_ce, const float* g_bbox, const float* g_giou,
+                       const float* g_var_box, const float* g_var_var, int64_t rows, float* d_logits,
+                       float* d_boxes, float* d_vars, cdetr_stream_t s);
+int cdetr_bbox_loss_fwd(const float* pred_wh, const float* points, const float* whs, int64_t n, float* out2,
+                        float* g_wh, float* g_giou, cdetr_stream_t s);
+int cdetr_bbox_loss_bwd(const float* upstream2, const float* g_wh, const float* g_giou, int64_t n, float* d_wh,
+                        cdetr_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif
