@@ -1,0 +1,764 @@
+"""Host-side sequencing of the sm_100a kernels for one forward / backward of the Counting-DETR hot path.
+
+The engine owns no math: every tensor op is a C-ABI call into libcdetr_sm100a.so (counting_detr_b200._lib);
+torch is used for device memory and streams only.  All intermediate buffers are allocated once per shape
+and reused at fixed addresses, and no call synchronises or reads device data on the host, so a whole
+train step can be captured in a CUDA graph.
+
+Layout: activations are channels-last rows ([B*H*W, C] / [B*L, E]); GEMM operands are split-bf16
+([2, rows, ld]); residual streams, norm statistics and attention maps are fp32.
+
+Reference call sites: AnchorDETR.forward (A2/models/anchor_detr.py:94-133, A1 :80-113), ResNet/Bottleneck
+(A2/models/resnet.py:140-160,261-271), BackboneAgg.extract_feature (A2/models/backbone.py:116-145),
+Transformer.forward and its layers (A2/models/transformer.py:109-215,242-279,352-426).
+"""
+import math
+
+import torch
+
+from . import _lib as L
+
+RESNET50_BLOCKS = (3, 4, 6, 3)
+RESNET50_PLANES = (64, 128, 256, 512)
+
+
+def _r8(n):
+    return (n + 7) // 8 * 8
+
+
+class Lin:
+    """A packed linear / conv-as-GEMM weight: split-bf16 [N, K] for forward, [K, N] for dgrad."""
+
+    def __init__(self, eng, wname, bname=None, bn=None, taps=1, trainable=True, need_t=True):
+        self.eng, self.wname, self.bname, self.bn, self.taps = eng, wname, bname, bn, taps
+        w = eng.params[wname]
+        self.n_out = w.shape[0]
+        self.cin = w.shape[1]
+        self.k = self.cin * taps
+        self.trainable = trainable and wname in eng.grad_views
+        self.need_t = need_t and trainable
+        dev = w.device
+        self.w = torch.zeros(2, self.n_out, _r8(self.k), device=dev, dtype=torch.bfloat16)
+        self.wt = torch.zeros(2, self.k, _r8(self.n_out), device=dev, dtype=torch.bfloat16) if self.need_t else None
+        self.scale = torch.empty(self.n_out, device=dev) if bn else None
+        self.shift = torch.empty(self.n_out, device=dev) if bn else None
+        self.bias = None
+        self.stage = None  # fp32 [n_out, taps*cin] wgrad staging for taps > 1
+
+    def pack(self):
+        p = self.eng.params
+        if self.bn:
+            L.call("cdetr_bn_fold", p[self.bn + ".weight"], p[self.bn + ".bias"], p[self.bn + ".running_mean"],
+                   p[self.bn + ".running_var"], 1e-5, self.n_out, self.scale, self.shift)
+            self.bias = self.shift
+        elif self.bname:
+            b = p[self.bname]
+            # stage-1 cls bias has shape [1] and broadcasts over the two logits (A1/models/transformer.py:84-88)
+            self.bias = b if b.numel() == self.n_out else b.expand(self.n_out).contiguous()
+        L.call("cdetr_pack_weight", p[self.wname], self.n_out, self.cin, self.taps, self.scale, self.w, self.wt)
+
+    # y[M, rows] = a[M, K] @ W[rows, :]^T + bias[rows]
+    def fwd(self, a, M, rows=None, **kw):
+        lo, hi = rows if rows else (0, self.n_out)
+        bias = self.bias[lo:hi] if self.bias is not None else None
+        L.gemm(a, self.w[:, lo:hi], M, hi - lo, self.k, mode=0, bias=bias, **kw)
+
+    # dx[M, K] = dy[M, rows] @ W[rows, :]
+    def dgrad(self, dy, M, rows=None, **kw):
+        lo, hi = rows if rows else (0, self.n_out)
+        L.gemm(dy, self.wt[:, :, lo:hi], M, self.k, hi - lo, mode=0, **kw)
+
+    # dW[rows, :] += scale * dy[M, rows]^T @ a[M, K];  db[rows] += colsum(dy)
+    def wgrad(self, dy, a, M, rows=None, bias_grad=True):
+        if not self.trainable:
+            return
+        lo, hi = rows if rows else (0, self.n_out)
+        n = hi - lo
+        tiles = math.ceil(n / 128) * math.ceil(self.k / 128)
+        kb = math.ceil(M / 64)
+        split_k = max(1, min(kb // 4, (2 * 148) // max(tiles, 1)))
+        if self.taps == 1:
+            out = self.eng.grad_views[self.wname].view(self.n_out, self.k)[lo:hi]
+        else:
+            out = self.stage[lo:hi]
+        L.gemm(dy, a, n, self.k, M, mode=1, out_f32=out, accumulate=True, split_k=split_k,
+               row_scale=self.scale[lo:hi] if self.scale is not None else None,
+               block_n=128 if self.k > 64 else 64)
+        if bias_grad and self.bname and self.bname in self.eng.grad_views:
+            g = self.eng.grad_views[self.bname]
+            if g.numel() != self.n_out:
+                raise NotImplementedError("gradient of a broadcast (shape-[1]) bias")
+            L.call("cdetr_colsum", None, dy, 0, M, n, g[lo:hi])
+
+    def finish_grad(self):
+        if self.trainable and self.taps > 1:
+            L.call("cdetr_unpack_conv_grad", self.stage, self.n_out, self.cin, self.taps,
+                   self.eng.grad_views[self.wname])
+
+
+class Engine:
+    def __init__(self, cfg, params, buffers, device, train_backbone=True):
+        """cfg: namespace with stage, hidden_dim, nheads, enc_layers, dec_layers, dim_feedforward,
+        num_query_position, num_query_pattern, spatial_prior, aux_loss.
+        params: name -> fp32 parameter tensor (reference names; shared heads under index 0);
+        buffers: FrozenBN buffers (name -> tensor)."""
+        L.lib()  # fail loudly if the CUDA library is missing
+        self.cfg = cfg
+        self.dev = device
+        self.params = dict(params)
+        self.params.update(buffers)
+        self.E, self.nh, self.F = cfg.hidden_dim, cfg.nheads, cfg.dim_feedforward
+        assert self.E == 256 and self.E // self.nh == 32, "kernels are specialised for E=256, head_dim=32"
+        self._bufs = {}
+        self.saved = {}
+        # ---- which parameters receive gradients (A2/models/backbone.py:93-95: conv1 + layer1 frozen, BN frozen)
+        self.trainable = []
+        for n, p in params.items():
+            if n.startswith("backbone."):
+                if not train_backbone or not any(k in n for k in ("layer2", "layer3", "layer4")):
+                    continue
+            if cfg.stage == 2 and n.startswith("input_proj."):
+                continue  # registered but never used in stage 2 (A2/models/anchor_detr.py:68-74,119)
+            if cfg.stage == 1 and ".cls_embed." in n:
+                continue  # stage-1 loss never touches pred_logits
+            self.trainable.append(n)
+        sizes = [self.params[n].numel() for n in self.trainable]
+        # 3x3 conv wgrad staging lives behind the parameter gradients so one memset clears both
+        self.lins = {}
+        self._build_lins(train_backbone)
+        stage_sizes = [(l, l.n_out * l.k) for l in self.lins.values() if l.trainable and l.taps > 1]
+        total = sum(_r8(s) for s in sizes) + sum(_r8(s) for _, s in stage_sizes)
+        self.grad_flat = torch.zeros(total, device=device)
+        self.grad_views, off = {}, 0
+        for n, s in zip(self.trainable, sizes):
+            self.grad_views[n] = self.grad_flat[off:off + s].view_as(self.params[n])
+            off += _r8(s)
+        self.n_param_grad = off
+        for l, s in stage_sizes:
+            l.stage = self.grad_flat[off:off + s].view(l.n_out, l.k)
+            off += _r8(s)
+        for l in self.lins.values():
+            l.trainable = l.trainable and l.wname in self.grad_views
+        self.packed = False
+
+    # ------------------------------------------------------------------ infrastructure
+    def buf(self, name, shape, dtype=torch.float32, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.zeros(*shape, device=self.dev, dtype=dtype)
+            self._bufs[key] = t
+        elif zero:
+            t.zero_()
+        return t
+
+    def sbuf(self, name, rows, cols):
+        return self.buf(name, (2, rows, _r8(cols)), torch.bfloat16)
+
+    def _lin(self, key, *a, **kw):
+        self.grad_views = getattr(self, "grad_views", {n: None for n in self.trainable})
+        l = Lin(self, *a, **kw)
+        self.lins[key] = l
+        return l
+
+    def _build_lins(self, train_backbone):
+        cfg, p = self.cfg, "backbone.body"
+        self._lin("stem", p + ".conv1.weight", bn=p + ".bn1", taps=49, trainable=False)
+        self.blocks = []
+        inpl = 64
+        for li, (nb, planes) in enumerate(zip(RESNET50_BLOCKS, RESNET50_PLANES)):
+            tr = train_backbone and li >= 1
+            for bi in range(nb):
+                q = f"{p}.layer{li + 1}.{bi}"
+                stride = 2 if (bi == 0 and li in (1, 2)) else 1
+                dil = 2 if (li == 3 and bi > 0) else 1
+                blk = dict(name=q, planes=planes, cin=inpl, stride=stride, dil=dil, train=tr, li=li, bi=bi,
+                           c1=self._lin(q + ".c1", q + ".conv1.weight", bn=q + ".bn1", trainable=tr),
+                           c2=self._lin(q + ".c2", q + ".conv2.weight", bn=q + ".bn2", taps=9, trainable=tr),
+                           c3=self._lin(q + ".c3", q + ".conv3.weight", bn=q + ".bn3", trainable=tr),
+                           ds=self._lin(q + ".ds", q + ".downsample.0.weight", bn=q + ".downsample.1",
+                                        trainable=tr) if bi == 0 else None)
+                self.blocks.append(blk)
+                inpl = planes * 4
+        proj = "aggr_input_proj.0" if cfg.stage == 2 else "input_proj.0"
+        self.proj_name = proj
+        self._lin("proj", proj + ".0.weight", proj + ".0.bias")
+        t = "transformer"
+        for i in range(cfg.enc_layers):
+            q = f"{t}.encoder_layers.{i}"
+            self._lin(q + ".in", q + ".self_attn.in_proj_weight", q + ".self_attn.in_proj_bias")
+            self._lin(q + ".out", q + ".self_attn.out_proj.weight", q + ".self_attn.out_proj.bias")
+            self._lin(q + ".l1", q + ".ffn.linear1.weight", q + ".ffn.linear1.bias")
+            self._lin(q + ".l2", q + ".ffn.linear2.weight", q + ".ffn.linear2.bias")
+        for i in range(cfg.dec_layers):
+            q = f"{t}.decoder_layers.{i}"
+            self._lin(q + ".sa_in", q + ".self_attn.in_proj_weight", q + ".self_attn.in_proj_bias")
+            self._lin(q + ".sa_out", q + ".self_attn.out_proj.weight", q + ".self_attn.out_proj.bias")
+            self._lin(q + ".ca_in", q + ".cross_attn.in_proj_weight", q + ".cross_attn.in_proj_bias")
+            self._lin(q + ".ca_out", q + ".cross_attn.out_proj.weight", q + ".cross_attn.out_proj.bias")
+            self._lin(q + ".l1", q + ".ffn.linear1.weight", q + ".ffn.linear1.bias")
+            self._lin(q + ".l2", q + ".ffn.linear2.weight", q + ".ffn.linear2.bias")
+        for name in ("adapt_pos1d", "adapt_pos2d"):
+            self._lin(name + ".0", f"{t}.{name}.0.weight", f"{t}.{name}.0.bias")
+            self._lin(name + ".2", f"{t}.{name}.2.weight", f"{t}.{name}.2.bias")
+        self._lin("cls", f"{t}.cls_embed.0.weight", f"{t}.cls_embed.0.bias")
+        heads = ["bbox_embed"] + (["bbox_variance"] if cfg.stage == 2 else [])
+        for h in heads:
+            for j in range(3):
+                self._lin(f"{h}.{j}", f"{t}.{h}.0.layers.{j}.weight", f"{t}.{h}.0.layers.{j}.bias")
+        del self.grad_views
+
+    def pack_weights(self):
+        """Re-pack every weight into split-bf16 (call after each optimizer step)."""
+        for l in self.lins.values():
+            l.pack()
+        self.packed = True
+
+    def zero_grad(self):
+        self.grad_flat.zero_()
+
+    # ------------------------------------------------------------------ backbone
+    def _backbone_fwd(self, image):
+        B, _, S1, S2 = image.shape
+        sv = self.saved
+        H0, W0 = (S1 + 6 - 7) // 2 + 1, (S2 + 6 - 7) // 2 + 1
+        col = self.sbuf("stem_col", B * H0 * W0, 152)
+        L.call("cdetr_stem_im2col", image, B, S1, S2, col)
+        a0 = self.sbuf("stem_out", B * H0 * W0, 64)
+        self.lins["stem"].fwd(col, B * H0 * W0, out_split=a0, relu=True)
+        H, W = (H0 + 2 - 3) // 2 + 1, (W0 + 2 - 3) // 2 + 1
+        x = self.sbuf("pool_out", B * H * W, 64)
+        L.call("cdetr_maxpool3x3s2", a0, B, H0, W0, 64, x)
+        max_col = 0
+        for blk in self.blocks:
+            Ho, Wo = (H - 1) // blk["stride"] + 1, (W - 1) // blk["stride"] + 1
+            max_col = max(max_col, B * Ho * Wo * _r8(9 * blk["planes"]))
+        colbuf = self.buf("col_scratch", (2, max_col), torch.bfloat16)
+        for blk in self.blocks:
+            n, p_, s, d = blk["name"], blk["planes"], blk["stride"], blk["dil"]
+            Min = B * H * W
+            Ho, Wo = (H - 1) // s + 1, (W - 1) // s + 1
+            Mo = B * Ho * Wo
+            a = self.sbuf(n + ".a", Min, p_)
+            blk["c1"].fwd(x, Min, out_split=a, relu=True)
+            col = colbuf[:, : Mo * 9 * p_].view(2, Mo, 9 * p_)
+            L.call("cdetr_im2col3x3", a, B, H, W, p_, s, d, col)
+            b = self.sbuf(n + ".b", Mo, p_)
+            blk["c2"].fwd(col, Mo, out_split=b, relu=True)
+            if blk["ds"] is not None:
+                if s == 2:
+                    xs = self.sbuf(n + ".xs", Mo, blk["cin"])
+                    L.call("cdetr_subsample2", x, B, H, W, blk["cin"], xs)
+                else:
+                    xs = x
+                idt = self.sbuf(n + ".idt", Mo, 4 * p_)
+                blk["ds"].fwd(xs, Mo, out_split=idt)
+            else:
+                xs, idt = None, x
+            out = self.sbuf(n + ".out", Mo, 4 * p_)
+            blk["c3"].fwd(b, Mo, out_split=out, add_split=idt, relu=True)
+            sv[n] = dict(x=x, a=a, b=b, xs=xs, out=out, H=H, W=W, Ho=Ho, Wo=Wo)
+            x, H, W = out, Ho, Wo
+        return x, H, W
+
+    def _backbone_bwd(self, g, B):
+        """g: split grad w.r.t. the last block's output, already masked by that output's ReLU."""
+        sv = self.saved
+        colbuf = self.buf("col_scratch", self._bufs_key_shape("col_scratch"), torch.bfloat16)
+        col2buf = self.buf("col_scratch2", self._bufs_key_shape("col_scratch"), torch.bfloat16)
+        for blk in reversed(self.blocks):
+            if not blk["train"]:
+                break
+            n, p_, s, d = blk["name"], blk["planes"], blk["stride"], blk["dil"]
+            t = sv[n]
+            H, W, Ho, Wo = t["H"], t["W"], t["Ho"], t["Wo"]
+            Min, Mo = B * H * W, B * Ho * Wo
+            first = blk["li"] == 1 and blk["bi"] == 0  # input comes from the frozen layer1: no dx
+            blk["c3"].wgrad(g, t["b"], Mo)
+            db = self.sbuf(n + ".db", Mo, p_)
+            blk["c3"].dgrad(g, Mo, out_split=db, mask=t["b"])
+            col = colbuf[:, : Mo * 9 * p_].view(2, Mo, 9 * p_)
+            L.call("cdetr_im2col3x3", t["a"], B, H, W, p_, s, d, col)
+            blk["c2"].wgrad(db, col, Mo)
+            dcol = col2buf[:, : Mo * 9 * p_].view(2, Mo, 9 * p_)
+            blk["c2"].dgrad(db, Mo, out_split=dcol)
+            da = self.sbuf(n + ".da", Min, p_)
+            L.call("cdetr_col2im3x3", dcol, B, H, W, p_, s, d, t["a"], da)
+            blk["c1"].wgrad(da, t["x"], Min)
+            if blk["ds"] is not None:
+                blk["ds"].wgrad(g, t["xs"], Mo)
+            if first:
+                break
+            if blk["ds"] is not None:
+                dids = self.sbuf(n + ".dids", Mo, blk["cin"])
+                blk["ds"].dgrad(g, Mo, out_split=dids)
+                if s == 2:
+                    didt = self.sbuf(n + ".didt", Min, blk["cin"])
+                    L.call("cdetr_upsample2_zero", dids, B, H, W, blk["cin"], didt)
+                else:
+                    didt = dids
+            else:
+                didt = g
+            dx = self.sbuf(n + ".dx", Min, blk["cin"])
+            blk["c1"].dgrad(da, Min, out_split=dx, add_split=didt, mask=t["x"])
+            g = dx
+        for blk in self.blocks:
+            if blk["train"]:
+                for k in ("c1", "c2", "c3", "ds"):
+                    if blk[k] is not None:
+                        blk[k].finish_grad()
+
+    def _bufs_key_shape(self, name):
+        for (n, shape, _), _t in self._bufs.items():
+            if n == name:
+                return shape
+        raise KeyError(name)
+
+    # ------------------------------------------------------------------ small helpers
+    def _mlp2_fwd(self, key, e0, n, tag):
+        """adapt_pos MLP: Linear-ReLU-Linear on split input e0 [n, E]; returns fp32 [n, E]."""
+        h = self.sbuf(tag + ".h", n, self.E)
+        self.lins[key + ".0"].fwd(e0, n, out_split=h, relu=True)
+        out = self.buf(tag + ".out", (n, self.E))
+        self.lins[key + ".2"].fwd(h, n, out_f32=out)
+        self.saved[tag] = dict(e0=e0, h=h, n=n)
+        return out
+
+    def _mlp2_bwd(self, key, dout, tag, need_de0=False):
+        t = self.saved[tag]
+        n = t["n"]
+        ds = self.sbuf(tag + ".dout_s", n, self.E)
+        L.call("cdetr_to_split", dout, n, self.E, self.E, ds)
+        self.lins[key + ".2"].wgrad(ds, t["h"], n)
+        dh = self.sbuf(tag + ".dh", n, self.E)
+        self.lins[key + ".2"].dgrad(ds, n, out_split=dh, mask=t["h"])
+        self.lins[key + ".0"].wgrad(dh, t["e0"], n)
+        if need_de0:
+            de0 = self.buf(tag + ".de0", (n, self.E))
+            self.lins[key + ".0"].dgrad(dh, n, out_f32=de0)
+            return de0
+        return None
+
+    def _ln_fwd(self, x, res, M, pname, tag):
+        p = self.params
+        z = self.buf(tag + ".z", (M, self.E))
+        y = self.buf(tag + ".y", (M, self.E))
+        ys = self.sbuf(tag + ".ys", M, self.E)
+        st = self.buf(tag + ".st", (M, 2))
+        L.call("cdetr_layernorm_fwd", x, res, M, self.E, p[pname + ".weight"], p[pname + ".bias"], 1e-5, z, y, ys, st)
+        self.saved[tag] = dict(z=z, st=st, M=M, pname=pname)
+        return y, ys
+
+    def _ln_bwd(self, dy, dy2, tag):
+        t = self.saved[tag]
+        M, pname = t["M"], t["pname"]
+        dz = self.buf(tag + ".dz", (M, self.E))
+        dzs = self.sbuf(tag + ".dzs", M, self.E)
+        L.call("cdetr_layernorm_bwd", dy, dy2, t["z"], t["st"], M, self.E, self.params[pname + ".weight"], dz, dzs,
+               self.grad_views[pname + ".weight"], self.grad_views[pname + ".bias"])
+        return dz, dzs
+
+    def _ffn_fwd(self, x, xs, M, q):
+        h = self.sbuf(q + ".ffn_h", M, self.F)
+        self.lins[q + ".l1"].fwd(xs, M, out_split=h, relu=True)
+        f = self.buf(q + ".ffn_f", (M, self.E))
+        self.lins[q + ".l2"].fwd(h, M, out_f32=f)
+        y, ys = self._ln_fwd(f, x, M, q + ".ffn.norm2", q + ".ln_ffn")
+        self.saved[q + ".ffn"] = dict(h=h, xs=xs, M=M)
+        return y, ys
+
+    def _ffn_bwd(self, dy, dy2, q):
+        """returns fp32 grad w.r.t. the FFN block input (residual + branch)."""
+        t = self.saved[q + ".ffn"]
+        M = t["M"]
+        dz, dzs = self._ln_bwd(dy, dy2, q + ".ln_ffn")
+        self.lins[q + ".l2"].wgrad(dzs, t["h"], M)
+        dh = self.sbuf(q + ".ffn_dh", M, self.F)
+        self.lins[q + ".l2"].dgrad(dzs, M, out_split=dh, mask=t["h"])
+        self.lins[q + ".l1"].wgrad(dh, t["xs"], M)
+        dx = self.buf(q + ".ffn_dx", (M, self.E))
+        self.lins[q + ".l1"].dgrad(dh, M, out_f32=dx, add_f32=dz)
+        return dx
+
+    def _rcda_fwd(self, q, lin_in, lin_out, B, Lq, H, W, qr_in, qc_in, kr_in, kc_in, v_in, masks):
+        E = self.E
+        M, N = B * Lq, B * H * W
+        qr = self.buf(q + ".qr", (M, E)); qc = self.buf(q + ".qc", (M, E))
+        kr = self.buf(q + ".kr", (B * W, E)); kc = self.buf(q + ".kc", (B * H, E))
+        v = self.buf(q + ".v", (N, E))
+        lin = self.lins[lin_in]
+        lin.fwd(qr_in, M, rows=(0, E), out_f32=qr)
+        lin.fwd(qc_in, M, rows=(E, 2 * E), out_f32=qc)
+        lin.fwd(kr_in, B * W, rows=(2 * E, 3 * E), out_f32=kr)
+        lin.fwd(kc_in, B * H, rows=(3 * E, 4 * E), out_f32=kc)
+        lin.fwd(v_in, N, rows=(4 * E, 5 * E), out_f32=v)
+        ar = self.buf(q + ".ar", (B, self.nh, W, Lq)); ac = self.buf(q + ".ac", (B, self.nh, H, Lq))
+        o = self.sbuf(q + ".o", M, E)
+        L.call("cdetr_rcda_fwd", B, Lq, H, W, E, self.nh, qr, qc, kr, kc, v, masks[0], masks[1], ar, ac, o)
+        attn = self.buf(q + ".attn", (M, E))
+        self.lins[lin_out].fwd(o, M, out_f32=attn)
+        self.saved[q + ".rcda"] = dict(qr=qr, qc=qc, kr=kr, kc=kc, v=v, ar=ar, ac=ac, o=o, qr_in=qr_in, qc_in=qc_in,
+                                       kr_in=kr_in, kc_in=kc_in, v_in=v_in, B=B, L=Lq, H=H, W=W)
+        return attn
+
+    def _rcda_bwd(self, q, lin_in, lin_out, dattn_s, dv_add=None):
+        """dattn_s: split grad of the attention output. Returns fp32 grads (dqr_in, dqc_in, dkr_in, dkc_in, dv_in);
+        dv_in has dv_add (fp32, e.g. the residual stream) accumulated into it when given."""
+        t = self.saved[q + ".rcda"]
+        E, B, Lq, H, W = self.E, t["B"], t["L"], t["H"], t["W"]
+        M, N = B * Lq, B * H * W
+        self.lins[lin_out].wgrad(dattn_s, t["o"], M)
+        dO = self.buf(q + ".dO", (M, E))
+        self.lins[lin_out].dgrad(dattn_s, M, out_f32=dO)
+        dsr = self.buf(q + ".dsr", (B, self.nh, W, Lq)); dsc = self.buf(q + ".dsc", (B, self.nh, H, Lq))
+        dqr = self.sbuf(q + ".dqr", M, E); dqc = self.sbuf(q + ".dqc", M, E)
+        dkr = self.sbuf(q + ".dkr", B * W, E); dkc = self.sbuf(q + ".dkc", B * H, E); dv = self.sbuf(q + ".dv", N, E)
+        L.call("cdetr_rcda_bwd", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], t["kr"], t["kc"], t["v"], t["ar"], t["ac"],
+               dO, dsr, dsc, dqr, dqc, dkr, dkc, dv)
+        lin = self.lins[lin_in]
+        lin.wgrad(dqr, t["qr_in"], M, rows=(0, E))
+        lin.wgrad(dqc, t["qc_in"], M, rows=(E, 2 * E))
+        lin.wgrad(dkr, t["kr_in"], B * W, rows=(2 * E, 3 * E))
+        lin.wgrad(dkc, t["kc_in"], B * H, rows=(3 * E, 4 * E))
+        lin.wgrad(dv, t["v_in"], N, rows=(4 * E, 5 * E))
+        g_qr = self.buf(q + ".g_qr", (M, E)); g_qc = self.buf(q + ".g_qc", (M, E))
+        g_kr = self.buf(q + ".g_kr", (B * W, E)); g_kc = self.buf(q + ".g_kc", (B * H, E))
+        g_v = self.buf(q + ".g_v", (N, E))
+        lin.dgrad(dqr, M, rows=(0, E), out_f32=g_qr)
+        lin.dgrad(dqc, M, rows=(E, 2 * E), out_f32=g_qc)
+        lin.dgrad(dkr, B * W, rows=(2 * E, 3 * E), out_f32=g_kr)
+        lin.dgrad(dkc, B * H, rows=(3 * E, 4 * E), out_f32=g_kc)
+        lin.dgrad(dv, N, rows=(4 * E, 5 * E), out_f32=g_v, add_f32=dv_add)
+        return g_qr, g_qc, g_kr, g_kc, g_v
+
+    # ------------------------------------------------------------------ forward
+    def reference_points(self, points=None):
+        cfg = self.cfg
+        if cfg.spatial_prior == "learned":
+            ref = self.params["transformer.position.weight"]
+        elif cfg.spatial_prior == "grid":
+            n = round(math.sqrt(cfg.num_query_position))
+            g = (torch.arange(n, dtype=torch.float32) + 0.5) / n
+            gx, gy = torch.meshgrid(g, g, indexing="ij")
+            ref = torch.stack([gx.reshape(-1), gy.reshape(-1)], -1).to(self.dev)
+        elif cfg.spatial_prior == "defined":
+            assert points is not None, "defined, provide points"
+            ref = torch.as_tensor(points, dtype=torch.float32).reshape(-1, 2).to(self.dev)
+        else:
+            raise ValueError(f"unknown {cfg.spatial_prior} spatial prior")
+        return ref.contiguous()
+
+    def forward(self, image, centres_yx=None, points=None, mask=None):
+        """image [B,3,S,S] fp32 cuda; centres_yx int32 [n_ex,2] (stage 2); returns dict of fp32 outputs."""
+        if not self.packed:
+            self.pack_weights()
+        cfg, E, sv = self.cfg, self.E, self.saved
+        B = image.shape[0]
+        feat, H, W = self._backbone_fwd(image.contiguous())
+        N = H * W
+        M = B * N
+        sv["dims"] = dict(B=B, H=H, W=W)
+        # ---- exemplar injection + 1x1 projection + GroupNorm
+        if cfg.stage == 2:
+            cat = self.sbuf("cat", M, 4096)
+            p_ex = self.buf("p_ex", (B, 2048))
+            L.call("cdetr_exemplar_concat", feat, B, H, W, 2048, centres_yx, centres_yx.shape[0], p_ex, cat)
+            sv["ex"] = dict(feat=feat, p=p_ex, yx=centres_yx, cat=cat)
+            proj_in = cat
+        else:
+            proj_in = feat
+            sv["ex"] = dict(feat=feat)
+        pre = self.buf("proj_pre", (M, E))
+        self.lins["proj"].fwd(proj_in, M, out_f32=pre)
+        src = self.buf("src0", (M, E)); src_s = self.sbuf("src0_s", M, E)
+        gst = self.buf("gn_stats", (B * 32 * 2,))
+        pn = self.proj_name + ".1"
+        L.call("cdetr_groupnorm_fwd", pre, B, N, E, 32, self.params[pn + ".weight"], self.params[pn + ".bias"], 1e-5,
+               src, src_s, gst)
+        sv["proj"] = dict(pre=pre, gst=gst, proj_in=proj_in)
+        # ---- positions: mask2pos (no padding: (i+0.5)/n; with a mask the caller passes per-sample positions)
+        if mask is None:
+            pos_row = ((torch.arange(W, device=self.dev, dtype=torch.float32) + 0.5) / W).repeat(B)
+            pos_col = ((torch.arange(H, device=self.dev, dtype=torch.float32) + 0.5) / H).repeat(B)
+            masks = (None, None)
+        else:
+            nm = ~mask
+            yv = nm[:, :, 0].cumsum(1, dtype=torch.float32); xv = nm[:, 0, :].cumsum(1, dtype=torch.float32)
+            pos_col = ((yv - 0.5) / yv[:, -1:]).reshape(-1).contiguous()
+            pos_row = ((xv - 0.5) / xv[:, -1:]).reshape(-1).contiguous()
+            masks = (mask[:, 0, :].to(torch.uint8).contiguous(), mask[:, :, 0].to(torch.uint8).contiguous())
+        ref = self.reference_points(points)            # [Qp, 2] (same for every sample)
+        P = cfg.num_query_pattern
+        Qp = ref.shape[0]
+        Q = Qp * P
+        ref_all = ref.repeat(P, 1).contiguous() if P > 1 else ref  # [Q, 2]
+        sv["ref"] = ref_all
+        # one adapt_pos1d call for [pos_row | pos_col | ref_x | ref_y]
+        n1 = B * W + B * H + 2 * Q
+        e1 = self.buf("pos1d_e", (n1, E))
+        L.call("cdetr_sine_embed", pos_row, B * W, 1, E, 0, E, e1)
+        L.call("cdetr_sine_embed", pos_col, B * H, 1, E, 0, E, e1[B * W:])
+        L.call("cdetr_sine_embed", ref_all, Q, 2, E, 0, E, e1[B * W + B * H:])
+        L.call("cdetr_sine_embed", ref_all[:, 1:], Q, 2, E, 0, E, e1[B * W + B * H + Q:])
+        e1s = self.sbuf("pos1d_es", n1, E)
+        L.call("cdetr_to_split", e1, n1, E, E, e1s)
+        pe1 = self._mlp2_fwd("adapt_pos1d", e1s, n1, "pos1d")
+        pe_row, pe_col = pe1[: B * W], pe1[B * W: B * W + B * H]
+        qx, qy = pe1[B * W + B * H: B * W + B * H + Q], pe1[B * W + B * H + Q:]
+        e2 = self.buf("pos2d_e", (Q, E))
+        L.call("cdetr_sine_embed", ref_all[:, 1:], Q, 2, 128, 0, E, e2)      # y half first (transformer.py:483)
+        L.call("cdetr_sine_embed", ref_all, Q, 2, 128, 128, E, e2)
+        e2s = self.sbuf("pos2d_es", Q, E)
+        L.call("cdetr_to_split", e2, Q, E, E, e2s)
+        qpos = self._mlp2_fwd("adapt_pos2d", e2s, Q, "pos2d")
+        sv["pos"] = dict(pe_row=pe_row, pe_col=pe_col, qx=qx, qy=qy, qpos=qpos, Q=Q, Qp=Qp, P=P)
+        # ---- encoder
+        x, xs = src, src_s
+        for i in range(cfg.enc_layers):
+            q = f"transformer.encoder_layers.{i}"
+            xr = self.sbuf(q + ".xr", M, E); xc = self.sbuf(q + ".xc", M, E)
+            L.call("cdetr_add_bcast", x, pe_row, M, E, 1, H, W, 0, None, xr)
+            L.call("cdetr_add_bcast", x, pe_col, M, E, 2, H, W, 0, None, xc)
+            krin = self.sbuf(q + ".krin", B * W, E); kcin = self.sbuf(q + ".kcin", B * H, E)
+            L.call("cdetr_reduce_axis", x, B, H, W, E, 1, 1.0 / H, pe_row, 0, None, krin)
+            L.call("cdetr_reduce_axis", x, B, H, W, E, 2, 1.0 / W, pe_col, 0, None, kcin)
+            attn = self._rcda_fwd(q, q + ".in", q + ".out", B, N, H, W, xr, xc, krin, kcin, xs, masks)
+            x1, x1s = self._ln_fwd(attn, x, M, q + ".norm1", q + ".ln1")
+            x, xs = self._ffn_fwd(x1, x1s, M, q)
+        memory, mem_s = x, xs
+        sv["memory"] = memory
+        # ---- decoder
+        krin_d = self.sbuf("dec.krin", B * W, E); kcin_d = self.sbuf("dec.kcin", B * H, E)
+        L.call("cdetr_reduce_axis", memory, B, H, W, E, 1, 1.0 / H, pe_row, 0, None, krin_d)
+        L.call("cdetr_reduce_axis", memory, B, H, W, E, 2, 1.0 / W, pe_col, 0, None, kcin_d)
+        MQ = B * Q
+        pat = self.params[self._pattern_key()]
+        tgt0 = pat.reshape(1, P, 1, E).expand(B, P, Qp, E).reshape(MQ, E)
+        tgt = self.buf("tgt0", (MQ, E)); tgt.copy_(tgt0)
+        tgt_s = self.sbuf("tgt0_s", MQ, E)
+        L.call("cdetr_to_split", tgt, MQ, E, E, tgt_s)
+        outs = []
+        for i in range(cfg.dec_layers):
+            q = f"transformer.decoder_layers.{i}"
+            qk = self.sbuf(q + ".qk", MQ, E)
+            L.call("cdetr_add_bcast", tgt, qpos, MQ, E, 3, 1, 1, Q, None, qk)
+            qkv = self.buf(q + ".qkv", (MQ, 3 * E))
+            lin = self.lins[q + ".sa_in"]
+            lin.fwd(qk, MQ, rows=(0, 2 * E), out_f32=qkv[:, : 2 * E])
+            lin.fwd(tgt_s, MQ, rows=(2 * E, 3 * E), out_f32=qkv[:, 2 * E:])
+            o = self.sbuf(q + ".sa_o", MQ, E); lse = self.buf(q + ".lse", (B, self.nh, Q))
+            L.call("cdetr_mha_fwd", B, Q, E, self.nh, qkv, qkv[:, E:], qkv[:, 2 * E:], 3 * E, o, lse)
+            sa = self.buf(q + ".sa", (MQ, E))
+            self.lins[q + ".sa_out"].fwd(o, MQ, out_f32=sa)
+            sv[q + ".sa"] = dict(qk=qk, tgt_s=tgt_s, qkv=qkv, o=o, lse=lse)
+            t1, t1s = self._ln_fwd(sa, tgt, MQ, q + ".norm2", q + ".ln2")
+            qr_in = self.sbuf(q + ".qr_in", MQ, E); qc_in = self.sbuf(q + ".qc_in", MQ, E)
+            L.call("cdetr_add_bcast", t1, qx, MQ, E, 3, 1, 1, Q, None, qr_in)
+            L.call("cdetr_add_bcast", t1, qy, MQ, E, 3, 1, 1, Q, None, qc_in)
+            ca = self._rcda_fwd(q, q + ".ca_in", q + ".ca_out", B, Q, H, W, qr_in, qc_in, krin_d, kcin_d, mem_s, masks)
+            t2, t2s = self._ln_fwd(ca, t1, MQ, q + ".norm1", q + ".ln1")
+            tgt, tgt_s = self._ffn_fwd(t2, t2s, MQ, q)
+            if cfg.aux_loss or i == cfg.dec_layers - 1:
+                outs.append(self._heads_fwd(tgt_s, MQ, Q, i))
+        sv["dec_out_s"] = tgt_s
+        return outs, dict(B=B, Q=Q, H=H, W=W)
+
+    def _pattern_key(self):
+        return "transformer.modify_pattern.weight" if self.cfg.stage == 1 else "transformer.pattern.weight"
+
+    def _heads_fwd(self, xs, MQ, Q, i):
+        """cls / bbox / variance heads (shared weights, A2/models/transformer.py:193-211)."""
+        tag = f"heads{i}"
+        logits = self.buf(tag + ".logits", (MQ, 2))
+        self.lins["cls"].fwd(xs, MQ, out_f32=logits)
+        h1 = self.sbuf(tag + ".b1", MQ, self.E); h2 = self.sbuf(tag + ".b2", MQ, self.E)
+        self.lins["bbox_embed.0"].fwd(xs, MQ, out_split=h1, relu=True)
+        self.lins["bbox_embed.1"].fwd(h1, MQ, out_split=h2, relu=True)
+        t = self.buf(tag + ".t", (MQ, 4))
+        self.lins["bbox_embed.2"].fwd(h2, MQ, out_f32=t)
+        boxes = self.buf(tag + ".boxes", (MQ, 4))
+        # reference points are identical for every sample: index rows modulo Q via a repeated view
+        ref_b = self.buf("ref_rep", (MQ, 2))
+        ref_b.view(-1, Q, 2).copy_(self.saved["ref"].unsqueeze(0).expand(MQ // Q, Q, 2))
+        L.call("cdetr_box_head_fwd", t, ref_b, MQ, boxes)
+        out = dict(logits=logits, boxes=boxes, xs=xs, h1=h1, h2=h2, ref_b=ref_b)
+        if self.cfg.stage == 2:
+            v1 = self.sbuf(tag + ".v1", MQ, self.E); v2 = self.sbuf(tag + ".v2", MQ, self.E)
+            self.lins["bbox_variance.0"].fwd(xs, MQ, out_split=v1, relu=True)
+            self.lins["bbox_variance.1"].fwd(v1, MQ, out_split=v2, relu=True)
+            vr = self.buf(tag + ".vars", (MQ, 2))
+            self.lins["bbox_variance.2"].fwd(v2, MQ, out_f32=vr)
+            out.update(vars=vr, v1=v1, v2=v2)
+        self.saved[tag] = out
+        return out
+
+    # ------------------------------------------------------------------ backward
+    def _heads_bwd(self, i, MQ, d_logits, d_boxes, d_vars, dx, first):
+        """accumulates the heads' input gradient into fp32 dx [MQ,E] (written when `first`)."""
+        h = self.saved[f"heads{i}"]
+        tag = f"heads{i}"
+        E = self.E
+        wrote = not first
+
+        def acc_dgrad(lin, dy, **kw):
+            nonlocal wrote
+            lin.dgrad(dy, MQ, out_f32=dx, add_f32=dx if wrote else None, **kw)
+            wrote = True
+
+        if d_logits is not None and self.lins["cls"].trainable:
+            dl = self.sbuf(tag + ".dl", MQ, 8)
+            L.call("cdetr_to_split", d_logits, MQ, 2, 2, dl)
+            self.lins["cls"].wgrad(dl, h["xs"], MQ)
+            acc_dgrad(self.lins["cls"], dl)
+        if d_boxes is not None:
+            dt = self.sbuf(tag + ".dt", MQ, 8)
+            dref = self.buf("dref_rep", (MQ, 2), zero=True) if self.cfg.spatial_prior == "learned" else None
+            L.call("cdetr_box_head_bwd", d_boxes, h["boxes"], h["ref_b"], MQ, None, dt, dref)
+            if dref is not None:
+                self.saved.setdefault("dref_list", []).append(dref)
+            self.lins["bbox_embed.2"].wgrad(dt, h["h2"], MQ)
+            d2 = self.sbuf(tag + ".d2", MQ, E); d1 = self.sbuf(tag + ".d1", MQ, E)
+            self.lins["bbox_embed.2"].dgrad(dt, MQ, out_split=d2, mask=h["h2"])
+            self.lins["bbox_embed.1"].wgrad(d2, h["h1"], MQ)
+            self.lins["bbox_embed.1"].dgrad(d2, MQ, out_split=d1, mask=h["h1"])
+            self.lins["bbox_embed.0"].wgrad(d1, h["xs"], MQ)
+            acc_dgrad(self.lins["bbox_embed.0"], d1)
+        if d_vars is not None and self.cfg.stage == 2:
+            dv = self.sbuf(tag + ".dvr", MQ, 8)
+            L.call("cdetr_to_split", d_vars, MQ, 2, 2, dv)
+            self.lins["bbox_variance.2"].wgrad(dv, h["v2"], MQ)
+            d2 = self.sbuf(tag + ".dv2", MQ, E); d1 = self.sbuf(tag + ".dv1", MQ, E)
+            self.lins["bbox_variance.2"].dgrad(dv, MQ, out_split=d2, mask=h["v2"])
+            self.lins["bbox_variance.1"].wgrad(d2, h["v1"], MQ)
+            self.lins["bbox_variance.1"].dgrad(d2, MQ, out_split=d1, mask=h["v1"])
+            self.lins["bbox_variance.0"].wgrad(d1, h["xs"], MQ)
+            acc_dgrad(self.lins["bbox_variance.0"], d1)
+        if not wrote:
+            dx.zero_()
+
+    def backward(self, grads):
+        """grads: list (one entry per emitted decoder layer, last = final layer) of dicts with optional
+        fp32 'logits' [B*Q,2], 'boxes' [B*Q,4], 'vars' [B*Q,2] gradients.  Accumulates into grad_flat."""
+        cfg, E, sv = self.cfg, self.E, self.saved
+        d = sv["dims"]; B, H, W = d["B"], d["H"], d["W"]
+        pos = sv["pos"]; Q, Qp, P = pos["Q"], pos["Qp"], pos["P"]
+        N = H * W; M = B * N; MQ = B * Q
+        sv["dref_list"] = []
+        emitted = list(range(cfg.dec_layers)) if cfg.aux_loss else [cfg.dec_layers - 1]
+        gmap = dict(zip(emitted, grads))
+        dmem, dmem_written = None, False
+        g_krd = self.buf("dec.g_kr_acc", (B * W, E), zero=True); g_kcd = self.buf("dec.g_kc_acc", (B * H, E), zero=True)
+        dqpos = self.buf("dqpos", (Q, E), zero=True); dqx = self.buf("dqx", (Q, E), zero=True); dqy = self.buf("dqy", (Q, E), zero=True)
+        dtgt = self.buf("dtgt", (MQ, E)); have_dtgt = False
+        # ---- decoder, last layer first
+        for i in reversed(range(cfg.dec_layers)):
+            q = f"transformer.decoder_layers.{i}"
+            if i in gmap:
+                g = gmap[i]
+                dh = self.buf(f"dheads{i}", (MQ, E))
+                self._heads_bwd(i, MQ, g.get("logits"), g.get("boxes"), g.get("vars"), dh, True)
+                dy, dy2 = (dh, dtgt) if have_dtgt else (dh, None)
+            else:
+                if not have_dtgt:
+                    continue  # layers after the last supervised one do not exist
+                dy, dy2 = dtgt, None
+            d2 = self._ffn_bwd(dy, dy2, q)                       # grad wrt t2 (post norm1)
+            dz1, dz1s = self._ln_bwd(d2, None, q + ".ln1")       # -> ca (split) and t1 residual (fp32)
+            g_qr, g_qc, g_kr, g_kc, g_v = self._rcda_bwd(q, q + ".ca_in", q + ".ca_out", dz1s,
+                                                        dv_add=dmem if dmem_written else None)
+            # value input is the memory: accumulate over decoder layers
+            dmem = g_v              # this layer's buffer now holds the sum over the layers processed so far
+            dmem_written = True
+            L.call("cdetr_add_bcast", g_krd, g_kr, B * W, E, 0, 1, 1, 0, g_krd, None)
+            L.call("cdetr_add_bcast", g_kcd, g_kc, B * H, E, 0, 1, 1, 0, g_kcd, None)
+            # queries: q_row_in = t1 + qx, q_col_in = t1 + qy
+            L.call("cdetr_reduce_axis", g_qr, 1, B, Q, E, 1, 1.0, None, 1, dqx, None)
+            L.call("cdetr_reduce_axis", g_qc, 1, B, Q, E, 1, 1.0, None, 1, dqy, None)
+            dt1 = self.buf(q + ".dt1", (MQ, E))
+            L.call("cdetr_combine_bcast", dz1, g_qr, g_qc, None, 0.0, None, 0.0, MQ, E, 1, 1, dt1)
+            dz2, dz2s = self._ln_bwd(dt1, None, q + ".ln2")      # -> sa (split), tgt residual (fp32)
+            t = sv[q + ".sa"]
+            self.lins[q + ".sa_out"].wgrad(dz2s, t["o"], MQ)
+            dO = self.buf(q + ".sa_dO", (MQ, E))
+            self.lins[q + ".sa_out"].dgrad(dz2s, MQ, out_f32=dO)
+            dsum = self.buf(q + ".dsum", (B, self.nh, Q))
+            dqkv = self.sbuf(q + ".dqkv", MQ, 3 * E)
+            dq_, dv_ = dqkv[:, :, : 2 * E], dqkv[:, :, 2 * E:]
+            qkv = t["qkv"]
+            L.call("cdetr_mha_bwd", B, Q, E, self.nh, qkv, qkv[:, E:], qkv[:, 2 * E:], 3 * E, t["o"], t["lse"], dO, dsum,
+                   dqkv[:, :, :E], dqkv[:, :, E: 2 * E], dv_)
+            lin = self.lins[q + ".sa_in"]
+            lin.wgrad(dq_, t["qk"], MQ, rows=(0, 2 * E))
+            lin.wgrad(dv_, t["tgt_s"], MQ, rows=(2 * E, 3 * E))
+            g_qk = self.buf(q + ".g_qk", (MQ, E))
+            lin.dgrad(dq_, MQ, rows=(0, 2 * E), out_f32=g_qk)
+            L.call("cdetr_reduce_axis", g_qk, 1, B, Q, E, 1, 1.0, None, 1, dqpos, None)
+            g_t = self.buf(q + ".g_t", (MQ, E))
+            lin.dgrad(dv_, MQ, rows=(2 * E, 3 * E), out_f32=g_t, add_f32=g_qk)
+            L.call("cdetr_combine_bcast", dz2, g_t, None, None, 0.0, None, 0.0, MQ, E, 1, 1, dtgt)
+            have_dtgt = True
+        # ---- pattern embedding: tgt0[b, p*Qp + j] = pattern[p]
+        gpat = self.grad_views[self._pattern_key()]
+        for b in range(B):
+            for p_ in range(P):
+                r0 = b * Q + p_ * Qp
+                L.call("cdetr_colsum", dtgt[r0:r0 + Qp], None, E, Qp, E, gpat[p_])
+        # ---- memory gradient: add the mean-over-H/W key paths accumulated over decoder layers
+        dpe = self.buf("dpe1", (B * W + B * H + 2 * Q, E), zero=True)
+        dpe_row, dpe_col = dpe[: B * W], dpe[B * W: B * W + B * H]
+        L.call("cdetr_add_bcast", dpe_row, g_krd, B * W, E, 0, 1, 1, 0, dpe_row, None)
+        L.call("cdetr_add_bcast", dpe_col, g_kcd, B * H, E, 0, 1, 1, 0, dpe_col, None)
+        dx = self.buf("denc", (M, E))
+        L.call("cdetr_combine_bcast", dmem, None, None, g_krd, 1.0 / H, g_kcd, 1.0 / W, M, E, H, W, dx)
+        # ---- encoder, last layer first
+        for i in reversed(range(cfg.enc_layers)):
+            q = f"transformer.encoder_layers.{i}"
+            d1 = self._ffn_bwd(dx, None, q)
+            dz1, dz1s = self._ln_bwd(d1, None, q + ".ln1")
+            g_qr, g_qc, g_kr, g_kc, g_v = self._rcda_bwd(q, q + ".in", q + ".out", dz1s, dv_add=dz1)
+            L.call("cdetr_reduce_axis", g_qr, B, H, W, E, 1, 1.0, g_kr, 1, dpe_row, None)
+            L.call("cdetr_reduce_axis", g_qc, B, H, W, E, 2, 1.0, g_kc, 1, dpe_col, None)
+            dx = self.buf(q + ".dx", (M, E))
+            L.call("cdetr_combine_bcast", g_qr, g_qc, g_v, g_kr, 1.0 / H, g_kc, 1.0 / W, M, E, H, W, dx)
+        # ---- position MLPs
+        L.call("cdetr_add_bcast", dpe[B * W + B * H: B * W + B * H + Q], dqx, Q, E, 0, 1, 1, 0,
+               dpe[B * W + B * H: B * W + B * H + Q], None)
+        L.call("cdetr_add_bcast", dpe[B * W + B * H + Q:], dqy, Q, E, 0, 1, 1, 0, dpe[B * W + B * H + Q:], None)
+        learned = cfg.spatial_prior == "learned"
+        de1 = self._mlp2_bwd("adapt_pos1d", dpe, "pos1d", need_de0=learned)
+        de2 = self._mlp2_bwd("adapt_pos2d", dqpos, "pos2d", need_de0=learned)
+        if learned:
+            ref = sv["ref"]
+            dref = self.buf("dref", (Q, 2), zero=True)
+            o = B * W + B * H
+            L.call("cdetr_sine_embed_bwd", ref, Q, 2, E, 0, E, de1[o:o + Q], dref)
+            L.call("cdetr_sine_embed_bwd", ref[:, 1:], Q, 2, E, 0, E, de1[o + Q:], dref[:, 1:])
+            L.call("cdetr_sine_embed_bwd", ref[:, 1:], Q, 2, 128, 0, E, de2, dref[:, 1:])
+            L.call("cdetr_sine_embed_bwd", ref, Q, 2, 128, 128, E, de2, dref)
+            for dr in sv["dref_list"]:   # inverse_sigmoid(ref) path of the box head, summed over the batch
+                L.call("cdetr_reduce_axis", dr, 1, B, Q, 2, 1, 1.0, None, 1, dref, None)
+            gp = self.grad_views["transformer.position.weight"]       # [Qp, 2]; patterns share positions
+            for p_ in range(P):
+                L.call("cdetr_colsum", dref[p_ * Qp:(p_ + 1) * Qp].reshape(1, -1), None, Qp * 2, 1, Qp * 2, gp.view(-1))
+        # ---- GroupNorm + projection (+ exemplar injection) + backbone
+        pj = sv["proj"]
+        pn = self.proj_name + ".1"
+        dpre = self.sbuf("dproj_pre", M, E)
+        L.call("cdetr_groupnorm_bwd", dx, pj["pre"], B, N, E, 32, self.params[pn + ".weight"], pj["gst"], None, dpre,
+               self.grad_views[pn + ".weight"], self.grad_views[pn + ".bias"])
+        lin = self.lins["proj"]
+        lin.wgrad(dpre, pj["proj_in"], M)
+        if not any(blk["train"] for blk in self.blocks):
+            return
+        ex = sv["ex"]
+        if cfg.stage == 2:
+            dcat = self.sbuf("dcat", M, 4096)
+            lin.dgrad(dpre, M, out_split=dcat)
+            g = self.sbuf("dfeat", M, 2048)
+            dp = self.buf("dp_ex", (B, 2048))
+            L.call("cdetr_exemplar_concat_bwd", dcat, ex["feat"], ex["p"], B, H, W, 2048, ex["yx"], ex["yx"].shape[0], dp,
+                   ex["feat"], g)
+        else:
+            g = self.sbuf("dfeat", M, 2048)
+            lin.dgrad(dpre, M, out_split=g, mask=ex["feat"])
+        self._backbone_bwd(g, B)

@@ -1,0 +1,579 @@
+"""Drop-in mirror of the reference's model/criterion API on top of the sm_100a engine.
+
+    from counting_detr_b200.models import build_model
+    model, criterion, postprocessors = build_model(args)      # same contract as models.build_model(args)
+
+Same constructor fields, forward signatures, output dict keys, parameter names and state_dict layout as
+the reference (A2/models/anchor_detr.py:34-140,143-445; A1/models/anchor_detr.py:317-409;
+A2/models/matcher.py:175-251), so `main.py` / `engine.py` of the reference run unchanged on it
+(INTEGRATION.md).  Every tensor op of the hot path is a call into libcdetr_sm100a.so; there is no
+eager/CPU fallback — constructing the model on a machine without the library or a GPU raises.
+"""
+import math
+import os
+import warnings
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib as L
+from .engine import RESNET50_BLOCKS, RESNET50_PLANES, Engine
+
+
+# --------------------------------------------------------------------------------------------- parameter tree
+class _Node(nn.Module):
+    """Name-space node: the modules below exist only to give parameters the reference's names."""
+
+
+def _walk(root, name):
+    parts = name.split(".")
+    m = root
+    for p in parts[:-1]:
+        nxt = m._modules.get(p)
+        if nxt is None:
+            nxt = _Node()
+            m.add_module(p, nxt)
+        m = nxt
+    return m, parts[-1]
+
+
+def _add_param(root, name, tensor):
+    m, leaf = _walk(root, name)
+    p = tensor if isinstance(tensor, nn.Parameter) else nn.Parameter(tensor)
+    m.register_parameter(leaf, p)
+    return p
+
+
+def _add_buffer(root, name, tensor):
+    m, leaf = _walk(root, name)
+    m.register_buffer(leaf, tensor)
+
+
+def _kaiming_uniform(shape, fan_in, gen=None):
+    bound = 1.0 / math.sqrt(fan_in)      # nn.Linear default (kaiming_uniform a=sqrt(5))
+    return (torch.rand(shape) * 2 - 1) * bound
+
+
+def _xavier_uniform(shape):
+    fan_out, fan_in = shape[0], int(np.prod(shape[1:]))
+    bound = math.sqrt(6.0 / (fan_in + fan_out))
+    return (torch.rand(shape) * 2 - 1) * bound
+
+
+def _linear(root, name, n_out, n_in, xavier=False, bias_zero=False):
+    _add_param(root, name + ".weight", _xavier_uniform((n_out, n_in)) if xavier else _kaiming_uniform((n_out, n_in), n_in))
+    _add_param(root, name + ".bias", torch.zeros(n_out) if bias_zero else _kaiming_uniform((n_out,), n_in))
+
+
+def _norm(root, name, c):
+    _add_param(root, name + ".weight", torch.ones(c))
+    _add_param(root, name + ".bias", torch.zeros(c))
+
+
+class AnchorDETR(nn.Module):
+    """AnchorDETR module of Counting-DETR (A2/models/anchor_detr.py:34-140; stage 1: A1 :34-113)."""
+
+    def __init__(self, args, stage):
+        super().__init__()
+        if getattr(args, "masks", False):
+            raise NotImplementedError("masks / DETRsegm are outside the hot path (SURVEY.md §2.1 #8)")
+        if getattr(args, "num_feature_levels", 1) != 1:
+            raise NotImplementedError("num_feature_levels > 1 is not supported (reference default is 1)")
+        if getattr(args, "attention_type", "RCDA") != "RCDA":
+            raise NotImplementedError("only attention_type='RCDA' is supported")
+        if getattr(args, "backbone", "resnet50") != "resnet50" or not getattr(args, "dilation", True):
+            raise NotImplementedError("only the ResNet-50 DC5 backbone is supported")
+        if args.hidden_dim != 256 or args.nheads != 8:
+            raise NotImplementedError("kernels are specialised for hidden_dim=256, nheads=8")
+        self.stage = stage
+        self.aux_loss = bool(getattr(args, "aux_loss", False)) if stage == 2 else False
+        self.spatial_prior = args.spatial_prior
+        self.num_pattern = args.num_query_pattern
+        self.num_position = args.num_query_position
+        self.train_backbone = args.lr_backbone > 0
+        self.cfg = _EngineCfg(stage, args, self.aux_loss)
+        E, F_ = args.hidden_dim, args.dim_feedforward
+        # ---- transformer (registration order follows the reference so state_dict order matches)
+        t = "transformer"
+        for i in range(args.enc_layers):
+            q = f"{t}.encoder_layers.{i}"
+            _add_param(self, q + ".self_attn.in_proj_weight", _xavier_uniform((5 * E, E)))
+            _add_param(self, q + ".self_attn.in_proj_bias", torch.zeros(5 * E))
+            _linear(self, q + ".self_attn.out_proj", E, E, bias_zero=True)
+            _norm(self, q + ".norm1", E)
+            _linear(self, q + ".ffn.linear1", F_, E)
+            _linear(self, q + ".ffn.linear2", E, F_)
+            _norm(self, q + ".ffn.norm2", E)
+        for i in range(args.dec_layers):
+            q = f"{t}.decoder_layers.{i}"
+            _add_param(self, q + ".cross_attn.in_proj_weight", _xavier_uniform((5 * E, E)))
+            _add_param(self, q + ".cross_attn.in_proj_bias", torch.zeros(5 * E))
+            _linear(self, q + ".cross_attn.out_proj", E, E, bias_zero=True)
+            _norm(self, q + ".norm1", E)
+            _add_param(self, q + ".self_attn.in_proj_weight", _xavier_uniform((3 * E, E)))
+            _add_param(self, q + ".self_attn.in_proj_bias", torch.zeros(3 * E))
+            _linear(self, q + ".self_attn.out_proj", E, E, bias_zero=True)
+            _norm(self, q + ".norm2", E)
+            _linear(self, q + ".ffn.linear1", F_, E)
+            _linear(self, q + ".ffn.linear2", E, F_)
+            _norm(self, q + ".ffn.norm2", E)
+        pat = "modify_pattern" if stage == 1 else "pattern"
+        _add_param(self, f"{t}.{pat}.weight", torch.randn(self.num_pattern, E))
+        if self.spatial_prior == "learned":
+            _add_param(self, f"{t}.position.weight", torch.rand(self.num_position, 2))
+        for name in ("adapt_pos2d", "adapt_pos1d"):
+            _linear(self, f"{t}.{name}.0", E, E)
+            _linear(self, f"{t}.{name}.2", E, E)
+        # heads: one module object repeated dec_layers times (A2/models/transformer.py:104-107)
+        prior = -math.log((1 - 0.01) / 0.01)
+        shared = {
+            "cls_embed.weight": nn.Parameter(_kaiming_uniform((2, E), E)),
+            "cls_embed.bias": nn.Parameter(torch.ones(2 if stage == 2 else 1) * prior),
+        }
+        for hname, nout in (("bbox_embed", 4),) + ((("bbox_variance", 2),) if stage == 2 else ()):
+            for j in range(3):
+                o = E if j < 2 else nout
+                shared[f"{hname}.layers.{j}.weight"] = nn.Parameter(_kaiming_uniform((o, E), E))
+                shared[f"{hname}.layers.{j}.bias"] = nn.Parameter(_kaiming_uniform((o,), E))
+        with torch.no_grad():
+            shared["bbox_embed.layers.2.weight"].zero_()
+            shared["bbox_embed.layers.2.bias"].zero_()
+            shared["bbox_embed.layers.2.bias"][2:] = -2.0
+            if stage == 2:
+                shared["bbox_variance.layers.2.weight"].fill_(0.01)
+                shared["bbox_variance.layers.2.bias"].fill_(0.01)
+        for hname in ("cls_embed", "bbox_embed") + (("bbox_variance",) if stage == 2 else ()):
+            for k in range(args.dec_layers):
+                for name, p in shared.items():
+                    mod, rest = name.split(".", 1)
+                    if mod == hname:
+                        _add_param(self, f"{t}.{hname}.{k}.{rest}", p)
+        # ---- projections
+        for name, cin in (("input_proj.0", 2048),):
+            _add_param(self, name + ".0.weight", _xavier_uniform((E, cin, 1, 1)))
+            _add_param(self, name + ".0.bias", torch.zeros(E))
+            _norm(self, name + ".1", E)
+        # ---- backbone (ResNet-50, FrozenBatchNorm buffers; A2/models/backbone.py:22-60,93-95)
+        b = "backbone.body"
+
+        def conv(name, cout, cin, k):
+            std = math.sqrt(2.0 / (cout * k * k))     # kaiming_normal fan_out, relu
+            _add_param(self, name, torch.randn(cout, cin, k, k) * std)
+
+        def fbn(name, c):
+            _add_buffer(self, name + ".weight", torch.ones(c))
+            _add_buffer(self, name + ".bias", torch.zeros(c))
+            _add_buffer(self, name + ".running_mean", torch.zeros(c))
+            _add_buffer(self, name + ".running_var", torch.ones(c))
+
+        conv(b + ".conv1.weight", 64, 3, 7)
+        fbn(b + ".bn1", 64)
+        inpl = 64
+        for li, (nb, planes) in enumerate(zip(RESNET50_BLOCKS, RESNET50_PLANES)):
+            for bi in range(nb):
+                q = f"{b}.layer{li + 1}.{bi}"
+                conv(q + ".conv1.weight", planes, inpl, 1); fbn(q + ".bn1", planes)
+                conv(q + ".conv2.weight", planes, planes, 3); fbn(q + ".bn2", planes)
+                conv(q + ".conv3.weight", planes * 4, planes, 1); fbn(q + ".bn3", planes * 4)
+                if bi == 0:
+                    conv(q + ".downsample.0.weight", planes * 4, inpl, 1); fbn(q + ".downsample.1", planes * 4)
+                inpl = planes * 4
+        if stage == 2:
+            _add_param(self, "aggr_input_proj.0.0.weight", _xavier_uniform((E, 4096, 1, 1)))
+            _add_param(self, "aggr_input_proj.0.0.bias", torch.zeros(E))
+            _norm(self, "aggr_input_proj.0.1", E)
+        for n, p in self.named_parameters():
+            if n.startswith("backbone.") and (not self.train_backbone or not any(k in n for k in ("layer2", "layer3", "layer4"))):
+                p.requires_grad_(False)
+        self._maybe_load_pretrained()
+        self._engine = None
+        self._param_version = None
+
+    def _maybe_load_pretrained(self):
+        path = os.path.join("pretrained_models", "resnet50-0676ba61.pth")   # A2/models/resnet.py:293-294
+        if os.path.exists(path):
+            sd = torch.load(path, map_location="cpu")
+            own = self.state_dict()
+            own.update({"backbone.body." + k: v for k, v in sd.items() if "backbone.body." + k in own})
+            self.load_state_dict(own)
+        else:
+            warnings.warn(f"{path} not found: ResNet-50 keeps its random initialisation")
+
+    # ------------------------------------------------------------------ engine plumbing
+    def engine(self):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise L.CdetrError("the hot path has no CPU fallback: move the model to a CUDA device (sm_100a)")
+        if self._engine is None or self._engine.dev != dev:
+            params = {}
+            for n, p in self.named_parameters():     # dedups the shared heads under their first name (index 0)
+                params[n] = p.data
+            buffers = {n: b for n, b in self.named_buffers()}
+            self._engine = Engine(self.cfg, params, buffers, dev, train_backbone=self.train_backbone)
+            self._names = [n for n, _ in self.named_parameters()]
+        return self._engine
+
+    def _current_version(self):
+        return tuple(p._version for p in self.parameters())
+
+    def forward(self, samples, points=None, rects=None):
+        """stage 2: model(samples, points=None, rects=[B,3,4]) -> (dict, reference_points)
+        stage 1: model(samples, scaled_sample_points[B,Q,2]) -> dict          (A1/A2 anchor_detr.py forward)"""
+        mask = None
+        if hasattr(samples, "decompose"):
+            samples, mask = samples.decompose()
+            if mask is not None and not bool(mask.any()):
+                mask = None
+        elif isinstance(samples, (list, tuple)):
+            samples = torch.stack(list(samples))
+        eng = self.engine()
+        ver = self._current_version()
+        if ver != self._param_version:       # weights changed (optimizer.step / load_state_dict): re-pack
+            eng.packed = False
+            self._param_version = ver
+        if self.stage == 2:
+            if rects is None:
+                raise ValueError("stage-2 forward needs exemplar rects")
+            B, _, S1, S2 = samples.shape
+            centres = exemplar_centres(rects, feat_size(S1), feat_size(S2))
+            pts = points
+        else:
+            centres = None
+            pts = points
+            if self.spatial_prior == "defined":
+                pts = torch.as_tensor(points).reshape(-1, 2) if points is not None else None
+        params = [p for p in self.parameters()]
+        outs = _ModelFn.apply(self, samples, centres, pts, mask, *params)
+        return self._pack_outputs(outs)
+
+    def _pack_outputs(self, flat):
+        n_per = 3 if self.stage == 2 else 2
+        ref = flat[-1]
+        layers = [flat[i * n_per:(i + 1) * n_per] for i in range((len(flat) - 1) // n_per)]
+        last = layers[-1]
+        if self.stage == 2:
+            out = {"pred_logits": last[0], "pred_boxes": last[1], "pred_vars": last[2]}
+            if self.aux_loss:
+                out["aux_outputs"] = [{"pred_logits": a[0], "pred_boxes": a[1]} for a in layers[:-1]]
+            return out, ref
+        return {"pred_logits": last[0], "pred_wh": last[1][..., 2:], "pred_points": last[1][..., :2]}
+
+
+def feat_size(s):
+    """spatial size of the DC5 layer4 map: 7x7 s2 p3 conv, 3x3 s2 p1 pool, two stride-2 stages."""
+    s = (s + 6 - 7) // 2 + 1
+    for _ in range(3):
+        s = (s - 1) // 2 + 1
+    return s
+
+
+def exemplar_centres(rects, H, W):
+    """int() truncation of the exemplar centres of SAMPLE 0 in fp32 (A2/models/backbone.py:122-128)."""
+    r0 = rects[0]
+    r0 = torch.as_tensor(np.asarray(r0.detach().cpu() if isinstance(r0, torch.Tensor) else r0), dtype=torch.float32)
+    out = []
+    for r in r0:
+        nx1, ny1, nx2, ny2 = r[0] * W, r[1] * H, r[2] * W, r[3] * H
+        out.append([int((ny1 + ny2) / 2), int((nx1 + nx2) / 2)])
+    return out
+
+
+class _EngineCfg:
+    def __init__(self, stage, args, aux_loss):
+        self.stage = stage
+        self.hidden_dim, self.nheads = args.hidden_dim, args.nheads
+        self.enc_layers, self.dec_layers = args.enc_layers, args.dec_layers
+        self.dim_feedforward = args.dim_feedforward
+        self.num_query_position, self.num_query_pattern = args.num_query_position, args.num_query_pattern
+        self.spatial_prior = args.spatial_prior
+        self.aux_loss = aux_loss
+
+
+class _ModelFn(torch.autograd.Function):
+    """One autograd node for the whole network: forward and backward are the engine's kernel sequences."""
+
+    @staticmethod
+    def forward(ctx, module, image, centres, points, mask, *params):
+        eng = module.engine()
+        dev = eng.dev
+        image = image.to(dev, torch.float32)
+        yx = torch.tensor(centres, dtype=torch.int32, device=dev) if centres is not None else None
+        eng.zero_grad()
+        outs, dims = eng.forward(image, yx, points, mask)
+        B, Q = dims["B"], dims["Q"]
+        flat = []
+        for o in outs:
+            flat.append(o["logits"].view(B, Q, 2).clone())
+            flat.append(o["boxes"].view(B, Q, 4).clone())
+            if module.stage == 2:
+                flat.append(o["vars"].view(B, Q, 2).clone())
+        ref = eng.saved["ref"].unsqueeze(0).expand(B, Q, 2).clone()
+        ctx.module = module
+        ctx.n_out = len(outs)
+        ctx.mark_non_differentiable(ref)
+        return tuple(flat) + (ref,)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        module = ctx.module
+        eng = module.engine()
+        n_per = 3 if module.stage == 2 else 2
+        grads = []
+        for i in range(ctx.n_out):
+            g = gouts[i * n_per:(i + 1) * n_per]
+            d = {}
+            if g[0] is not None:
+                d["logits"] = g[0].contiguous().view(-1, 2)
+            if g[1] is not None:
+                d["boxes"] = g[1].contiguous().view(-1, 4)
+            if module.stage == 2 and g[2] is not None:
+                d["vars"] = g[2].contiguous().view(-1, 2)
+            grads.append(d)
+        eng.backward(grads)
+        # parameter gradients live in the engine's flat buffer (one allocation: all-reduce friendly)
+        out = []
+        for n, p in zip(module._names, module.parameters()):
+            gv = eng.grad_views.get(n)
+            out.append(gv if (gv is not None and p.requires_grad) else None)
+        return (None, None, None, None, None) + tuple(out)
+
+
+# --------------------------------------------------------------------------------------------- matcher / criteria
+class _Targets:
+    """Device-resident concatenated target boxes + prefix offsets (static buffers, graph friendly)."""
+
+    def __init__(self):
+        self.boxes = None
+        self.off = None
+        self.lens = None
+
+    def update(self, targets, dev):
+        lens = [int(t["boxes"].shape[0]) for t in targets]
+        total = max(sum(lens), 1)
+        if self.boxes is None or self.boxes.shape[0] < total or self.boxes.device != dev:
+            self.boxes = torch.zeros(total, 4, device=dev)
+        if self.off is None or self.off.numel() != len(lens) + 1 or self.off.device != dev:
+            self.off = torch.zeros(len(lens) + 1, dtype=torch.int32, device=dev)
+        if sum(lens):
+            cat = torch.cat([t["boxes"].to(dev, torch.float32) for t in targets if t["boxes"].shape[0]])
+            self.boxes[: cat.shape[0]].copy_(cat)
+        if lens != self.lens:
+            self.off.copy_(torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32))
+            self.lens = lens
+        return lens
+
+
+class HungarianMatcher(nn.Module):
+    """OriginalHungarianMatcher (A2/models/matcher.py:175-247) / HungarianMatcher (A1 :19-95): the cost
+    block and scipy's exact assignment both run on the device."""
+
+    def __init__(self, cost_class: float = 1, cost_bbox: float = 1, cost_giou: float = 1):
+        super().__init__()
+        assert cost_class != 0 or cost_bbox != 0 or cost_giou != 0, "all costs cant be 0"
+        self.cost_class, self.cost_bbox, self.cost_giou = cost_class, cost_bbox, cost_giou
+        self._tg = _Targets()
+        self._bufs = {}
+
+    def _buf(self, name, shape, dtype, dev):
+        key = (name, tuple(shape), dtype, dev)
+        if key not in self._bufs:
+            self._bufs[key] = torch.zeros(*shape, dtype=dtype, device=dev)
+        return self._bufs[key]
+
+    @torch.no_grad()
+    def match_device(self, logits, boxes, targets):
+        """returns (idx_q [B,K] int64, idx_t [B,K] int64, n [B] int32, lens) on the device; no host sync."""
+        dev = logits.device
+        B, Q, C = logits.shape
+        lens = self._tg.update(targets, dev)
+        Tmax = max(lens) if lens else 0
+        K = max(min(Q, Tmax), 1)
+        cost = self._buf("cost", (B, Q * max(Tmax, 1)), torch.float32, dev)
+        oq = self._buf("oq", (B, K), torch.int64, dev)
+        ot = self._buf("ot", (B, K), torch.int64, dev)
+        on = self._buf("on", (B,), torch.int32, dev)
+        status = self._buf("status", (1,), torch.int32, dev)
+        lg = logits.detach().contiguous().float()
+        bx = boxes.detach().contiguous().float()
+        L.call("cdetr_match_cost", lg, C, bx, self._tg.boxes, self._tg.off, B, Q, Tmax, self.cost_class,
+               self.cost_bbox, self.cost_giou, cost)
+        L.call("cdetr_lsap", cost, self._tg.off, B, Q, Tmax, oq, ot, on, status)
+        return oq, ot, on, lens
+
+    @torch.no_grad()
+    def forward(self, outputs, targets):
+        """Reference contract: list of (index_i, index_j) int64 CPU tensors (A2/models/matcher.py:247)."""
+        oq, ot, on, lens = self.match_device(outputs["pred_logits"], outputs["pred_boxes"], targets)
+        oq, ot, on = oq.cpu(), ot.cpu(), on.cpu()
+        return [(oq[b, : on[b]].clone(), ot[b, : on[b]].clone()) for b in range(len(lens))]
+
+
+OriginalHungarianMatcher = HungarianMatcher
+
+
+def _world_size():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class _SetLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, crit, logits, boxes, pvars, targets, num_boxes):
+        dev = logits.device
+        B, Q, _ = logits.shape
+        oq, ot, on, lens = crit.matcher.match_device(logits, boxes, targets)
+        K = oq.shape[1]
+        tg = crit.matcher._tg
+        out6 = torch.empty(6, device=dev)
+        g_ce = torch.empty(B, Q, 2, device=dev); g_bbox = torch.empty(B, Q, 4, device=dev)
+        g_giou = torch.empty(B, Q, 4, device=dev); g_vb = torch.empty(B, Q, 4, device=dev)
+        g_vv = torch.empty(B, Q, 2, device=dev); matched = torch.empty(B * Q, dtype=torch.uint8, device=dev)
+        L.call("cdetr_set_loss_fwd", logits.contiguous(), boxes.contiguous(), pvars.contiguous(), tg.boxes, tg.off, oq,
+               ot, on, B, Q, K, num_boxes, crit.focal_alpha, out6, g_ce, g_bbox, g_giou, g_vb, g_vv, matched)
+        ctx.save_for_backward(g_ce, g_bbox, g_giou, g_vb, g_vv)
+        ctx.rows = B * Q
+        crit.last_indices = (oq, ot, on)
+        outs = tuple(out6[i] for i in range(6))
+        ctx.mark_non_differentiable(outs[1], outs[4])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_ce_, g_err, g_bbox_, g_giou_, g_card, g_var_):
+        g_ce, g_bbox, g_giou, g_vb, g_vv = ctx.saved_tensors
+        dev = g_ce.device
+        z = torch.zeros((), device=dev)
+        up = torch.stack([g if g is not None else z for g in (g_ce_, g_bbox_, g_giou_, g_var_)]).float().contiguous()
+        dl = torch.empty_like(g_ce); db = torch.empty_like(g_bbox); dv = torch.empty_like(g_vv)
+        L.call("cdetr_set_loss_bwd", up, g_ce, g_bbox, g_giou, g_vb, g_vv, ctx.rows, dl, db, dv)
+        return None, dl, db, dv, None, None
+
+
+class SetCriterion(nn.Module):
+    """SetCriterion of stage 2 (A2/models/anchor_detr.py:143-367): labels (focal), boxes (L1 + GIoU),
+    cardinality, vars (Laplace-style w/h uncertainty).  One matcher launch pair + one loss launch."""
+
+    def __init__(self, num_classes, matcher, weight_dict, losses, focal_alpha=0.25):
+        super().__init__()
+        if num_classes != 1:
+            raise NotImplementedError("Counting-DETR uses a single object class")
+        unsupported = set(losses) - {"labels", "boxes", "cardinality", "vars"}
+        if unsupported:
+            raise NotImplementedError(f"losses {sorted(unsupported)} are outside the hot path")
+        self.num_classes, self.matcher, self.weight_dict = num_classes, matcher, weight_dict
+        self.losses, self.focal_alpha = losses, focal_alpha
+        self.last_indices = None
+
+    def forward(self, outputs, targets):
+        if "aux_outputs" in outputs:
+            # the reference asserts "pred_vars" in every aux dict, which they never contain
+            # (A2/models/anchor_detr.py:140,268): stage 2 is only runnable with --no_aux_loss
+            raise AssertionError("aux_outputs lack 'pred_vars': run stage 2 with --no_aux_loss (reference behaviour)")
+        num_boxes = sum(len(t["labels"]) for t in targets)
+        ws = _world_size()
+        if ws > 1:
+            nb = torch.as_tensor([num_boxes], dtype=torch.float, device=outputs["pred_logits"].device)
+            torch.distributed.all_reduce(nb)
+            num_boxes = nb.item()
+        num_boxes = max(num_boxes / ws, 1.0)
+        ce, err, bbox, giou, card, var = _SetLossFn.apply(self, outputs["pred_logits"], outputs["pred_boxes"],
+                                                         outputs["pred_vars"], targets, float(num_boxes))
+        res = {}
+        for name in self.losses:
+            if name == "labels":
+                res["loss_ce"], res["class_error"] = ce, err
+            elif name == "boxes":
+                res["loss_bbox"], res["loss_giou"] = bbox, giou
+            elif name == "cardinality":
+                res["cardinality_error"] = card
+            elif name == "vars":
+                res["loss_variance"] = var
+        return res
+
+
+class _BBoxLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_wh, points, whs):
+        n = pred_wh.numel() // 2
+        dev = pred_wh.device
+        out2 = torch.empty(2, device=dev); gw = torch.empty(n, 2, device=dev); gg = torch.empty(n, 2, device=dev)
+        L.call("cdetr_bbox_loss_fwd", pred_wh.contiguous(), points.contiguous().float(), whs.contiguous().float(), n,
+               out2, gw, gg)
+        ctx.save_for_backward(gw, gg)
+        ctx.shape = pred_wh.shape
+        return out2[0], out2[1]
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        gw, gg = ctx.saved_tensors
+        z = torch.zeros((), device=gw.device)
+        up = torch.stack([g0 if g0 is not None else z, g1 if g1 is not None else z]).float().contiguous()
+        d = torch.empty_like(gw)
+        L.call("cdetr_bbox_loss_bwd", up, gw, gg, gw.shape[0], d)
+        return d.view(ctx.shape), None, None
+
+
+class BoundingBoxCriterion(nn.Module):
+    """Stage-1 criterion (A1/models/anchor_detr.py:317-337): L1(w,h) + (1 - GIoU) of boxes built from the
+    ground-truth points and the predicted sizes; no matching."""
+
+    def __init__(self):
+        super().__init__()
+        self.weight_dict = {"loss_wh": 1, "loss_giou": 0.4}
+
+    def forward(self, outputs, targets):
+        dev = outputs["pred_wh"].device
+        lw, lg = _BBoxLossFn.apply(outputs["pred_wh"], targets["points"].to(dev), targets["whs"].to(dev))
+        return {"loss_wh": lw, "loss_giou": lg}
+
+
+class PostProcess(nn.Module):
+    """PostProcess (A2/models/anchor_detr.py:370-402): top-100 over the flattened (query, class) scores.
+    Not on the training hot path (no live caller in the reference); plain tensor ops."""
+
+    @torch.no_grad()
+    def forward(self, outputs, target_sizes):
+        out_logits, out_bbox = outputs["pred_logits"], outputs["pred_boxes"]
+        assert len(out_logits) == len(target_sizes)
+        assert target_sizes.shape[1] == 2
+        prob = out_logits.sigmoid()
+        scores, idx = torch.topk(prob.view(out_logits.shape[0], -1), 100, dim=1)
+        qi = idx // out_logits.shape[2]
+        labels = idx % out_logits.shape[2]
+        cx, cy, w, h = out_bbox.unbind(-1)
+        xyxy = torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], -1)
+        xyxy = torch.gather(xyxy, 1, qi.unsqueeze(-1).repeat(1, 1, 4))
+        img_h, img_w = target_sizes.unbind(1)
+        xyxy = xyxy * torch.stack([img_w, img_h, img_w, img_h], dim=1)[:, None, :]
+        return [{"scores": s, "labels": l, "boxes": b} for s, l, b in zip(scores, labels, xyxy)]
+
+
+def _stage_of(args):
+    # stage 2 args carry the SetCriterion coefficients (A2/main.py:105-120); stage 1 args do not
+    return 2 if hasattr(args, "variance_loss_coef") or hasattr(args, "cost_class") else 1
+
+
+def build(args, stage=None):
+    """models.build_model(args) of the reference (A2/models/anchor_detr.py:405-445, A1 :375-409)."""
+    stage = stage or _stage_of(args)
+    device = torch.device(args.device)
+    model = AnchorDETR(args, stage)
+    if stage == 2:
+        matcher = HungarianMatcher(args.cost_class, args.cost_bbox, args.cost_giou)
+        weight_dict = {"loss_ce": args.cls_loss_coef, "loss_bbox": args.bbox_loss_coef,
+                       "loss_giou": args.giou_loss_coef, "loss_variance": args.variance_loss_coef}
+        if getattr(args, "aux_loss", False):
+            aux = {}
+            for i in range(args.dec_layers - 1):
+                aux.update({k + f"_{i}": v for k, v in weight_dict.items()})
+            aux.update({k + "_enc": v for k, v in weight_dict.items()})
+            weight_dict.update(aux)
+        criterion = SetCriterion(1, matcher, weight_dict, ["labels", "boxes", "cardinality", "vars"],
+                                 focal_alpha=args.focal_alpha)
+    else:
+        criterion = BoundingBoxCriterion()
+    criterion.to(device)
+    return model, criterion, {"bbox": PostProcess()}
+
+
+build_model = build
