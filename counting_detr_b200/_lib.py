@@ -71,6 +71,12 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+# kernel-launch accounting (bench.py's gpu_launches) and optional per-GEMM event trace (bench.py's roofline)
+COUNTER = {"launches": 0}
+_LAUNCHES = {"cdetr_exemplar_concat": 2, "cdetr_exemplar_concat_bwd": 2, "cdetr_rcda_bwd": 3, "cdetr_mha_bwd": 2}
+GEMM_TRACE = None
+
+
 def gemm(a, b, M, N, K, mode=0, out_f32=None, out_split=None, bias=None, row_scale=None,
          add_split=None, add_f32=None, mask=None, relu=False, accumulate=False, block_n=0, split_k=1):
     """cdetr_gemm: see include/cdetr.h. a, b, add_split, mask, out_split are split tensors [2, rows, ld]."""
@@ -87,6 +93,14 @@ def gemm(a, b, M, N, K, mode=0, out_f32=None, out_split=None, bias=None, row_sca
     g.out_f32 = _ptr(out_f32)
     g.ld_out_f32 = out_f32.stride(0) if out_f32 is not None else 0
     g.out_split = split_view(out_split)
+    COUNTER["launches"] += 1
+    if GEMM_TRACE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib().cdetr_gemm(C.byref(g), stream_ptr()), "cdetr_gemm")
+        e1.record()
+        GEMM_TRACE.append((M, N, K, e0, e1))
+        return
     check(lib().cdetr_gemm(C.byref(g), stream_ptr()), "cdetr_gemm")
 
 
@@ -171,6 +185,7 @@ def call(name, *args):
             conv.append(float(a))
         else:
             conv.append(int(a))
+    COUNTER["launches"] += _LAUNCHES.get(name, 1)
     check(_bind(name)(*conv, torch.cuda.current_stream().cuda_stream), name)
 
 

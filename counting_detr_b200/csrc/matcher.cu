@@ -283,8 +283,7 @@ extern "C" int cdetr_lsap(const float* cost, const int* tgt_off, int B, int Q, i
     if (ncap > 2048) nt = 1024;
     const size_t smem = lsap_smem(ncap, nt);
     CDETR_CHECK_ARG(smem <= 200 * 1024, "lsap: problem too large for shared memory (n=%d)", ncap);
-    CDETR_CHECK_CUDA(cudaFuncSetAttribute(lsap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          200 * 1024));
+    { static bool once_lsap_kernel_false_ = false; if (!once_lsap_kernel_false_) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(lsap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); once_lsap_kernel_false_ = true; } }
     lsap_kernel<false><<<B, nt, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status);
   }
   CDETR_CHECK_LAUNCH();

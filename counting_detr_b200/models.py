@@ -189,6 +189,11 @@ class AnchorDETR(nn.Module):
         self._maybe_load_pretrained()
         self._engine = None
         self._param_version = None
+        self._grad_group = None
+
+    def enable_grad_sync(self, group):
+        """Average parameter gradients over `group` (torch.distributed, NCCL) at the end of every backward."""
+        self._grad_group = group
 
     def _maybe_load_pretrained(self):
         path = os.path.join("pretrained_models", "resnet50-0676ba61.pth")   # A2/models/resnet.py:293-294
@@ -298,7 +303,13 @@ class _ModelFn(torch.autograd.Function):
         eng = module.engine()
         dev = eng.dev
         image = image.to(dev, torch.float32)
-        yx = torch.tensor(centres, dtype=torch.int32, device=dev) if centres is not None else None
+        yx = None
+        if centres is not None:
+            # static device copy, refreshed only when the centres change (keeps the step graph-capturable)
+            if getattr(module, "_centres_host", None) != centres:
+                module._centres_dev = torch.tensor(centres, dtype=torch.int32, device=dev)
+                module._centres_host = [list(c) for c in centres]
+            yx = module._centres_dev
         eng.zero_grad()
         outs, dims = eng.forward(image, yx, points, mask)
         B, Q = dims["B"], dims["Q"]
@@ -331,6 +342,12 @@ class _ModelFn(torch.autograd.Function):
                 d["vars"] = g[2].contiguous().view(-1, 2)
             grads.append(d)
         eng.backward(grads)
+        if module._grad_group is not None:
+            # data parallel: one all-reduce of the flat gradient buffer (the path shards by image)
+            import torch.distributed as dist
+            flat = eng.grad_flat[: eng.n_param_grad]
+            dist.all_reduce(flat, group=module._grad_group)
+            L.call("cdetr_scale", flat, flat.numel(), 1.0 / dist.get_world_size(module._grad_group))
         # parameter gradients live in the engine's flat buffer (one allocation: all-reduce friendly)
         out = []
         for n, p in zip(module._names, module.parameters()):
