@@ -156,6 +156,7 @@ def run_ours(args):
     from counting_detr_b200 import _lib as L
     from counting_detr_b200.models import build_model
     from counting_detr_b200 import synthetic as SY
+    from counting_detr_b200.parallel import shard_seed
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -171,7 +172,7 @@ def run_ours(args):
     model.to(dev).train(); crit.train()
     if world > 1:
         model.enable_grad_sync(dist.group.WORLD)
-    inp = SY.make_inputs(B, S, T=T, seed=rank, stage=st, Q=Q)
+    inp = SY.make_inputs(B, S, T=T, seed=shard_seed(0, rank), stage=st, Q=Q)
     img_h = inp["image"].pin_memory()
     img_d = img_h.to(dev)
     rects_h = inp.get("rects")

@@ -344,10 +344,9 @@ class _ModelFn(torch.autograd.Function):
         eng.backward(grads)
         if module._grad_group is not None:
             # data parallel: one all-reduce of the flat gradient buffer (the path shards by image)
-            import torch.distributed as dist
-            flat = eng.grad_flat[: eng.n_param_grad]
-            dist.all_reduce(flat, group=module._grad_group)
-            L.call("cdetr_scale", flat, flat.numel(), 1.0 / dist.get_world_size(module._grad_group))
+            from .parallel import average_flat_grads
+            average_flat_grads(eng.grad_flat[: eng.n_param_grad], module._grad_group,
+                               scale_fn=lambda t, s: L.call("cdetr_scale", t, t.numel(), s))
         # parameter gradients live in the engine's flat buffer (one allocation: all-reduce friendly)
         out = []
         for n, p in zip(module._names, module.parameters()):
