@@ -6,7 +6,7 @@
 // One CTA computes one 128 x BN output tile (optionally one K-split of it):
 //   warp 0     TMA producer  : cp.async.bulk.tensor (SWIZZLE_128B) of the hi+lo planes of A and B
 //   warp 1     MMA issuer    : per 64-wide k block, 4 k-steps x 3 tcgen05.mma (hi*lo, lo*hi, hi*hi)
-//   warps 2-5  epilogue      : tcgen05.ld of the fp32 accumulator (one TMEM lane = one row per thread)
+//   warps 2-9  epilogue      : tcgen05.ld of the fp32 accumulator (one TMEM lane = one row per thread)
 //                              -> row-scale / bias / residual / ReLU / ReLU-mask -> fp32 and/or split-bf16
 // smem stages are recycled through full/empty mbarriers; the accumulator lives in TMEM.
 //
@@ -18,7 +18,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (2 per TMEM lane quarter)
 constexpr int MAX_STAGES = 6;
 
 struct EpilogueArgs {
@@ -52,7 +52,7 @@ struct KernelArgs {
 };
 
 template <bool NT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 3)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const KernelArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -159,131 +159,144 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
+    // Each warp owns 32 accumulator rows (its TMEM lane quarter) and half of the tile's columns.  Per
+    // 32-column chunk: TMEM -> registers (one row per thread) -> per-warp shared-memory staging (the
+    // pipeline stages are idle once the accumulator is complete) -> re-read with 4 lanes per row so that
+    // every global access of the warp covers 8 rows x 128 contiguous bytes (fp32) / 64 bytes (bf16 plane).
     const EpilogueArgs& ep = args.ep;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < args.M;
-    const float rs = (ep.row_scale != nullptr && row_ok) ? ep.row_scale[row] : 1.0f;
+    const int half = (warp - 2) >> 2;  // two warps share a quarter and split the tile's columns
+    const int nchunks = BN / 16;
+    const int c_begin = half == 0 ? 0 : ((nchunks + 1) / 2) * 16;
+    const int c_end = half == 0 ? ((nchunks + 1) / 2) * 16 : BN;
+    constexpr int STG_LD = 33;
+    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * STG_LD);
+    const int row_t = m0 + q * 32 + lane;  // row held by this thread in the TMEM phase
+    const float rs = (ep.row_scale != nullptr && row_t < args.M) ? ep.row_scale[row_t] : 1.0f;
     const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool vec_ok = ((ep.ld_out_f32 & 3) == 0) && ((ep.ld_out_split & 7) == 0) &&
                         ((ep.ld_add & 7) == 0) && ((ep.ld_add_f32 & 3) == 0) &&
                         ((ep.ld_mask & 7) == 0);
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(taddr_row + (uint32_t)c0, r);
-      tmem_ld_wait();
-      const int nb = n0 + c0;
-      if (!row_ok || nb >= args.N) continue;
-      float v[16];
+    const int g8 = (lane & 3) * 8;  // column group of this lane in the coalesced phase
+    const int rr = lane >> 2;       // row sub-index 0..7
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * rs;
-      const bool full = vec_ok && (nb + 16 <= args.N);
-      if (ep.bias != nullptr) {
+      for (int u = 0; u < 2; ++u) {
+        if (c0 + 16 * u < c_end) {  // warp-uniform
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(taddr_row + (uint32_t)(c0 + 16 * u), r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (nb + j < args.N) v[j] += __ldg(ep.bias + nb + j);
-      }
-      if (ep.add_hi != nullptr) {
-        const __nv_bfloat16* ph = ep.add_hi + (int64_t)row * ep.ld_add + nb;
-        const __nv_bfloat16* pl = ep.add_lo + (int64_t)row * ep.ld_add + nb;
-        if (full) {
-          uint4 h[2], l[2];
-          h[0] = __ldg(reinterpret_cast<const uint4*>(ph));
-          h[1] = __ldg(reinterpret_cast<const uint4*>(ph) + 1);
-          l[0] = __ldg(reinterpret_cast<const uint4*>(pl));
-          l[1] = __ldg(reinterpret_cast<const uint4*>(pl) + 1);
-          const uint32_t* hw = reinterpret_cast<const uint32_t*>(h);
-          const uint32_t* lw = reinterpret_cast<const uint32_t*>(l);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[2 * j] += bf16_bits_to_float(hw[j] & 0xffffu) + bf16_bits_to_float(lw[j] & 0xffffu);
-            v[2 * j + 1] += bf16_bits_to_float(hw[j] >> 16) + bf16_bits_to_float(lw[j] >> 16);
-          }
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < args.N) v[j] += join_bf16(ph[j], pl[j]);
+          for (int j = 0; j < 16; ++j) stg[lane * STG_LD + 16 * u + j] = __uint_as_float(r[j]) * rs;
         }
       }
-      if (ep.add_f32 != nullptr) {
-        const float* pa = ep.add_f32 + (int64_t)row * ep.ld_add_f32 + nb;
-        if (full) {
+      __syncwarp();
+      const int cl = c0 + g8;     // tile-local first column of this lane's 8-vector
+      const int nb = n0 + cl;
+      if (cl < c_end && nb < args.N) {
+        const bool full = vec_ok && (nb + 8 <= args.N);
+        float bias8[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(pa) + j);
-            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+        for (int j = 0; j < 8; ++j) bias8[j] = (ep.bias != nullptr && nb + j < args.N) ? __ldg(ep.bias + nb + j) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rl = rr + 8 * i;
+          const int row = m0 + q * 32 + rl;
+          if (row >= args.M) continue;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = stg[rl * STG_LD + g8 + j] + bias8[j];
+          if (ep.add_hi != nullptr) {
+            const __nv_bfloat16* ph = ep.add_hi + (int64_t)row * ep.ld_add + nb;
+            const __nv_bfloat16* pl = ep.add_lo + (int64_t)row * ep.ld_add + nb;
+            if (full) {
+              const uint4 h = __ldg(reinterpret_cast<const uint4*>(ph));
+              const uint4 l = __ldg(reinterpret_cast<const uint4*>(pl));
+              const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[2 * j] += bf16_bits_to_float(hw[j] & 0xffffu) + bf16_bits_to_float(lw[j] & 0xffffu);
+                v[2 * j + 1] += bf16_bits_to_float(hw[j] >> 16) + bf16_bits_to_float(lw[j] >> 16);
+              }
+            } else {
+              for (int j = 0; j < 8; ++j)
+                if (nb + j < args.N) v[j] += join_bf16(ph[j], pl[j]);
+            }
           }
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < args.N) v[j] += pa[j];
+          if (ep.add_f32 != nullptr) {
+            const float* pa = ep.add_f32 + (int64_t)row * ep.ld_add_f32 + nb;
+            if (full) {
+              const float4 t0 = __ldg(reinterpret_cast<const float4*>(pa));
+              const float4 t1 = __ldg(reinterpret_cast<const float4*>(pa) + 1);
+              v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
+              v[4] += t1.x; v[5] += t1.y; v[6] += t1.z; v[7] += t1.w;
+            } else {
+              for (int j = 0; j < 8; ++j)
+                if (nb + j < args.N) v[j] += pa[j];
+            }
+          }
+          if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+          }
+          if (ep.mask_hi != nullptr) {
+            const __nv_bfloat16* pm = ep.mask_hi + (int64_t)row * ep.ld_mask + nb;
+            if (full) {
+              const uint4 h = __ldg(reinterpret_cast<const uint4*>(pm));
+              const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (!(bf16_bits_to_float(hw[j] & 0xffffu) > 0.0f)) v[2 * j] = 0.0f;
+                if (!(bf16_bits_to_float(hw[j] >> 16) > 0.0f)) v[2 * j + 1] = 0.0f;
+              }
+            } else {
+              for (int j = 0; j < 8; ++j)
+                if (nb + j < args.N && !(__bfloat162float(pm[j]) > 0.0f)) v[j] = 0.0f;
+            }
+          }
+          if (ep.out_f32 != nullptr) {
+            float* po = ep.out_f32 + (int64_t)row * ep.ld_out_f32 + nb;
+            if (ep.atomic) {
+              if (full) {
+                atomicAdd(reinterpret_cast<float4*>(po), make_float4(v[0], v[1], v[2], v[3]));
+                atomicAdd(reinterpret_cast<float4*>(po) + 1, make_float4(v[4], v[5], v[6], v[7]));
+              } else {
+                for (int j = 0; j < 8; ++j)
+                  if (nb + j < args.N) atomicAdd(po + j, v[j]);
+              }
+            } else if (full) {
+              reinterpret_cast<float4*>(po)[0] = make_float4(v[0], v[1], v[2], v[3]);
+              reinterpret_cast<float4*>(po)[1] = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+              for (int j = 0; j < 8; ++j)
+                if (nb + j < args.N) po[j] = v[j];
+            }
+          }
+          if (ep.out_hi != nullptr) {
+            __nv_bfloat16* ph = ep.out_hi + (int64_t)row * ep.ld_out_split + nb;
+            __nv_bfloat16* pl = ep.out_lo + (int64_t)row * ep.ld_out_split + nb;
+            if (full) {
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(v[2 * j], h0, l0);
+                split_bf16(v[2 * j + 1], h1, l1);
+                hw[j] = pack_bf16x2(h0, h1);
+                lw[j] = pack_bf16x2(l0, l1);
+              }
+              *reinterpret_cast<uint4*>(ph) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(pl) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            } else {
+              for (int j = 0; j < 8; ++j)
+                if (nb + j < args.N) split_bf16(v[j], ph[j], pl[j]);
+            }
+          }
         }
       }
-      if (ep.relu) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
-      }
-      if (ep.mask_hi != nullptr) {
-        const __nv_bfloat16* pm = ep.mask_hi + (int64_t)row * ep.ld_mask + nb;
-        if (full) {
-          uint4 h[2];
-          h[0] = __ldg(reinterpret_cast<const uint4*>(pm));
-          h[1] = __ldg(reinterpret_cast<const uint4*>(pm) + 1);
-          const uint32_t* hw = reinterpret_cast<const uint32_t*>(h);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (!(bf16_bits_to_float(hw[j] & 0xffffu) > 0.0f)) v[2 * j] = 0.0f;
-            if (!(bf16_bits_to_float(hw[j] >> 16) > 0.0f)) v[2 * j + 1] = 0.0f;
-          }
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < args.N && !(__bfloat162float(pm[j]) > 0.0f)) v[j] = 0.0f;
-        }
-      }
-      if (ep.out_f32 != nullptr) {
-        float* po = ep.out_f32 + (int64_t)row * ep.ld_out_f32 + nb;
-        if (ep.atomic) {
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              atomicAdd(reinterpret_cast<float4*>(po) + j,
-                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-          } else {
-            for (int j = 0; j < 16; ++j)
-              if (nb + j < args.N) atomicAdd(po + j, v[j]);
-          }
-        } else if (full) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            reinterpret_cast<float4*>(po)[j] =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < args.N) po[j] = v[j];
-        }
-      }
-      if (ep.out_hi != nullptr) {
-        __nv_bfloat16* ph = ep.out_hi + (int64_t)row * ep.ld_out_split + nb;
-        __nv_bfloat16* pl = ep.out_lo + (int64_t)row * ep.ld_out_split + nb;
-        if (full) {
-          uint32_t hw[8], lw[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v[2 * j], h0, l0);
-            split_bf16(v[2 * j + 1], h1, l1);
-            hw[j] = pack_bf16x2(h0, h1);
-            lw[j] = pack_bf16x2(l0, l1);
-          }
-          reinterpret_cast<uint4*>(ph)[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          reinterpret_cast<uint4*>(ph)[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-          reinterpret_cast<uint4*>(pl)[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-          reinterpret_cast<uint4*>(pl)[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (nb + j < args.N) split_bf16(v[j], ph[j], pl[j]);
-        }
-      }
+      __syncwarp();
     }
   }
 
@@ -403,8 +416,15 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   const uint32_t smem_budget = 227u * 1024u - 1024u - tail_bytes;
   int stages = (int)(smem_budget / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages > kb_per_split) stages = kb_per_split < 2 ? 2 : kb_per_split;
-  if ((uint32_t)stages * stage_bytes > smem_budget) stages = (int)(smem_budget / stage_bytes);
+  if (kb_per_split <= 8) {
+    // short K loops are epilogue/latency bound: keep the CTA small enough for 2-3 CTAs per SM so that one
+    // CTA's epilogue overlaps another's loads and MMAs (TMEM: each CTA holds <= 256 of the 512 columns)
+    int s2 = (int)((113u * 1024u) / stage_bytes);
+    if (s2 < 1) s2 = 1;
+    if (stages > s2) stages = s2;
+  }
+  if (stages > kb_per_split) stages = kb_per_split;
+  if (stages < 1) stages = 1;
   CDETR_CHECK_ARG(stages >= 1, "gemm: tile does not fit shared memory");
   ka.stages = stages;
   const size_t smem_bytes = (size_t)stages * stage_bytes + tail_bytes + 1024;

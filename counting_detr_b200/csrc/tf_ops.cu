@@ -146,20 +146,49 @@ __global__ void combine_bcast_kernel(const float* __restrict__ a, const float* _
   }
 }
 
-// out[n] += sum_m x[m,n]  (bias gradients); x fp32 [M, N] or split.  grid.x tiles rows, block covers columns.
+// out[n] += sum_m x[m,n]  (bias gradients); x fp32 [M, N] or split.  8 warps stride the rows of a row block,
+// each lane owns 8 consecutive columns (16-byte loads per plane); warps are reduced through shared memory and
+// the CTA issues one atomic per column.
 __global__ void colsum_kernel(const float* __restrict__ x, const __nv_bfloat16* x_hi,
                               const __nv_bfloat16* x_lo, int64_t ld, int64_t M, int N, int rows_per_cta,
                               float* __restrict__ out) {
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r1 = min(M, r0 + rows_per_cta);
-  for (int n = blockIdx.y * blockDim.x + threadIdx.x; n < N; n += gridDim.y * blockDim.x) {
-    float s = 0.0f;
-    if (x) {
-      for (int64_t r = r0; r < r1; ++r) s += x[r * ld + n];
-    } else {
-      for (int64_t r = r0; r < r1; ++r) s += join_bf16(x_hi[r * ld + n], x_lo[r * ld + n]);
+  const int c0 = blockIdx.y * 256 + lane * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool vec = x == nullptr && (ld % 8 == 0) && c0 + 8 <= N &&
+                   ((reinterpret_cast<uintptr_t>(x_hi) | reinterpret_cast<uintptr_t>(x_lo)) & 15) == 0;
+  if (vec) {
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(x_hi + r * ld + c0));
+      const uint4 l = __ldg(reinterpret_cast<const uint4*>(x_lo + r * ld + c0));
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += bf16_bits_to_float(hw[j] & 0xffffu) + bf16_bits_to_float(lw[j] & 0xffffu);
+        acc[2 * j + 1] += bf16_bits_to_float(hw[j] >> 16) + bf16_bits_to_float(lw[j] >> 16);
+      }
     }
-    atomicAdd(out + n, s);
+  } else {
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (c0 + j < N)
+          acc[j] += x ? x[r * ld + c0 + j] : join_bf16(x_hi[r * ld + c0 + j], x_lo[r * ld + c0 + j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  if (c < N) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(out + c, s);
   }
 }
 
@@ -272,7 +301,8 @@ extern "C" int cdetr_combine_bcast(const float* a, const float* b, const float* 
 extern "C" int cdetr_colsum(const float* x, cdetr_split_t x_split, int64_t ld, int64_t M, int N, float* out,
                             cdetr_stream_t s) {
   CDETR_CHECK_ARG((x || x_split.base) && out && M > 0 && N > 0, "colsum: bad args");
-  const int rows_per_cta = 128;
+  int rows_per_cta = 512;
+  while (rows_per_cta > 64 && cdiv(M, rows_per_cta) * cdiv(N, 256) < 2 * 148) rows_per_cta >>= 1;
   dim3 grid(cdiv(M, rows_per_cta), cdiv(N, 256));
   colsum_kernel<<<grid, 256, 0, STREAM(s)>>>(x, SPLIT_HI(x_split), SPLIT_LO(x_split),
                                              x ? ld : x_split.ld, M, N, rows_per_cta, out);
