@@ -73,7 +73,7 @@ def _ptr(t):
 
 # kernel-launch accounting (bench.py's gpu_launches) and optional per-GEMM event trace (bench.py's roofline)
 COUNTER = {"launches": 0}
-_LAUNCHES = {"cdetr_exemplar_concat": 2, "cdetr_exemplar_concat_bwd": 2, "cdetr_rcda_bwd": 3, "cdetr_mha_bwd": 2}
+_LAUNCHES = {"cdetr_exemplar_concat": 2, "cdetr_exemplar_concat_bwd": 2, "cdetr_rcda_bwd": 3, "cdetr_rcda_bwd_kv": 2, "cdetr_mha_bwd": 2}
 GEMM_TRACE = None
 
 
@@ -147,6 +147,9 @@ _SIGS = {
     "cdetr_box_head_bwd": "ppplpSp",
     "cdetr_scale": "plf",
     "cdetr_rcda_fwd": "iiiiiipppppppppS",
+    "cdetr_rcda_fwd_tc": "iiiiiippppSppppS",
+    "cdetr_rcda_bwd_q_tc": "iiiiiippSpppppSS",
+    "cdetr_rcda_bwd_kv": "iiiiiipppppppSSS",
     "cdetr_rcda_bwd": "iiiiiippppppppppSSSSS",
     "cdetr_mha_fwd": "iiiippplSp",
     "cdetr_mha_bwd": "iiiippplSpppSSS",

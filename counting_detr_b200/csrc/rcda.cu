@@ -430,3 +430,31 @@ extern "C" int cdetr_rcda_bwd(int B, int L, int H, int W, int E, int nh, const f
   CDETR_CHECK_LAUNCH();
   return 0;
 }
+
+// dK_r / dK_c / dV given the dS maps (produced by cdetr_rcda_bwd or by the tensor-core query-side kernel).
+extern "C" int cdetr_rcda_bwd_kv(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc,
+                                 const float* ar, const float* ac, const float* d_o, const float* dsr,
+                                 const float* dsc, cdetr_split_t dkr, cdetr_split_t dkc, cdetr_split_t dv,
+                                 cdetr_stream_t s_) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
+  CDETR_CHECK_ARG(E == nh * HD, "rcda_bwd_kv: head dim must be 32");
+  CDETR_CHECK_ARG(qr && qc && ar && ac && d_o && dsr && dsc && dkr.base && dkc.base && dv.base, "rcda_bwd_kv: null pointer");
+  CDETR_CHECK_ARG(dkr.ld == dkc.ld && dkr.ld == dv.ld, "rcda_bwd_kv: gradient tensors must share ld");
+  RcdaArgs a = {};
+  a.B = B; a.L = L; a.H = H; a.W = W; a.E = E; a.nh = nh;
+  a.qr = qr; a.qc = qc; a.ar = const_cast<float*>(ar); a.ac = const_cast<float*>(ac);
+  a.d_o = d_o; a.dsr = const_cast<float*>(dsr); a.dsc = const_cast<float*>(dsc);
+  auto hi = [](cdetr_split_t t) { return reinterpret_cast<__nv_bfloat16*>(t.base); };
+  a.dkr_hi = hi(dkr); a.dkr_lo = hi(dkr) + dkr.plane;
+  a.dkc_hi = hi(dkc); a.dkc_lo = hi(dkc) + dkc.plane;
+  a.dv_hi = hi(dv); a.dv_lo = hi(dv) + dv.plane;
+  a.ld_g = dkr.ld;
+  const int TV = 256;
+  const size_t smem_v = sizeof(float) * ((size_t)TQ * HD + (size_t)(W + H) * (TQ + 1));
+  { static bool once = false; if (!once) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); once = true; } }
+  rcda_bwd_v_kernel<<<dim3(cdiv(H * W, TV), nh, B), TV, smem_v, s>>>(a);
+  CDETR_CHECK_LAUNCH();
+  rcda_bwd_k_kernel<<<dim3(nh, B, 2), dim3(32, 32), 0, s>>>(a);
+  CDETR_CHECK_LAUNCH();
+  return 0;
+}

@@ -391,13 +391,18 @@ class Engine:
         lin.fwd(qc_in, M, rows=(E, 2 * E), out_f32=qc)
         lin.fwd(kr_in, B * W, rows=(2 * E, 3 * E), out_f32=kr)
         lin.fwd(kc_in, B * H, rows=(3 * E, 4 * E), out_f32=kc)
-        lin.fwd(v_in, N, rows=(4 * E, 5 * E), out_f32=v)
+        use_tc = H <= 32 and W <= 32      # tcgen05 kernel; larger feature maps use the CUDA-core kernel
+        v_s = self.sbuf(q + ".v_s", N, E) if use_tc else None
+        lin.fwd(v_in, N, rows=(4 * E, 5 * E), out_f32=v, out_split=v_s)
         ar = self.buf(q + ".ar", (B, self.nh, W, Lq)); ac = self.buf(q + ".ac", (B, self.nh, H, Lq))
         o = self.sbuf(q + ".o", M, E)
-        L.call("cdetr_rcda_fwd", B, Lq, H, W, E, self.nh, qr, qc, kr, kc, v, masks[0], masks[1], ar, ac, o)
+        if use_tc:
+            L.call("cdetr_rcda_fwd_tc", B, Lq, H, W, E, self.nh, qr, qc, kr, kc, v_s, masks[0], masks[1], ar, ac, o)
+        else:
+            L.call("cdetr_rcda_fwd", B, Lq, H, W, E, self.nh, qr, qc, kr, kc, v, masks[0], masks[1], ar, ac, o)
         attn = self.buf(q + ".attn", (M, E))
         self.lins[lin_out].fwd(o, M, out_f32=attn)
-        self.saved[q + ".rcda"] = dict(qr=qr, qc=qc, kr=kr, kc=kc, v=v, ar=ar, ac=ac, o=o, qr_in=qr_in, qc_in=qc_in,
+        self.saved[q + ".rcda"] = dict(qr=qr, qc=qc, kr=kr, kc=kc, v=v, v_s=v_s, ar=ar, ac=ac, o=o, qr_in=qr_in, qc_in=qc_in,
                                        kr_in=kr_in, kc_in=kc_in, v_in=v_in, B=B, L=Lq, H=H, W=W)
         return attn
 
@@ -413,8 +418,14 @@ class Engine:
         dsr = self.buf(q + ".dsr", (B, self.nh, W, Lq)); dsc = self.buf(q + ".dsc", (B, self.nh, H, Lq))
         dqr = self.sbuf(q + ".dqr", M, E); dqc = self.sbuf(q + ".dqc", M, E)
         dkr = self.sbuf(q + ".dkr", B * W, E); dkc = self.sbuf(q + ".dkc", B * H, E); dv = self.sbuf(q + ".dv", N, E)
-        L.call("cdetr_rcda_bwd", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], t["kr"], t["kc"], t["v"], t["ar"], t["ac"],
-               dO, dsr, dsc, dqr, dqc, dkr, dkc, dv)
+        if t["v_s"] is not None:     # tcgen05 query-side kernel + key/value-side kernels
+            L.call("cdetr_rcda_bwd_q_tc", B, Lq, H, W, E, self.nh, t["kr"], t["kc"], t["v_s"], t["ar"], t["ac"], dO,
+                   dsr, dsc, dqr, dqc)
+            L.call("cdetr_rcda_bwd_kv", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], t["ar"], t["ac"], dO, dsr, dsc,
+                   dkr, dkc, dv)
+        else:
+            L.call("cdetr_rcda_bwd", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], t["kr"], t["kc"], t["v"], t["ar"],
+                   t["ac"], dO, dsr, dsc, dqr, dqc, dkr, dkc, dv)
         lin = self.lins[lin_in]
         lin.wgrad(dqr, t["qr_in"], M, rows=(0, E))
         lin.wgrad(dqc, t["qc_in"], M, rows=(E, 2 * E))

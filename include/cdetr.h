@@ -146,6 +146,19 @@ int cdetr_scale(float* x, int64_t n, float a, cdetr_stream_t s);
 int cdetr_rcda_fwd(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc, const float* kr,
                    const float* kc, const float* v, const uint8_t* mask_row, const uint8_t* mask_col, float* ar,
                    float* ac, cdetr_split_t o, cdetr_stream_t s);
+/* Same contract as cdetr_rcda_fwd with the contraction on tcgen05 tensor cores (V given as a split tensor
+ * [B*H*W, E]); requires H, W <= 32. */
+int cdetr_rcda_fwd_tc(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc, const float* kr,
+                      const float* kc, cdetr_split_t v, const uint8_t* mask_row, const uint8_t* mask_col, float* ar,
+                      float* ac, cdetr_split_t o, cdetr_stream_t s);
+/* Query-side backward on tensor cores (dS maps + dq); pair it with cdetr_rcda_bwd_kv for dK/dV.  H, W <= 32. */
+int cdetr_rcda_bwd_q_tc(int B, int L, int H, int W, int E, int nh, const float* kr, const float* kc, cdetr_split_t v,
+                        const float* ar, const float* ac, const float* d_o, float* dsr, float* dsc,
+                        cdetr_split_t dqr, cdetr_split_t dqc, cdetr_stream_t s);
+/* Key/value-side backward given dsr/dsc: dK_r, dK_c (split) and dV (split). */
+int cdetr_rcda_bwd_kv(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc, const float* ar,
+                      const float* ac, const float* d_o, const float* dsr, const float* dsc, cdetr_split_t dkr,
+                      cdetr_split_t dkc, cdetr_split_t dv, cdetr_stream_t s);
 int cdetr_rcda_bwd(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc, const float* kr,
                    const float* kc, const float* v, const float* ar, const float* ac, const float* d_o,
                    float* dsr, float* dsc, cdetr_split_t dqr, cdetr_split_t dqc, cdetr_split_t dkr,

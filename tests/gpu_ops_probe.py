@@ -209,11 +209,28 @@ for (Bz, Lq, Hh, Ww) in [(2, 300, 32, 32), (1, 70, 9, 13), (1, 1024, 32, 32), (1
     tag = f"B{Bz} L{Lq} {Hh}x{Ww}"
     report(f"rcda_fwd {tag}", L.from_split(o).view(Bz, Lq, E), ref.detach(), 2e-5)
     report(f"rcda_fwd A_r {tag}", ar.permute(0, 1, 3, 2), a_r.detach(), 1e-5)
+    if Hh <= 32 and Ww <= 32:
+        ar2 = torch.empty_like(ar); ac2 = torch.empty_like(ac); o2 = zs(Bz * Lq, E)
+        L.call("cdetr_rcda_fwd_tc", Bz, Lq, Hh, Ww, E, nh, qr, qc, kr, kc, S(v.detach()), None, None, ar2, ac2, o2)
+        report(f"rcda_fwd_tc {tag}", L.from_split(o2).view(Bz, Lq, E), ref.detach(), 3e-5)
+        report(f"rcda_fwd_tc A_r {tag}", ar2.permute(0, 1, 3, 2), a_r.detach(), 1e-5)
+        report(f"rcda_fwd_tc A_c {tag}", ac2.permute(0, 1, 3, 2), a_c.detach(), 1e-5)
     dO = torch.randn(Bz, Lq, E, device=dev)
     ref.backward(dO)
     dsr = torch.empty_like(ar); dsc = torch.empty_like(ac)
     dqr, dqc, dkr, dkc, dv = zs(Bz * Lq, E), zs(Bz * Lq, E), zs(Bz * Ww, E), zs(Bz * Hh, E), zs(Bz * Hh * Ww, E)
     L.call("cdetr_rcda_bwd", Bz, Lq, Hh, Ww, E, nh, qr, qc, kr, kc, v, ar, ac, dO, dsr, dsc, dqr, dqc, dkr, dkc, dv)
+    if Hh <= 32 and Ww <= 32:
+        dsr2 = torch.empty_like(ar); dsc2 = torch.empty_like(ac)
+        dqr2, dqc2, dkr2, dkc2, dv2 = zs(Bz * Lq, E), zs(Bz * Lq, E), zs(Bz * Ww, E), zs(Bz * Hh, E), zs(Bz * Hh * Ww, E)
+        L.call("cdetr_rcda_bwd_q_tc", Bz, Lq, Hh, Ww, E, nh, kr, kc, S(v.detach()), ar, ac, dO, dsr2, dsc2, dqr2, dqc2)
+        L.call("cdetr_rcda_bwd_kv", Bz, Lq, Hh, Ww, E, nh, qr, qc, ar, ac, dO, dsr2, dsc2, dkr2, dkc2, dv2)
+        report(f"rcda_bwd_tc dqr {tag}", L.from_split(dqr2).view_as(qr), qr.grad, 5e-5)
+        report(f"rcda_bwd_tc dqc {tag}", L.from_split(dqc2).view_as(qc), qc.grad, 5e-5)
+        report(f"rcda_bwd_tc dsr {tag}", dsr2, dsr, 5e-5)
+        report(f"rcda_bwd_tc dkr {tag}", L.from_split(dkr2).view_as(kr), kr.grad, 5e-5)
+        report(f"rcda_bwd_tc dkc {tag}", L.from_split(dkc2).view_as(kc), kc.grad, 5e-5)
+        report(f"rcda_bwd_tc dv {tag}", L.from_split(dv2).view_as(v), v.grad, 5e-5)
     report(f"rcda_bwd dqr {tag}", L.from_split(dqr).view_as(qr), qr.grad, 5e-5)
     report(f"rcda_bwd dqc {tag}", L.from_split(dqc).view_as(qc), qc.grad, 5e-5)
     report(f"rcda_bwd dkr {tag}", L.from_split(dkr).view_as(kr), kr.grad, 5e-5)
@@ -229,6 +246,9 @@ ar = torch.empty(Bz, nh, Ww, Lq, device=dev); ac = torch.empty(Bz, nh, Hh, Lq, d
 L.call("cdetr_rcda_fwd", Bz, Lq, Hh, Ww, E, nh, qr, qc, kr, kc, v, mr, mc, ar, ac, o)
 ref, _, _ = rcda_ref(qr, qc, kr[:, :5], kc[:, :4], v[:, :4, :5], nh)
 report("rcda_fwd masked", L.from_split(o).view(Bz, Lq, E), ref, 2e-5)
+o2 = zs(Bz * Lq, E)
+L.call("cdetr_rcda_fwd_tc", Bz, Lq, Hh, Ww, E, nh, qr, qc, kr, kc, S(v), mr, mc, ar, ac, o2)
+report("rcda_fwd_tc masked", L.from_split(o2).view(Bz, Lq, E), ref, 3e-5)
 
 for (Bz, Lq) in [(2, 300), (1, 77), (1, 500)]:
     nh = 8; d = 32
