@@ -155,7 +155,7 @@ _SIGS = {
     "cdetr_mha_bwd": "iiiippplSpppSSS",
     "cdetr_match_cost": "pipppiiifffp",
     "cdetr_lsap": "ppiiipppp",
-    "cdetr_set_loss_fwd": "ppppppppiiiffppppppp",
+    "cdetr_set_loss_fwd": "ppppppppiiipffppppppp",
     "cdetr_set_loss_bwd": "pppppplppp",
     "cdetr_bbox_loss_fwd": "ppplppp",
     "cdetr_bbox_loss_bwd": "ppplp",

@@ -75,13 +75,16 @@ __global__ void set_loss_fwd_kernel(const float* __restrict__ logits, const floa
                                     const float* __restrict__ vars, const float* __restrict__ tgt,
                                     const int* __restrict__ tgt_off, const int64_t* __restrict__ idx_q,
                                     const int64_t* __restrict__ idx_t, const int* __restrict__ idx_n, int B,
-                                    int Q, int Kmax, float num_boxes, float alpha, float* __restrict__ out,
+                                    int Q, int Kmax, const float* __restrict__ num_boxes_sum, float inv_world,
+                                    float alpha, float* __restrict__ out,
                                     float* __restrict__ g_ce, float* __restrict__ g_bbox,
                                     float* __restrict__ g_giou, float* __restrict__ g_var_box,
                                     float* __restrict__ g_var_var, unsigned char* __restrict__ matched) {
   __shared__ float red[33];
   const int tid = threadIdx.x, nt = blockDim.x;
-  const float inv_nb = 1.0f / num_boxes;
+  // num_boxes = clamp(sum over ranks / world, min 1)  (A2/models/anchor_detr.py:321-325), read from device memory
+  // so the criterion never synchronises with the host
+  const float inv_nb = 1.0f / fmaxf(num_boxes_sum[0] * inv_world, 1.0f);
   for (int i = tid; i < B * Q; i += nt) matched[i] = 0;
   for (int i = tid; i < B * Q * 4; i += nt) { g_bbox[i] = 0.0f; g_giou[i] = 0.0f; g_var_box[i] = 0.0f; }
   for (int i = tid; i < B * Q * 2; i += nt) g_var_var[i] = 0.0f;
@@ -239,14 +242,17 @@ __global__ void bbox_loss_bwd_kernel(const float* __restrict__ up, const float* 
 extern "C" int cdetr_set_loss_fwd(const float* logits, const float* boxes, const float* vars,
                                   const float* tgt_boxes, const int* tgt_off, const int64_t* idx_q,
                                   const int64_t* idx_t, const int* idx_n, int B, int Q, int Kmax,
-                                  float num_boxes, float focal_alpha, float* out6, float* g_ce, float* g_bbox,
+                                  const float* num_boxes_sum, float inv_world, float focal_alpha, float* out6,
+                                  float* g_ce, float* g_bbox,
                                   float* g_giou, float* g_var_box, float* g_var_var, unsigned char* matched,
                                   cdetr_stream_t s) {
   CDETR_CHECK_ARG(logits && boxes && vars && tgt_boxes && tgt_off && idx_q && idx_t && idx_n && out6 && g_ce &&
-                      g_bbox && g_giou && g_var_box && g_var_var && matched && B > 0 && Q > 0 && num_boxes > 0,
+                      g_bbox && g_giou && g_var_box && g_var_var && matched && B > 0 && Q > 0 && num_boxes_sum &&
+                      inv_world > 0,
                   "set_loss_fwd: bad args");
   set_loss_fwd_kernel<<<1, 1024, 0, STREAM(s)>>>(logits, boxes, vars, tgt_boxes, tgt_off, idx_q, idx_t, idx_n, B,
-                                                 Q, Kmax > 0 ? Kmax : 1, num_boxes, focal_alpha, out6, g_ce, g_bbox,
+                                                 Q, Kmax > 0 ? Kmax : 1, num_boxes_sum, inv_world, focal_alpha, out6, g_ce,
+                                                 g_bbox,
                                                  g_giou, g_var_box, g_var_var, matched);
   CDETR_CHECK_LAUNCH();
   return 0;

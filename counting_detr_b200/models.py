@@ -190,10 +190,23 @@ class AnchorDETR(nn.Module):
         self._engine = None
         self._param_version = None
         self._grad_group = None
+        self._alias_grads = False
 
     def enable_grad_sync(self, group):
         """Average parameter gradients over `group` (torch.distributed, NCCL) at the end of every backward."""
         self._grad_group = group
+
+    def alias_param_grads(self, on=True):
+        """p.grad becomes a view of the engine's flat gradient buffer (no per-step copy).  Lets a training loop
+        keep NCCL out of a captured CUDA graph: replay fwd+bwd, then call allreduce_grads()."""
+        self._alias_grads = on
+
+    def allreduce_grads(self, group):
+        """One all-reduce (+ in-place average) of the flat gradient buffer; p.grad views see the result."""
+        from .parallel import average_flat_grads
+        eng = self.engine()
+        average_flat_grads(eng.grad_flat[: eng.n_param_grad], group,
+                           scale_fn=lambda t, s: L.call("cdetr_scale", t, t.numel(), s))
 
     def _maybe_load_pretrained(self):
         path = os.path.join("pretrained_models", "resnet50-0676ba61.pth")   # A2/models/resnet.py:293-294
@@ -351,7 +364,14 @@ class _ModelFn(torch.autograd.Function):
         out = []
         for n, p in zip(module._names, module.parameters()):
             gv = eng.grad_views.get(n)
-            out.append(gv if (gv is not None and p.requires_grad) else None)
+            if gv is None or not p.requires_grad:
+                out.append(None)
+            elif module._alias_grads:
+                if p.grad is None or p.grad.data_ptr() != gv.data_ptr():
+                    p.grad = gv
+                out.append(None)
+            else:
+                out.append(gv)
         return (None, None, None, None, None) + tuple(out)
 
 
@@ -435,7 +455,7 @@ def _world_size():
 
 class _SetLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, crit, logits, boxes, pvars, targets, num_boxes):
+    def forward(ctx, crit, logits, boxes, pvars, targets, num_boxes, inv_world):
         dev = logits.device
         B, Q, _ = logits.shape
         oq, ot, on, lens = crit.matcher.match_device(logits, boxes, targets)
@@ -446,7 +466,7 @@ class _SetLossFn(torch.autograd.Function):
         g_giou = torch.empty(B, Q, 4, device=dev); g_vb = torch.empty(B, Q, 4, device=dev)
         g_vv = torch.empty(B, Q, 2, device=dev); matched = torch.empty(B * Q, dtype=torch.uint8, device=dev)
         L.call("cdetr_set_loss_fwd", logits.contiguous(), boxes.contiguous(), pvars.contiguous(), tg.boxes, tg.off, oq,
-               ot, on, B, Q, K, num_boxes, crit.focal_alpha, out6, g_ce, g_bbox, g_giou, g_vb, g_vv, matched)
+               ot, on, B, Q, K, num_boxes, inv_world, crit.focal_alpha, out6, g_ce, g_bbox, g_giou, g_vb, g_vv, matched)
         ctx.save_for_backward(g_ce, g_bbox, g_giou, g_vb, g_vv)
         ctx.rows = B * Q
         crit.last_indices = (oq, ot, on)
@@ -462,7 +482,7 @@ class _SetLossFn(torch.autograd.Function):
         up = torch.stack([g if g is not None else z for g in (g_ce_, g_bbox_, g_giou_, g_var_)]).float().contiguous()
         dl = torch.empty_like(g_ce); db = torch.empty_like(g_bbox); dv = torch.empty_like(g_vv)
         L.call("cdetr_set_loss_bwd", up, g_ce, g_bbox, g_giou, g_vb, g_vv, ctx.rows, dl, db, dv)
-        return None, dl, db, dv, None, None
+        return None, dl, db, dv, None, None, None
 
 
 class SetCriterion(nn.Module):
@@ -479,21 +499,35 @@ class SetCriterion(nn.Module):
         self.num_classes, self.matcher, self.weight_dict = num_classes, matcher, weight_dict
         self.losses, self.focal_alpha = losses, focal_alpha
         self.last_indices = None
+        self.fixed_num_boxes = None      # per-rank target count when it is constant (benchmarks)
+        self._nb_dev = self._nb_host = self._nb_last = None
 
     def forward(self, outputs, targets):
         if "aux_outputs" in outputs:
             # the reference asserts "pred_vars" in every aux dict, which they never contain
             # (A2/models/anchor_detr.py:140,268): stage 2 is only runnable with --no_aux_loss
             raise AssertionError("aux_outputs lack 'pred_vars': run stage 2 with --no_aux_loss (reference behaviour)")
-        num_boxes = sum(len(t["labels"]) for t in targets)
+        # num_boxes = clamp(all_reduce(sum T) / world, 1) stays on the device (the reference's .item() sync,
+        # A2/models/anchor_detr.py:321-325, is gone); fixed_num_boxes (benchmarks with constant T) skips the
+        # collective so the step can be captured in a CUDA graph without NCCL inside
+        dev = outputs["pred_logits"].device
         ws = _world_size()
-        if ws > 1:
-            nb = torch.as_tensor([num_boxes], dtype=torch.float, device=outputs["pred_logits"].device)
-            torch.distributed.all_reduce(nb)
-            num_boxes = nb.item()
-        num_boxes = max(num_boxes / ws, 1.0)
+        if self._nb_dev is None or self._nb_dev.device != dev:
+            self._nb_host = torch.zeros(1, pin_memory=True)
+            self._nb_dev = torch.zeros(1, device=dev)
+            self._nb_last = None
+        if self.fixed_num_boxes is not None:
+            val, reduce = float(self.fixed_num_boxes) * ws, False
+        else:
+            val, reduce = float(sum(len(t["labels"]) for t in targets)), ws > 1
+        if reduce or val != self._nb_last:
+            self._nb_host[0] = val
+            self._nb_dev.copy_(self._nb_host, non_blocking=True)
+            self._nb_last = None if reduce else val
+            if reduce:
+                torch.distributed.all_reduce(self._nb_dev)
         ce, err, bbox, giou, card, var = _SetLossFn.apply(self, outputs["pred_logits"], outputs["pred_boxes"],
-                                                         outputs["pred_vars"], targets, float(num_boxes))
+                                                         outputs["pred_vars"], targets, self._nb_dev, 1.0 / ws)
         res = {}
         for name in self.losses:
             if name == "labels":

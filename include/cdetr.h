@@ -181,10 +181,12 @@ int cdetr_match_cost(const float* logits, int num_logits, const float* boxes, co
                      float* cost, cdetr_stream_t s);
 int cdetr_lsap(const float* cost, const int* tgt_off, int B, int Q, int Tmax, int64_t* out_q, int64_t* out_t,
                int* out_n, int* status, cdetr_stream_t s);
-/* out6 = loss_ce, class_error, loss_bbox, loss_giou, cardinality_error, loss_variance */
+/* out6 = loss_ce, class_error, loss_bbox, loss_giou, cardinality_error, loss_variance.
+ * num_boxes_sum: device float = sum of target counts over all ranks; num_boxes = max(sum * inv_world, 1). */
 int cdetr_set_loss_fwd(const float* logits, const float* boxes, const float* vars, const float* tgt_boxes,
                        const int* tgt_off, const int64_t* idx_q, const int64_t* idx_t, const int* idx_n, int B,
-                       int Q, int Kmax, float num_boxes, float focal_alpha, float* out6, float* g_ce,
+                       int Q, int Kmax, const float* num_boxes_sum, float inv_world, float focal_alpha,
+                       float* out6, float* g_ce,
                        float* g_bbox, float* g_giou, float* g_var_box, float* g_var_var, unsigned char* matched,
                        cdetr_stream_t s);
 int cdetr_set_loss_bwd(const float* upstream4, const float* g_ce, const float* g_bbox, const float* g_giou,
