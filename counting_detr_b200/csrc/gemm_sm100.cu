@@ -13,6 +13,7 @@
 // Replaces the ATen GEMM call sites listed in include/cdetr.h (cdetr_gemm).
 #include "common.cuh"
 #include "../../include/cdetr.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -367,7 +368,8 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
 
   int bn = g->block_n;
   if (bn <= 0) {
-    if (g->N >= 256 && (int64_t)cdiv(g->M, BM) * cdiv(g->N, 256) >= 120) bn = 256;
+    // measured on B200 (tools/gemm_sweep.py): 256-wide tiles only pay for long K loops on wide outputs
+    if (!nt && g->N >= 512 && g->K >= 1024) bn = 256;
     else if (g->N > 64) bn = 128;
     else if (g->N > 32) bn = 64;
     else if (g->N > 16) bn = 32;
@@ -416,15 +418,20 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   const uint32_t smem_budget = 227u * 1024u - 1024u - tail_bytes;
   int stages = (int)(smem_budget / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (kb_per_split <= 8) {
-    // short K loops are epilogue/latency bound: keep the CTA small enough for 2-3 CTAs per SM so that one
-    // CTA's epilogue overlaps another's loads and MMAs (TMEM: each CTA holds <= 256 of the 512 columns)
+  {
+    // One tile per CTA means a CTA's epilogue cannot overlap its own main loop, so co-resident CTAs do the
+    // overlapping: keep the CTA at <= ~113 KB so 2-3 fit per SM (TMEM: each holds <= 256 of the 512 columns).
+    // Measured (tools/gemm_sweep.py): 2 CTAs x 1 stage beats 1 CTA x 2-3 stages on every shape of the step.
     int s2 = (int)((113u * 1024u) / stage_bytes);
     if (s2 < 1) s2 = 1;
     if (stages > s2) stages = s2;
   }
   if (stages > kb_per_split) stages = kb_per_split;
   if (stages < 1) stages = 1;
+  if (const char* e = getenv("CDETR_GEMM_STAGES")) {  // tuning hook (tools/gemm_sweep.py)
+    const int f = atoi(e);
+    if (f >= 1 && f <= MAX_STAGES && (uint32_t)f * stage_bytes <= smem_budget) stages = f < kb_per_split ? f : kb_per_split;
+  }
   CDETR_CHECK_ARG(stages >= 1, "gemm: tile does not fit shared memory");
   ka.stages = stages;
   const size_t smem_bytes = (size_t)stages * stage_bytes + tail_bytes + 1024;

@@ -1,4 +1,4 @@
-// RCDA forward on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), one CTA per (sample, head, 128 queries).
+// RCDA forward on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), one CTA per (sample, head, 2 x 128 queries).
 //
 //   O[q,:] = sum_h A_c[q,h] * ( sum_w A_r[q,w] * V[h,w,:] )
 //            `--- CUDA cores, TMEM->register epilogue ---'  `--- tcgen05.mma: [128 x W] x [W x (H*32)] ---'
@@ -6,7 +6,9 @@
 //   warp 0      TMA: the head's V slice (hi + lo planes, [H][W][32] bf16, SWIZZLE_64B) -> shared memory
 //   warp 1      MMA issuer: for each block of 8 key rows h: D[128 x 256] = A_r[128 x W] * V[W x (8*32)], three
 //               bf16 passes (hi*lo, lo*hi, hi*hi), fp32 accumulation in one of two 256-column TMEM buffers
-//   warps 2-5   one query per thread: both softmaxes (fp32, CUDA cores; logits are 128x32 per side), A_r written
+//   warps 2-9   two groups of four warps, each group owns one 128-query tile and one 256-column TMEM buffer (the
+//               tensor core works on one tile while the other tile's epilogue runs; V is staged once for both);
+//               one query per thread: both softmaxes (fp32, CUDA cores; logits are 128x32 per side), A_r written
 //               to shared memory as the split-bf16 A operand (manual SWIZZLE_64B), then the epilogue:
 //               tcgen05.ld of T[q, h, 0:32] and acc += A_c[q,h] * T   (the only CUDA-core FMAs: 1/32 of the MACs)
 // The reference materialises [B*heads, L, W, 32] in HBM (A2/models/row_column_decoupled_attention.py:262-291);
@@ -70,33 +72,34 @@ __device__ __forceinline__ void softmax32(const float* __restrict__ qv, const fl
   for (int k = 0; k < 32; ++k) p[k] *= inv;
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Vs = smem;                                   // [2][HP][WP][32] bf16, SW64
-  uint8_t* As = Vs + 2 * V_PLANE_BYTES;                 // [2][128][32] bf16, SW64 K-major
-  float* Ksr = reinterpret_cast<float*>(As + 2 * A_PLANE_BYTES);  // [32][32]
+  uint8_t* As = Vs + 2 * V_PLANE_BYTES;                 // [2 tiles][2 planes][128][32] bf16, SW64 K-major
+  float* Ksr = reinterpret_cast<float*>(As + 4 * A_PLANE_BYTES);  // [32][32]
   float* Ksc = Ksr + 32 * HD;
   uint64_t* bars = reinterpret_cast<uint64_t*>(Ksc + 32 * HD);
   uint64_t* v_full = bars;
-  uint64_t* a_ready = bars + 1;
-  uint64_t* t_full = bars + 2;   // [2]
-  uint64_t* t_empty = bars + 4;  // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* a_ready = bars + 1;  // [2]
+  uint64_t* t_full = bars + 3;   // [2]
+  uint64_t* t_empty = bars + 5;  // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, b = blockIdx.z;
-  const int q0 = blockIdx.x * TQ;
+  const int q_cta = blockIdx.x * 2 * TQ;
+  const int nblk = (a.H + 7) / 8;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmV);
     mbar_init(v_full, 1);
-    mbar_init(a_ready, 128);
-    mbar_init(&t_full[0], 1);
-    mbar_init(&t_full[1], 1);
-    mbar_init(&t_empty[0], 128);
-    mbar_init(&t_empty[1], 128);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&a_ready[g], 128);
+      mbar_init(&t_full[g], 1);
+      mbar_init(&t_empty[g], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -116,139 +119,143 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      const int ngroups = (q_cta + TQ < a.L) ? 2 : 1;
       mbar_wait(v_full, 0);
-      mbar_wait(a_ready, 0);
-      tc_fence_after();
-      const uint32_t a_base = smem_u32(As), v_base = smem_u32(Vs);
-      const int nblk = (a.H + 7) / 8;
+      const uint32_t v_base = smem_u32(Vs);
       for (int p = 0; p < nblk; ++p) {
-        if (p >= 2) {
-          mbar_wait(&t_empty[p & 1], (uint32_t)((p >> 1) - 1) & 1u);
+        for (int g = 0; g < ngroups; ++g) {
+          if (p == 0) mbar_wait(&a_ready[g], 0);
+          else mbar_wait(&t_empty[g], (uint32_t)(p - 1) & 1u);
           tc_fence_after();
-        }
-        const uint32_t d = tmem_base + (uint32_t)(p & 1) * 256u;
+          const uint32_t a_base = smem_u32(As) + (uint32_t)g * 2u * A_PLANE_BYTES;
+          const uint32_t d = tmem_base + (uint32_t)g * 256u;
 #pragma unroll
-        for (int ks = 0; ks < WP / 16; ++ks) {
-          // A_r: K-major SW64 (64-byte rows, 8-row groups 512 B apart, k-step +32 B)
-          const uint64_t a_hi = make_smem_desc(a_base + ks * 32, 16, 512, 4);
-          const uint64_t a_lo = make_smem_desc(a_base + A_PLANE_BYTES + ks * 32, 16, 512, 4);
-          // V: MN-major SW64: MN chunk = one key row h (32 channels, 64 B); chunks WP*64 B apart (LBO);
-          // 8 key columns w (the k index) per 512-byte group (SBO); one k-step = 16 w = +1024 B
-          const uint32_t vb = v_base + (uint32_t)p * 8u * (WP * 64) + ks * 1024;
-          const uint64_t b_hi = make_smem_desc(vb, WP * 64, 512, 4);
-          const uint64_t b_lo = make_smem_desc(vb + V_PLANE_BYTES, WP * 64, 512, 4);
-          umma_bf16_ss(d, a_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u);
-          umma_bf16_ss(d, a_lo, b_hi, a.idesc, 1);
-          umma_bf16_ss(d, a_hi, b_hi, a.idesc, 1);
+          for (int ks = 0; ks < WP / 16; ++ks) {
+            // A_r: K-major SW64 (64-byte rows, 8-row groups 512 B apart, k-step +32 B)
+            const uint64_t a_hi = make_smem_desc(a_base + ks * 32, 16, 512, 4);
+            const uint64_t a_lo = make_smem_desc(a_base + A_PLANE_BYTES + ks * 32, 16, 512, 4);
+            // V: MN-major SW64: MN chunk = one key row h (32 channels, 64 B); chunks WP*64 B apart (LBO);
+            // 8 key columns w (the k index) per 512-byte group (SBO); one k-step = 16 w = +1024 B
+            const uint32_t vb = v_base + (uint32_t)p * 8u * (WP * 64) + ks * 1024;
+            const uint64_t b_hi = make_smem_desc(vb, WP * 64, 512, 4);
+            const uint64_t b_lo = make_smem_desc(vb + V_PLANE_BYTES, WP * 64, 512, 4);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc, 1);
+          }
+          umma_commit(&t_full[g]);
         }
-        umma_commit(&t_full[p & 1]);
       }
     }
   } else {
     // ------------------------------ compute warps: one query per thread ------------------------------
-    const int ct = threadIdx.x - 64;       // 0..127
+    const int ct = threadIdx.x - 64;       // 0..255
+    const int g = (warp - 2) >> 2;         // tile / TMEM buffer of this warp group
     const int quarter = warp & 3;          // TMEM lane quarter accessible to this warp
     const int r = quarter * 32 + lane;     // row inside the 128-query tile == TMEM lane
-    const int q = q0 + r;
+    const int q = q_cta + g * TQ + r;
     const bool ok = q < a.L;
-    for (int i = ct; i < 32 * HD; i += 128) {
+    const bool active = q_cta + g * TQ < a.L;   // whole group idle when its tile is past the end
+    for (int i = ct; i < 32 * HD; i += 256) {
       const int k = i / HD, dch = i % HD;
       Ksr[i] = k < a.W ? a.kr[((int64_t)b * a.W + k) * a.E + head * HD + dch] : 0.0f;
       Ksc[i] = k < a.H ? a.kc[((int64_t)b * a.H + k) * a.E + head * HD + dch] : 0.0f;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const float scale = rsqrtf((float)HD);
-    const int64_t bh = (int64_t)b * a.nh + head;
-    float ac[32];
-    {
-      float ar[32], qv[HD];
-      if (ok) {
-        const float4* qp = reinterpret_cast<const float4*>(a.qr + ((int64_t)b * a.L + q) * a.E + head * HD);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (active) {
+      uint8_t* Ag = As + (size_t)g * 2 * A_PLANE_BYTES;
+      const float scale = rsqrtf((float)HD);
+      const int64_t bh = (int64_t)b * a.nh + head;
+      float ac[32];
+      {
+        float ar[32], qv[HD];
+        if (ok) {
+          const float4* qp = reinterpret_cast<const float4*>(a.qr + ((int64_t)b * a.L + q) * a.E + head * HD);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = __ldg(qp + j);
-          qv[4 * j] = t.x * scale; qv[4 * j + 1] = t.y * scale; qv[4 * j + 2] = t.z * scale; qv[4 * j + 3] = t.w * scale;
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(qp + j);
+            qv[4 * j] = t.x * scale; qv[4 * j + 1] = t.y * scale; qv[4 * j + 2] = t.z * scale; qv[4 * j + 3] = t.w * scale;
+          }
+          softmax32(qv, Ksr, a.W, a.mask_row ? a.mask_row + (int64_t)b * a.W : nullptr, ar);
+#pragma unroll
+          for (int w = 0; w < 32; ++w)
+            if (w < a.W) a.ar[(bh * a.W + w) * a.L + q] = ar[w];
+        } else {
+#pragma unroll
+          for (int w = 0; w < 32; ++w) ar[w] = 0.0f;
         }
-        softmax32(qv, Ksr, a.W, a.mask_row ? a.mask_row + (int64_t)b * a.W : nullptr, ar);
-#pragma unroll
-        for (int w = 0; w < 32; ++w)
-          if (w < a.W) a.ar[(bh * a.W + w) * a.L + q] = ar[w];
-      } else {
-#pragma unroll
-        for (int w = 0; w < 32; ++w) ar[w] = 0.0f;
-      }
-      // A operand: row r, 4 chunks of 8 k-values; SWIZZLE_64B: 16-byte chunk j of row r lives at j ^ ((r >> 1) & 3)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(ar[8 * j + 2 * i], h0, l0);
-          split_bf16(ar[8 * j + 2 * i + 1], h1, l1);
-          hw[i] = pack_bf16x2(h0, h1);
-          lw[i] = pack_bf16x2(l0, l1);
-        }
-        const uint32_t off = (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4);
-        *reinterpret_cast<uint4*>(As + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(As + A_PLANE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      }
-      fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core (async proxy)
-      mbar_arrive(a_ready);
-      if (ok) {
-        const float4* qp = reinterpret_cast<const float4*>(a.qc + ((int64_t)b * a.L + q) * a.E + head * HD);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = __ldg(qp + j);
-          qv[4 * j] = t.x * scale; qv[4 * j + 1] = t.y * scale; qv[4 * j + 2] = t.z * scale; qv[4 * j + 3] = t.w * scale;
-        }
-        softmax32(qv, Ksc, a.H, a.mask_col ? a.mask_col + (int64_t)b * a.H : nullptr, ac);
-#pragma unroll
-        for (int h = 0; h < 32; ++h)
-          if (h < a.H) a.ac[(bh * a.H + h) * a.L + q] = ac[h];
-      } else {
-#pragma unroll
-        for (int h = 0; h < 32; ++h) ac[h] = 0.0f;
-      }
-    }
-    float acc[HD];
-#pragma unroll
-    for (int c = 0; c < HD; ++c) acc[c] = 0.0f;
-    const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int nblk = (a.H + 7) / 8;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      if (p < nblk) {
-        mbar_wait(&t_full[p & 1], (uint32_t)(p >> 1) & 1u);
-        tc_fence_after();
-#pragma unroll
-        for (int hi = 0; hi < 8; ++hi) {
-          uint32_t t[32];
-          tmem_ld_32x32b_x32(taddr_row + (uint32_t)(p & 1) * 256u + (uint32_t)hi * 32u, t);
-          tmem_ld_wait();
-          const float coef = ac[p * 8 + hi];
-#pragma unroll
-          for (int c = 0; c < HD; ++c) acc[c] += coef * __uint_as_float(t[c]);
-        }
-        tc_fence_before();
-        mbar_arrive(&t_empty[p & 1]);
-      }
-    }
-    if (ok) {
-      const int64_t off = ((int64_t)b * a.L + q) * a.ld_o + head * HD;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint32_t hw[4], lw[4];
+        // A operand: row r, 4 chunks of 8 k-values; SWIZZLE_64B: 16-byte chunk j of row r lives at j ^ ((r >> 1) & 3)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(acc[g * 8 + 2 * j], h0, l0);
-          split_bf16(acc[g * 8 + 2 * j + 1], h1, l1);
-          hw[j] = pack_bf16x2(h0, h1);
-          lw[j] = pack_bf16x2(l0, l1);
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(ar[8 * j + 2 * i], h0, l0);
+            split_bf16(ar[8 * j + 2 * i + 1], h1, l1);
+            hw[i] = pack_bf16x2(h0, h1);
+            lw[i] = pack_bf16x2(l0, l1);
+          }
+          const uint32_t off = (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(Ag + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(Ag + A_PLANE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
-        reinterpret_cast<uint4*>(a.o_hi + off)[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        reinterpret_cast<uint4*>(a.o_lo + off)[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core (async proxy)
+        mbar_arrive(&a_ready[g]);
+        if (ok) {
+          const float4* qp = reinterpret_cast<const float4*>(a.qc + ((int64_t)b * a.L + q) * a.E + head * HD);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(qp + j);
+            qv[4 * j] = t.x * scale; qv[4 * j + 1] = t.y * scale; qv[4 * j + 2] = t.z * scale; qv[4 * j + 3] = t.w * scale;
+          }
+          softmax32(qv, Ksc, a.H, a.mask_col ? a.mask_col + (int64_t)b * a.H : nullptr, ac);
+#pragma unroll
+          for (int h = 0; h < 32; ++h)
+            if (h < a.H) a.ac[(bh * a.H + h) * a.L + q] = ac[h];
+        } else {
+#pragma unroll
+          for (int h = 0; h < 32; ++h) ac[h] = 0.0f;
+        }
+      }
+      float acc[HD];
+#pragma unroll
+      for (int c = 0; c < HD; ++c) acc[c] = 0.0f;
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * 256u;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        if (p < nblk) {
+          mbar_wait(&t_full[g], (uint32_t)p & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int hi = 0; hi < 8; ++hi) {
+            uint32_t t[32];
+            tmem_ld_32x32b_x32(taddr_row + (uint32_t)hi * 32u, t);
+            tmem_ld_wait();
+            const float coef = ac[p * 8 + hi];
+#pragma unroll
+            for (int c = 0; c < HD; ++c) acc[c] += coef * __uint_as_float(t[c]);
+          }
+          tc_fence_before();
+          mbar_arrive(&t_empty[g]);
+        }
+      }
+      if (ok) {
+        const int64_t off = ((int64_t)b * a.L + q) * a.ld_o + head * HD;
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(acc[gg * 8 + 2 * j], h0, l0);
+            split_bf16(acc[gg * 8 + 2 * j + 1], h1, l1);
+            hw[j] = pack_bf16x2(h0, h1);
+            lw[j] = pack_bf16x2(l0, l1);
+          }
+          reinterpret_cast<uint4*>(a.o_hi + off)[gg] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          reinterpret_cast<uint4*>(a.o_lo + off)[gg] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
       }
     }
   }
@@ -280,33 +287,32 @@ struct TcBwdArgs {
   uint32_t idesc;
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Vs = smem;
-  uint8_t* As = Vs + 2 * V_PLANE_BYTES;   // dO tile [2][128][32] bf16, SW64 K-major
-  float* Ksr = reinterpret_cast<float*>(As + 2 * A_PLANE_BYTES);
-  float* Ksc = Ksr + 32 * HD;
-  float* acs = Ksc + 32 * HD;      // [32][128] A_c per query thread (keeps registers for A_r / dA_r / the G row)
-  float* dacs = acs + 32 * TQ;     // [32][128] dA_c
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dacs + 32 * TQ);
+  uint8_t* Vs = smem;                     // V hi/lo; after the last MMA its first 8 KB are reused for the K slices
+  uint8_t* As = Vs + 2 * V_PLANE_BYTES;   // dO tiles [2 tiles][2 planes][128][32] bf16, SW64 K-major
+  float* acs = reinterpret_cast<float*>(As + 4 * A_PLANE_BYTES);   // [2][32][128] A_c per query thread
+  float* dacs = acs + 2 * 32 * TQ;                                  // [2][32][128] dA_c
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dacs + 2 * 32 * TQ);
   uint64_t* v_full = bars;
-  uint64_t* a_ready = bars + 1;
-  uint64_t* t_full = bars + 2;
-  uint64_t* t_empty = bars + 4;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* a_ready = bars + 1;  // [2]
+  uint64_t* t_full = bars + 3;   // [2]
+  uint64_t* t_empty = bars + 5;  // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 7);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, b = blockIdx.z;
-  const int q0 = blockIdx.x * TQ;
+  const int q_cta = blockIdx.x * 2 * TQ;
+  const int nblk = (a.H + 7) / 8;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmV);
     mbar_init(v_full, 1);
-    mbar_init(a_ready, 128);
-    mbar_init(&t_full[0], 1);
-    mbar_init(&t_full[1], 1);
-    mbar_init(&t_empty[0], 128);
-    mbar_init(&t_empty[1], 128);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&a_ready[g], 128);
+      mbar_init(&t_full[g], 1);
+      mbar_init(&t_empty[g], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -317,7 +323,6 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  const int nblk = (a.H + 7) / 8;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -327,111 +332,122 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      const int ngroups = (q_cta + TQ < a.L) ? 2 : 1;
       mbar_wait(v_full, 0);
-      mbar_wait(a_ready, 0);
-      tc_fence_after();
-      const uint32_t a_base = smem_u32(As), v_base = smem_u32(Vs);
+      const uint32_t v_base = smem_u32(Vs);
       for (int p = 0; p < nblk; ++p) {
-        if (p >= 2) {
-          mbar_wait(&t_empty[p & 1], (uint32_t)((p >> 1) - 1) & 1u);
+        for (int g = 0; g < ngroups; ++g) {
+          if (p == 0) mbar_wait(&a_ready[g], 0);
+          else mbar_wait(&t_empty[g], (uint32_t)(p - 1) & 1u);
           tc_fence_after();
-        }
-        const uint32_t d = tmem_base + (uint32_t)(p & 1) * 256u;
+          const uint32_t a_base = smem_u32(As) + (uint32_t)g * 2u * A_PLANE_BYTES;
+          const uint32_t d = tmem_base + (uint32_t)g * 256u;
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks) {
-          const uint64_t a_hi = make_smem_desc(a_base + ks * 32, 16, 512, 4);
-          const uint64_t a_lo = make_smem_desc(a_base + A_PLANE_BYTES + ks * 32, 16, 512, 4);
-          // V as K-major B: row n = (h_local*32 + w) at 64 B pitch, 8-row groups 512 B apart, k-step (16 c) = +32 B
-          const uint32_t vb = v_base + (uint32_t)p * 256u * 64u + ks * 32;
-          const uint64_t b_hi = make_smem_desc(vb, 16, 512, 4);
-          const uint64_t b_lo = make_smem_desc(vb + V_PLANE_BYTES, 16, 512, 4);
-          umma_bf16_ss(d, a_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u);
-          umma_bf16_ss(d, a_lo, b_hi, a.idesc, 1);
-          umma_bf16_ss(d, a_hi, b_hi, a.idesc, 1);
+          for (int ks = 0; ks < HD / 16; ++ks) {
+            const uint64_t a_hi = make_smem_desc(a_base + ks * 32, 16, 512, 4);
+            const uint64_t a_lo = make_smem_desc(a_base + A_PLANE_BYTES + ks * 32, 16, 512, 4);
+            // V as K-major B: row n = (h_local*32 + w) at 64 B pitch, 8-row groups 512 B apart, k-step (16 c) = +32 B
+            const uint32_t vb = v_base + (uint32_t)p * 256u * 64u + ks * 32;
+            const uint64_t b_hi = make_smem_desc(vb, 16, 512, 4);
+            const uint64_t b_lo = make_smem_desc(vb + V_PLANE_BYTES, 16, 512, 4);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc, 1);
+          }
+          umma_commit(&t_full[g]);
         }
-        umma_commit(&t_full[p & 1]);
       }
     }
   } else {
-    const int ct = threadIdx.x - 64;
+    const int ct = threadIdx.x - 64;       // 0..255
+    const int g = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    const int q = q0 + r;
+    const int q = q_cta + g * TQ + r;
     const bool ok = q < a.L;
+    const bool active = q_cta + g * TQ < a.L;
     const int64_t bh = (int64_t)b * a.nh + head;
-    // dO row -> split-bf16 A operand (SWIZZLE_64B)
-    {
-      float dov[HD];
-      if (ok) {
-        const float4* dp = reinterpret_cast<const float4*>(a.d_o + ((int64_t)b * a.L + q) * a.E + head * HD);
+    float* acg = acs + g * 32 * TQ;
+    float* dacg = dacs + g * 32 * TQ;
+    float ar[32], dar[32];
+    if (active) {
+      uint8_t* Ag = As + (size_t)g * 2 * A_PLANE_BYTES;
+      {  // dO row -> split-bf16 A operand (SWIZZLE_64B)
+        float dov[HD];
+        if (ok) {
+          const float4* dp = reinterpret_cast<const float4*>(a.d_o + ((int64_t)b * a.L + q) * a.E + head * HD);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = __ldg(dp + j);
-          dov[4 * j] = t.x; dov[4 * j + 1] = t.y; dov[4 * j + 2] = t.z; dov[4 * j + 3] = t.w;
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(dp + j);
+            dov[4 * j] = t.x; dov[4 * j + 1] = t.y; dov[4 * j + 2] = t.z; dov[4 * j + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < HD; ++j) dov[j] = 0.0f;
         }
-      } else {
 #pragma unroll
-        for (int j = 0; j < HD; ++j) dov[j] = 0.0f;
+        for (int j = 0; j < 4; ++j) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(dov[8 * j + 2 * i], h0, l0);
+            split_bf16(dov[8 * j + 2 * i + 1], h1, l1);
+            hw[i] = pack_bf16x2(h0, h1);
+            lw[i] = pack_bf16x2(l0, l1);
+          }
+          const uint32_t off = (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(Ag + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(Ag + A_PLANE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        fence_proxy_async();
+        mbar_arrive(&a_ready[g]);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(dov[8 * j + 2 * i], h0, l0);
-          split_bf16(dov[8 * j + 2 * i + 1], h1, l1);
-          hw[i] = pack_bf16x2(h0, h1);
-          lw[i] = pack_bf16x2(l0, l1);
-        }
-        const uint32_t off = (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4);
-        *reinterpret_cast<uint4*>(As + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(As + A_PLANE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      for (int k = 0; k < 32; ++k) {
+        ar[k] = (ok && k < a.W) ? __ldg(a.ar + (bh * a.W + k) * a.L + q) : 0.0f;
+        acg[k * TQ + r] = (ok && k < a.H) ? __ldg(a.ac + (bh * a.H + k) * a.L + q) : 0.0f;
+        dacg[k * TQ + r] = 0.0f;
+        dar[k] = 0.0f;
       }
-      fence_proxy_async();
-      mbar_arrive(a_ready);
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * 256u;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        if (p < nblk) {
+          mbar_wait(&t_full[g], (uint32_t)p & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int hi = 0; hi < 8; ++hi) {
+            uint32_t t[32];
+            tmem_ld_32x32b_x32(taddr_row + (uint32_t)hi * 32u, t);
+            tmem_ld_wait();
+            const float cc = acg[(p * 8 + hi) * TQ + r];
+            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 32; w += 2) {
+              const float g0 = __uint_as_float(t[w]), g1 = __uint_as_float(t[w + 1]);
+              s0 += ar[w] * g0;
+              s1 += ar[w + 1] * g1;
+              dar[w] += cc * g0;
+              dar[w + 1] += cc * g1;
+            }
+            dacg[(p * 8 + hi) * TQ + r] = s0 + s1;
+          }
+          tc_fence_before();
+          mbar_arrive(&t_empty[g]);
+        }
+      }
     }
-    for (int i = ct; i < 32 * HD; i += 128) {
+    // every MMA has completed once both groups are past their last t_full wait: reuse the V region for K
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float* Ksr = reinterpret_cast<float*>(Vs);
+    float* Ksc = Ksr + 32 * HD;
+    for (int i = ct; i < 32 * HD; i += 256) {
       const int k = i / HD, dch = i % HD;
       Ksr[i] = k < a.W ? a.kr[((int64_t)b * a.W + k) * a.E + head * HD + dch] : 0.0f;
       Ksc[i] = k < a.H ? a.kc[((int64_t)b * a.H + k) * a.E + head * HD + dch] : 0.0f;
     }
-    float ar[32], dar[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      ar[k] = (ok && k < a.W) ? __ldg(a.ar + (bh * a.W + k) * a.L + q) : 0.0f;
-      acs[k * TQ + ct] = (ok && k < a.H) ? __ldg(a.ac + (bh * a.H + k) * a.L + q) : 0.0f;
-      dacs[k * TQ + ct] = 0.0f;
-      dar[k] = 0.0f;
-    }
-    const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      if (p < nblk) {
-        mbar_wait(&t_full[p & 1], (uint32_t)(p >> 1) & 1u);
-        tc_fence_after();
-#pragma unroll
-        for (int hi = 0; hi < 8; ++hi) {
-          uint32_t t[32];
-          tmem_ld_32x32b_x32(taddr_row + (uint32_t)(p & 1) * 256u + (uint32_t)hi * 32u, t);
-          tmem_ld_wait();
-          const float cc = acs[(p * 8 + hi) * TQ + ct];
-          float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-          for (int w = 0; w < 32; w += 2) {
-            const float g0 = __uint_as_float(t[w]), g1 = __uint_as_float(t[w + 1]);
-            s0 += ar[w] * g0;
-            s1 += ar[w + 1] * g1;
-            dar[w] += cc * g0;
-            dar[w + 1] += cc * g1;
-          }
-          dacs[(p * 8 + hi) * TQ + ct] = s0 + s1;
-        }
-        tc_fence_before();
-        mbar_arrive(&t_empty[p & 1]);
-      }
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // K slices staged
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (ok) {
       const float scale = rsqrtf((float)HD);
       {
@@ -454,30 +470,30 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
         }
         const int64_t off = ((int64_t)b * a.L + q) * a.ld_g + head * HD;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int gg = 0; gg < 4; ++gg) {
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(dq[g * 8 + 2 * j] * scale, h0, l0);
-            split_bf16(dq[g * 8 + 2 * j + 1] * scale, h1, l1);
+            split_bf16(dq[gg * 8 + 2 * j] * scale, h0, l0);
+            split_bf16(dq[gg * 8 + 2 * j + 1] * scale, h1, l1);
             hw[j] = pack_bf16x2(h0, h1);
             lw[j] = pack_bf16x2(l0, l1);
           }
-          reinterpret_cast<uint4*>(a.dqr_hi + off)[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          reinterpret_cast<uint4*>(a.dqr_lo + off)[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          reinterpret_cast<uint4*>(a.dqr_hi + off)[gg] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          reinterpret_cast<uint4*>(a.dqr_lo + off)[gg] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
       }
       {
         float dot = 0.0f;
 #pragma unroll
-        for (int h = 0; h < 32; ++h) dot += acs[h * TQ + ct] * dacs[h * TQ + ct];
+        for (int h = 0; h < 32; ++h) dot += acg[h * TQ + r] * dacg[h * TQ + r];
         float dq[HD];
 #pragma unroll
         for (int j = 0; j < HD; ++j) dq[j] = 0.0f;
 #pragma unroll
         for (int h = 0; h < 32; ++h) {
-          const float ds = acs[h * TQ + ct] * (dacs[h * TQ + ct] - dot);
+          const float ds = acg[h * TQ + r] * (dacg[h * TQ + r] - dot);
           if (h < a.H) a.dsc[(bh * a.H + h) * a.L + q] = ds;
           const float4* kp = reinterpret_cast<const float4*>(Ksc + h * HD);
 #pragma unroll
@@ -488,18 +504,18 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
         }
         const int64_t off = ((int64_t)b * a.L + q) * a.ld_g + head * HD;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int gg = 0; gg < 4; ++gg) {
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(dq[g * 8 + 2 * j] * scale, h0, l0);
-            split_bf16(dq[g * 8 + 2 * j + 1] * scale, h1, l1);
+            split_bf16(dq[gg * 8 + 2 * j] * scale, h0, l0);
+            split_bf16(dq[gg * 8 + 2 * j + 1] * scale, h1, l1);
             hw[j] = pack_bf16x2(h0, h1);
             lw[j] = pack_bf16x2(l0, l1);
           }
-          reinterpret_cast<uint4*>(a.dqc_hi + off)[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          reinterpret_cast<uint4*>(a.dqc_lo + off)[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          reinterpret_cast<uint4*>(a.dqc_hi + off)[gg] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          reinterpret_cast<uint4*>(a.dqc_lo + off)[gg] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
       }
     }
@@ -556,13 +572,13 @@ extern "C" int cdetr_rcda_fwd_tc(int B, int L, int H, int W, int E, int nh, cons
   a.qr = qr; a.qc = qc; a.kr = kr; a.kc = kc; a.mask_row = mask_row; a.mask_col = mask_col; a.ar = ar; a.ac = ac;
   a.o_hi = reinterpret_cast<__nv_bfloat16*>(o.base); a.o_lo = a.o_hi + o.plane; a.ld_o = o.ld;
   a.idesc = make_idesc_bf16_f32(TQ, 256, 0, 1);
-  const size_t smem = 2 * V_PLANE_BYTES + 2 * A_PLANE_BYTES + 2 * 32 * HD * sizeof(float) + 64 + 1024;
+  const size_t smem = 2 * V_PLANE_BYTES + 4 * A_PLANE_BYTES + 2 * 32 * HD * sizeof(float) + 128 + 1024;
   static bool once = false;
   if (!once) {
     CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     once = true;
   }
-  rcda_fwd_tc_kernel<<<dim3(cdiv(L, TQ), nh, B), 192, smem, reinterpret_cast<cudaStream_t>(s)>>>(tm, a);
+  rcda_fwd_tc_kernel<<<dim3(cdiv(L, 2 * TQ), nh, B), 320, smem, reinterpret_cast<cudaStream_t>(s)>>>(tm, a);
   CDETR_CHECK_LAUNCH();
   return 0;
 }
@@ -602,13 +618,13 @@ extern "C" int cdetr_rcda_bwd_q_tc(int B, int L, int H, int W, int E, int nh, co
   a.dqc_hi = reinterpret_cast<__nv_bfloat16*>(dqc.base); a.dqc_lo = a.dqc_hi + dqc.plane;
   a.ld_g = dqr.ld;
   a.idesc = make_idesc_bf16_f32(TQ, 256, 0, 0);
-  const size_t smem = 2 * V_PLANE_BYTES + 2 * A_PLANE_BYTES + 2 * 32 * HD * sizeof(float) + 2 * 32 * TQ * sizeof(float) + 64 + 1024;
+  const size_t smem = 2 * V_PLANE_BYTES + 4 * A_PLANE_BYTES + 4 * 32 * TQ * sizeof(float) + 128 + 1024;
   static bool once = false;
   if (!once) {
     CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_q_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     once = true;
   }
-  rcda_bwd_q_tc_kernel<<<dim3(cdiv(L, TQ), nh, B), 192, smem, reinterpret_cast<cudaStream_t>(s)>>>(tm, a);
+  rcda_bwd_q_tc_kernel<<<dim3(cdiv(L, 2 * TQ), nh, B), 320, smem, reinterpret_cast<cudaStream_t>(s)>>>(tm, a);
   CDETR_CHECK_LAUNCH();
   return 0;
 }

@@ -229,10 +229,10 @@ class Engine:
         H, W = (H0 + 2 - 3) // 2 + 1, (W0 + 2 - 3) // 2 + 1
         x = self.sbuf("pool_out", B * H * W, 64)
         L.call("cdetr_maxpool3x3s2", a0, B, H0, W0, 64, x)
-        max_col = 0
+        max_col, Hs, Ws = 0, H, W
         for blk in self.blocks:
-            Ho, Wo = (H - 1) // blk["stride"] + 1, (W - 1) // blk["stride"] + 1
-            max_col = max(max_col, B * Ho * Wo * _r8(9 * blk["planes"]))
+            Hs, Ws = (Hs - 1) // blk["stride"] + 1, (Ws - 1) // blk["stride"] + 1
+            max_col = max(max_col, B * Hs * Ws * _r8(9 * blk["planes"]))
         colbuf = self.buf("col_scratch", (2, max_col), torch.bfloat16)
         for blk in self.blocks:
             n, p_, s, d = blk["name"], blk["planes"], blk["stride"], blk["dil"]
@@ -241,7 +241,10 @@ class Engine:
             Mo = B * Ho * Wo
             a = self.sbuf(n + ".a", Min, p_)
             blk["c1"].fwd(x, Min, out_split=a, relu=True)
-            col = colbuf[:, : Mo * 9 * p_].view(2, Mo, 9 * p_)
+            if blk["train"]:     # kept for the wgrad GEMM of the backward pass (3 GB at C3; saves the re-gather)
+                col = self.sbuf(n + ".col", Mo, 9 * p_)
+            else:
+                col = colbuf[:, : Mo * 9 * p_].view(2, Mo, 9 * p_)
             L.call("cdetr_im2col3x3", a, B, H, W, p_, s, d, col)
             b = self.sbuf(n + ".b", Mo, p_)
             blk["c2"].fwd(col, Mo, out_split=b, relu=True)
@@ -257,15 +260,14 @@ class Engine:
                 xs, idt = None, x
             out = self.sbuf(n + ".out", Mo, 4 * p_)
             blk["c3"].fwd(b, Mo, out_split=out, add_split=idt, relu=True)
-            sv[n] = dict(x=x, a=a, b=b, xs=xs, out=out, H=H, W=W, Ho=Ho, Wo=Wo)
+            sv[n] = dict(x=x, a=a, b=b, xs=xs, out=out, col=col, H=H, W=W, Ho=Ho, Wo=Wo)
             x, H, W = out, Ho, Wo
         return x, H, W
 
     def _backbone_bwd(self, g, B):
         """g: split grad w.r.t. the last block's output, already masked by that output's ReLU."""
         sv = self.saved
-        colbuf = self.buf("col_scratch", self._bufs_key_shape("col_scratch"), torch.bfloat16)
-        col2buf = self.buf("col_scratch2", self._bufs_key_shape("col_scratch"), torch.bfloat16)
+        col2buf = self.buf("col_scratch", self._bufs_key_shape("col_scratch"), torch.bfloat16)  # free after the forward
         for blk in reversed(self.blocks):
             if not blk["train"]:
                 break
@@ -277,9 +279,7 @@ class Engine:
             blk["c3"].wgrad(g, t["b"], Mo)
             db = self.sbuf(n + ".db", Mo, p_)
             blk["c3"].dgrad(g, Mo, out_split=db, mask=t["b"])
-            col = colbuf[:, : Mo * 9 * p_].view(2, Mo, 9 * p_)
-            L.call("cdetr_im2col3x3", t["a"], B, H, W, p_, s, d, col)
-            blk["c2"].wgrad(db, col, Mo)
+            blk["c2"].wgrad(db, t["col"], Mo)
             dcol = col2buf[:, : Mo * 9 * p_].view(2, Mo, 9 * p_)
             blk["c2"].dgrad(db, Mo, out_split=dcol)
             da = self.sbuf(n + ".da", Min, p_)
