@@ -149,6 +149,8 @@ _SIGS = {
     "cdetr_rcda_fwd": "iiiiiipppppppppS",
     "cdetr_rcda_fwd_tc": "iiiiiippppSppppS",
     "cdetr_rcda_bwd_q_tc": "iiiiiippSpppppSS",
+    "cdetr_rcda_bwd_v_tc": "iiiiiippSS",
+    "cdetr_rcda_bwd_k": "iiiiiippppSS",
     "cdetr_rcda_bwd_kv": "iiiiiipppppppSSS",
     "cdetr_rcda_bwd": "iiiiiippppppppppSSSSS",
     "cdetr_mha_fwd": "iiiippplSp",

@@ -326,8 +326,14 @@ __global__ void rcda_bwd_v_kernel(const RcdaArgs a) {
 }
 
 // ------------------------------------------------------------------ backward 3: dK_r / dK_c
-// dK[k,d] = s * sum_q dS[k,q] * q[q,d];  grid (nh, B, 2), block (32, 32): threadIdx.x = d, y strides keys.
-__global__ void rcda_bwd_k_kernel(const RcdaArgs a) {
+// dK[k,d] = s * sum_q dS[k,q] * q[q,d];  grid (nh, B, 2), 256 threads = 8 key groups x 32 channels.
+// Queries are staged in tiles of 64 (dS rows and q rows both load coalesced); warp = key group, so the dS
+// operand is a shared-memory broadcast and the q operand is conflict-free.
+constexpr int KQ = 64;
+constexpr int KMAX = 64;   // max keys per side handled by this kernel (H, W <= 64)
+__global__ void __launch_bounds__(256) rcda_bwd_k_kernel(const RcdaArgs a) {
+  __shared__ float dss[KMAX][KQ + 1];
+  __shared__ float qs[KQ][HD];
   const int head = blockIdx.x, b = blockIdx.y, which = blockIdx.z;
   const int n = which == 0 ? a.W : a.H;
   const float* ds = which == 0 ? a.dsr : a.dsc;
@@ -335,19 +341,36 @@ __global__ void rcda_bwd_k_kernel(const RcdaArgs a) {
   __nv_bfloat16* ohi = which == 0 ? a.dkr_hi : a.dkc_hi;
   __nv_bfloat16* olo = which == 0 ? a.dkr_lo : a.dkc_lo;
   const int64_t bh = (int64_t)b * a.nh + head;
-  const int d = threadIdx.x;
-  const float scale = rsqrtf((float)HD);
-  for (int k = threadIdx.y; k < n; k += blockDim.y) {
-    const float* dsk = ds + (bh * n + k) * a.L;
-    float acc0 = 0.0f, acc1 = 0.0f;
-    int q = 0;
-    for (; q + 1 < a.L; q += 2) {
-      acc0 += __ldg(dsk + q) * __ldg(qp + ((int64_t)b * a.L + q) * a.E + head * HD + d);
-      acc1 += __ldg(dsk + q + 1) * __ldg(qp + ((int64_t)b * a.L + q + 1) * a.E + head * HD + d);
+  const int d = threadIdx.x & 31, kg = threadIdx.x >> 5;
+  float acc[KMAX / 8];
+#pragma unroll
+  for (int i = 0; i < KMAX / 8; ++i) acc[i] = 0.0f;
+  for (int q0 = 0; q0 < a.L; q0 += KQ) {
+    const int nq = min(KQ, a.L - q0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * KQ; i += 256) {
+      const int k = i / KQ, qq = i % KQ;
+      dss[k][qq] = qq < nq ? __ldg(ds + (bh * n + k) * a.L + q0 + qq) : 0.0f;
     }
-    if (q < a.L) acc0 += __ldg(dsk + q) * __ldg(qp + ((int64_t)b * a.L + q) * a.E + head * HD + d);
-    const int64_t off = ((int64_t)b * n + k) * a.ld_g + head * HD + d;
-    split_bf16((acc0 + acc1) * scale, ohi[off], olo[off]);
+    for (int i = threadIdx.x; i < KQ * HD; i += 256) {
+      const int qq = i / HD, dd = i % HD;
+      qs[qq][dd] = qq < nq ? __ldg(qp + ((int64_t)b * a.L + q0 + qq) * a.E + head * HD + dd) : 0.0f;
+    }
+    __syncthreads();
+    for (int qq = 0; qq < KQ; ++qq) {
+      const float qv = qs[qq][d];
+#pragma unroll
+      for (int i = 0; i < KMAX / 8; ++i) acc[i] += dss[kg + 8 * i][qq] * qv;
+    }
+  }
+  const float scale = rsqrtf((float)HD);
+#pragma unroll
+  for (int i = 0; i < KMAX / 8; ++i) {
+    const int k = kg + 8 * i;
+    if (k < n) {
+      const int64_t off = ((int64_t)b * n + k) * a.ld_g + head * HD + d;
+      split_bf16(acc[i] * scale, ohi[off], olo[off]);
+    }
   }
 }
 
@@ -394,6 +417,7 @@ extern "C" int cdetr_rcda_bwd(int B, int L, int H, int W, int E, int nh, const f
                               cdetr_stream_t s_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
   CDETR_CHECK_ARG(E == nh * HD, "rcda_bwd: head dim must be 32");
+  CDETR_CHECK_ARG(H <= KMAX && W <= KMAX, "rcda_bwd: H, W must be <= 64");
   CDETR_CHECK_ARG(qr && qc && kr && kc && v && ar && ac && d_o && dsr && dsc && dqr.base && dqc.base &&
                       dkr.base && dkc.base && dv.base,
                   "rcda_bwd: null pointer");
@@ -426,7 +450,7 @@ extern "C" int cdetr_rcda_bwd(int B, int L, int H, int W, int E, int nh, const f
   { static bool once_rcda_bwd_v_kernel = false; if (!once_rcda_bwd_v_kernel) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); once_rcda_bwd_v_kernel = true; } }
   rcda_bwd_v_kernel<<<dim3(cdiv(H * W, TV), nh, B), TV, smem_v, s>>>(a);
   CDETR_CHECK_LAUNCH();
-  rcda_bwd_k_kernel<<<dim3(nh, B, 2), dim3(32, 32), 0, s>>>(a);
+  rcda_bwd_k_kernel<<<dim3(nh, B, 2), 256, 0, s>>>(a);
   CDETR_CHECK_LAUNCH();
   return 0;
 }
@@ -438,6 +462,7 @@ extern "C" int cdetr_rcda_bwd_kv(int B, int L, int H, int W, int E, int nh, cons
                                  cdetr_stream_t s_) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
   CDETR_CHECK_ARG(E == nh * HD, "rcda_bwd_kv: head dim must be 32");
+  CDETR_CHECK_ARG(H <= KMAX && W <= KMAX, "rcda_bwd_kv: H, W must be <= 64");
   CDETR_CHECK_ARG(qr && qc && ar && ac && d_o && dsr && dsc && dkr.base && dkc.base && dv.base, "rcda_bwd_kv: null pointer");
   CDETR_CHECK_ARG(dkr.ld == dkc.ld && dkr.ld == dv.ld, "rcda_bwd_kv: gradient tensors must share ld");
   RcdaArgs a = {};
@@ -454,7 +479,25 @@ extern "C" int cdetr_rcda_bwd_kv(int B, int L, int H, int W, int E, int nh, cons
   { static bool once = false; if (!once) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); once = true; } }
   rcda_bwd_v_kernel<<<dim3(cdiv(H * W, TV), nh, B), TV, smem_v, s>>>(a);
   CDETR_CHECK_LAUNCH();
-  rcda_bwd_k_kernel<<<dim3(nh, B, 2), dim3(32, 32), 0, s>>>(a);
+  rcda_bwd_k_kernel<<<dim3(nh, B, 2), 256, 0, s>>>(a);
+  CDETR_CHECK_LAUNCH();
+  return 0;
+}
+
+// dK_r / dK_c only (the tensor-core path computes dV in cdetr_rcda_bwd_v_tc).
+extern "C" int cdetr_rcda_bwd_k(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc,
+                                const float* dsr, const float* dsc, cdetr_split_t dkr, cdetr_split_t dkc,
+                                cdetr_stream_t s_) {
+  CDETR_CHECK_ARG(E == nh * HD, "rcda_bwd_k: head dim must be 32");
+  CDETR_CHECK_ARG(H <= KMAX && W <= KMAX, "rcda_bwd_k: H, W must be <= 64");
+  CDETR_CHECK_ARG(qr && qc && dsr && dsc && dkr.base && dkc.base && dkr.ld == dkc.ld, "rcda_bwd_k: bad args");
+  RcdaArgs a = {};
+  a.B = B; a.L = L; a.H = H; a.W = W; a.E = E; a.nh = nh;
+  a.qr = qr; a.qc = qc; a.dsr = const_cast<float*>(dsr); a.dsc = const_cast<float*>(dsc);
+  a.dkr_hi = reinterpret_cast<__nv_bfloat16*>(dkr.base); a.dkr_lo = a.dkr_hi + dkr.plane;
+  a.dkc_hi = reinterpret_cast<__nv_bfloat16*>(dkc.base); a.dkc_lo = a.dkc_hi + dkc.plane;
+  a.ld_g = dkr.ld;
+  rcda_bwd_k_kernel<<<dim3(nh, B, 2), 256, 0, reinterpret_cast<cudaStream_t>(s_)>>>(a);
   CDETR_CHECK_LAUNCH();
   return 0;
 }

@@ -528,6 +528,191 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward (value side) on tensor cores:  dV[(h,w), c] = sum_q A_c[q,h] A_r[q,w] dO[q,c]
+// One CTA per (sample, head).  Per block of 64 queries: dO tile by TMA (split planes, SWIZZLE_64B, MN-major B
+// operand), the attention maps of those queries staged in shared memory, and for each 128-row tile of key
+// positions the compute warps build P[(h,w), q] = A_c A_r as a split-bf16 K-major A operand (SWIZZLE_128B,
+// double buffered) which one thread multiplies into the tile's 32 TMEM columns: the [L, H*W] outer-product
+// matrix exists only 32 KB at a time.  All ceil(HW/128) accumulators (<= 256 TMEM columns) stay resident.
+constexpr int VK = 64;                                   // queries per k block
+constexpr uint32_t P_TILE_BYTES = 128 * VK * 2;          // one plane of the P tile: 16 KB
+constexpr uint32_t DO_PLANE_BYTES = VK * HD * 2;         // 4 KB
+constexpr int MAP_LD = 68;                               // padded pitch of the staged attention maps
+
+struct TcBwdVArgs {
+  int B, L, H, W, E, nh;
+  const float* ar;  // [B,nh,W,L]
+  const float* ac;  // [B,nh,H,L]
+  __nv_bfloat16 *dv_hi, *dv_lo;
+  int64_t ld_g;
+  uint32_t idesc;
+};
+
+__global__ void __launch_bounds__(320, 1)
+rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Ps = smem;                                    // [2 bufs][2 planes][128][64] bf16, SW128 K-major
+  uint8_t* Ds = Ps + 4 * P_TILE_BYTES;                   // [2 bufs][2 planes][64 q][32 c] bf16, SW64
+  float* ars = reinterpret_cast<float*>(Ds + 4 * DO_PLANE_BYTES);   // [32][MAP_LD]
+  float* acs = ars + 32 * MAP_LD;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(acs + 32 * MAP_LD);
+  uint64_t* d_full = bars;       // [2]
+  uint64_t* d_empty = bars + 2;  // [2]
+  uint64_t* p_full = bars + 4;   // [2]
+  uint64_t* p_empty = bars + 6;  // [2]
+  uint64_t* acc_full = bars + 8;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 9);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int HW = a.H * a.W;
+  const int ntile = (HW + 127) / 128;
+  const int nkb = (a.L + VK - 1) / VK;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmD);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d_full[i], 1);
+      mbar_init(&d_empty[i], 1);
+      mbar_init(&p_full[i], 256);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        if (kb >= 2) mbar_wait(&d_empty[s], (uint32_t)((kb >> 1) - 1) & 1u);
+        mbar_arrive_expect_tx(&d_full[s], 2 * DO_PLANE_BYTES);
+        tma_load_3d(Ds + s * 2 * DO_PLANE_BYTES, &tmD, &d_full[s], head * HD, b * a.L + kb * VK, 0);
+        tma_load_3d(Ds + s * 2 * DO_PLANE_BYTES + DO_PLANE_BYTES, &tmD, &d_full[s], head * HD, b * a.L + kb * VK, 1);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int u = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        mbar_wait(&d_full[s], (uint32_t)(kb >> 1) & 1u);
+        const uint32_t d_base = smem_u32(Ds) + (uint32_t)s * 2u * DO_PLANE_BYTES;
+        for (int mt = 0; mt < ntile; ++mt, ++u) {
+          const int pb = u & 1;
+          mbar_wait(&p_full[pb], (uint32_t)(u >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t p_base = smem_u32(Ps) + (uint32_t)pb * 2u * P_TILE_BYTES;
+          const uint32_t d = tmem_base + (uint32_t)mt * 32u;
+#pragma unroll
+          for (int ks = 0; ks < VK / 16; ++ks) {
+            const uint64_t a_hi = make_smem_desc(p_base + ks * 32, 16, 1024, 2);                 // K-major SW128
+            const uint64_t a_lo = make_smem_desc(p_base + P_TILE_BYTES + ks * 32, 16, 1024, 2);
+            const uint64_t b_hi = make_smem_desc(d_base + ks * 1024, 4096, 512, 4);              // MN-major SW64
+            const uint64_t b_lo = make_smem_desc(d_base + DO_PLANE_BYTES + ks * 1024, 4096, 512, 4);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc, 1);
+          }
+          umma_commit(&p_empty[pb]);
+        }
+        umma_commit(&d_empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int ct = threadIdx.x - 64;        // 0..255
+    const int ml = ct >> 1;                 // row of the P tile built by this thread
+    const int qh = ct & 1;                  // which half (32 queries) of the k block
+    const int64_t bh = (int64_t)b * a.nh + head;
+    int u = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int q0 = kb * VK;
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // previous block's tiles are all built
+      for (int i = ct; i < 32 * VK; i += 256) {
+        const int k = i / VK, qq = i % VK;
+        const bool qok = q0 + qq < a.L;
+        ars[k * MAP_LD + qq] = (qok && k < a.W) ? __ldg(a.ar + (bh * a.W + k) * a.L + q0 + qq) : 0.0f;
+        acs[k * MAP_LD + qq] = (qok && k < a.H) ? __ldg(a.ac + (bh * a.H + k) * a.L + q0 + qq) : 0.0f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int mt = 0; mt < ntile; ++mt, ++u) {
+        const int pb = u & 1;
+        if (u >= 2) mbar_wait(&p_empty[pb], (uint32_t)((u >> 1) - 1) & 1u);
+        const int m = mt * 128 + ml;
+        const bool mok = m < HW;
+        const int h = mok ? m / a.W : 0, w = mok ? m % a.W : 0;
+        const float4* cr = reinterpret_cast<const float4*>(acs + h * MAP_LD + qh * 32);
+        const float4* rr = reinterpret_cast<const float4*>(ars + w * MAP_LD + qh * 32);
+        uint8_t* Pb = Ps + (size_t)pb * 2 * P_TILE_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {        // 4 chunks of 8 queries
+          float pv[8];
+          const float4 c0 = cr[2 * j], c1 = cr[2 * j + 1], r0 = rr[2 * j], r1 = rr[2 * j + 1];
+          pv[0] = c0.x * r0.x; pv[1] = c0.y * r0.y; pv[2] = c0.z * r0.z; pv[3] = c0.w * r0.w;
+          pv[4] = c1.x * r1.x; pv[5] = c1.y * r1.y; pv[6] = c1.z * r1.z; pv[7] = c1.w * r1.w;
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(mok ? pv[2 * i] : 0.0f, h0, l0);
+            split_bf16(mok ? pv[2 * i + 1] : 0.0f, h1, l1);
+            hw[i] = pack_bf16x2(h0, h1);
+            lw[i] = pack_bf16x2(l0, l1);
+          }
+          const uint32_t off = (uint32_t)ml * 128u + (uint32_t)(((qh * 4 + j) ^ (ml & 7)) << 4);
+          *reinterpret_cast<uint4*>(Pb + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(Pb + P_TILE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        fence_proxy_async();
+        mbar_arrive(&p_full[pb]);
+      }
+    }
+    // ---- epilogue: accumulators -> dV (split)
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    for (int mt = grp; mt < ntile; mt += 2) {
+      uint32_t t[32];
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)mt * 32u, t);
+      tmem_ld_wait();
+      const int m = mt * 128 + quarter * 32 + lane;
+      if (m < HW) {
+        const int64_t off = ((int64_t)b * HW + m) * a.ld_g + head * HD;
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(__uint_as_float(t[gg * 8 + 2 * j]), h0, l0);
+            split_bf16(__uint_as_float(t[gg * 8 + 2 * j + 1]), h1, l1);
+            hw[j] = pack_bf16x2(h0, h1);
+            lw[j] = pack_bf16x2(l0, l1);
+          }
+          reinterpret_cast<uint4*>(a.dv_hi + off)[gg] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          reinterpret_cast<uint4*>(a.dv_lo + off)[gg] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -625,6 +810,40 @@ extern "C" int cdetr_rcda_bwd_q_tc(int B, int L, int H, int W, int E, int nh, co
     once = true;
   }
   rcda_bwd_q_tc_kernel<<<dim3(cdiv(L, 2 * TQ), nh, B), 320, smem, reinterpret_cast<cudaStream_t>(s)>>>(tm, a);
+  CDETR_CHECK_LAUNCH();
+  return 0;
+}
+
+// Value-side backward on tensor cores.  d_o: split [B*L, E] (gradient of the attention output before out_proj).
+extern "C" int cdetr_rcda_bwd_v_tc(int B, int L, int H, int W, int E, int nh, const float* ar, const float* ac,
+                                   cdetr_split_t d_o, cdetr_split_t dv, cdetr_stream_t s) {
+  CDETR_CHECK_ARG(E == nh * HD, "rcda_bwd_v_tc: head dim must be 32");
+  CDETR_CHECK_ARG(H >= 1 && W >= 1 && H <= 32 && W <= 32, "rcda_bwd_v_tc: H, W must be <= 32");
+  CDETR_CHECK_ARG(ar && ac && d_o.base && dv.base, "rcda_bwd_v_tc: null pointer");
+  CDETR_CHECK_ARG(d_o.ld % 8 == 0 && d_o.plane % 8 == 0 && (reinterpret_cast<uintptr_t>(d_o.base) & 15) == 0,
+                  "rcda_bwd_v_tc: dO must be 16-byte aligned with ld/plane multiples of 8");
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { cdetr_set_error("cuTensorMapEncodeTiled entry point unavailable"); return CDETR_ERR_CUDA; }
+  CUtensorMap tm;
+  cuuint64_t gdim[3] = {(cuuint64_t)E, (cuuint64_t)B * L, 2};
+  cuuint64_t gstr[2] = {(cuuint64_t)d_o.ld * 2, (cuuint64_t)d_o.plane * 2};
+  cuuint32_t box[3] = {HD, VK, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, d_o.base, gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { cdetr_set_error("rcda_bwd_v_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return CDETR_ERR_CUDA; }
+  TcBwdVArgs a = {};
+  a.B = B; a.L = L; a.H = H; a.W = W; a.E = E; a.nh = nh; a.ar = ar; a.ac = ac;
+  a.dv_hi = reinterpret_cast<__nv_bfloat16*>(dv.base); a.dv_lo = a.dv_hi + dv.plane; a.ld_g = dv.ld;
+  a.idesc = make_idesc_bf16_f32(128, HD, 0, 1);
+  const size_t smem = 4 * P_TILE_BYTES + 4 * DO_PLANE_BYTES + 2 * 32 * MAP_LD * sizeof(float) + 128 + 1024;
+  static bool once = false;
+  if (!once) {
+    CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_v_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    once = true;
+  }
+  rcda_bwd_v_tc_kernel<<<dim3(nh, B), 320, smem, reinterpret_cast<cudaStream_t>(s)>>>(tm, a);
   CDETR_CHECK_LAUNCH();
   return 0;
 }

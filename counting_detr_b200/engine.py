@@ -414,15 +414,16 @@ class Engine:
         M, N = B * Lq, B * H * W
         self.lins[lin_out].wgrad(dattn_s, t["o"], M)
         dO = self.buf(q + ".dO", (M, E))
-        self.lins[lin_out].dgrad(dattn_s, M, out_f32=dO)
+        dO_s = self.sbuf(q + ".dO_s", M, E) if t["v_s"] is not None else None
+        self.lins[lin_out].dgrad(dattn_s, M, out_f32=dO, out_split=dO_s)
         dsr = self.buf(q + ".dsr", (B, self.nh, W, Lq)); dsc = self.buf(q + ".dsc", (B, self.nh, H, Lq))
         dqr = self.sbuf(q + ".dqr", M, E); dqc = self.sbuf(q + ".dqc", M, E)
         dkr = self.sbuf(q + ".dkr", B * W, E); dkc = self.sbuf(q + ".dkc", B * H, E); dv = self.sbuf(q + ".dv", N, E)
         if t["v_s"] is not None:     # tcgen05 query-side kernel + key/value-side kernels
             L.call("cdetr_rcda_bwd_q_tc", B, Lq, H, W, E, self.nh, t["kr"], t["kc"], t["v_s"], t["ar"], t["ac"], dO,
                    dsr, dsc, dqr, dqc)
-            L.call("cdetr_rcda_bwd_kv", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], t["ar"], t["ac"], dO, dsr, dsc,
-                   dkr, dkc, dv)
+            L.call("cdetr_rcda_bwd_v_tc", B, Lq, H, W, E, self.nh, t["ar"], t["ac"], dO_s, dv)
+            L.call("cdetr_rcda_bwd_k", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], dsr, dsc, dkr, dkc)
         else:
             L.call("cdetr_rcda_bwd", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], t["kr"], t["kc"], t["v"], t["ar"],
                    t["ac"], dO, dsr, dsc, dqr, dqc, dkr, dkc, dv)

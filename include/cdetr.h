@@ -155,6 +155,12 @@ int cdetr_rcda_fwd_tc(int B, int L, int H, int W, int E, int nh, const float* qr
 int cdetr_rcda_bwd_q_tc(int B, int L, int H, int W, int E, int nh, const float* kr, const float* kc, cdetr_split_t v,
                         const float* ar, const float* ac, const float* d_o, float* dsr, float* dsc,
                         cdetr_split_t dqr, cdetr_split_t dqc, cdetr_stream_t s);
+/* Value-side backward on tensor cores (d_o as a split tensor [B*L, E]); H, W <= 32. */
+int cdetr_rcda_bwd_v_tc(int B, int L, int H, int W, int E, int nh, const float* ar, const float* ac,
+                        cdetr_split_t d_o, cdetr_split_t dv, cdetr_stream_t s);
+/* Key-side backward only: dK_r, dK_c (split) from the dS maps. */
+int cdetr_rcda_bwd_k(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc, const float* dsr,
+                     const float* dsc, cdetr_split_t dkr, cdetr_split_t dkc, cdetr_stream_t s);
 /* Key/value-side backward given dsr/dsc: dK_r, dK_c (split) and dV (split). */
 int cdetr_rcda_bwd_kv(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc, const float* ar,
                       const float* ac, const float* d_o, const float* dsr, const float* dsc, cdetr_split_t dkr,

@@ -225,6 +225,12 @@ for (Bz, Lq, Hh, Ww) in [(2, 300, 32, 32), (1, 70, 9, 13), (1, 1024, 32, 32), (1
         dqr2, dqc2, dkr2, dkc2, dv2 = zs(Bz * Lq, E), zs(Bz * Lq, E), zs(Bz * Ww, E), zs(Bz * Hh, E), zs(Bz * Hh * Ww, E)
         L.call("cdetr_rcda_bwd_q_tc", Bz, Lq, Hh, Ww, E, nh, kr, kc, S(v.detach()), ar, ac, dO, dsr2, dsc2, dqr2, dqc2)
         L.call("cdetr_rcda_bwd_kv", Bz, Lq, Hh, Ww, E, nh, qr, qc, ar, ac, dO, dsr2, dsc2, dkr2, dkc2, dv2)
+        dv3 = zs(Bz * Hh * Ww, E); dkr3, dkc3 = zs(Bz * Ww, E), zs(Bz * Hh, E)
+        L.call("cdetr_rcda_bwd_v_tc", Bz, Lq, Hh, Ww, E, nh, ar, ac, S(dO), dv3)
+        L.call("cdetr_rcda_bwd_k", Bz, Lq, Hh, Ww, E, nh, qr, qc, dsr2, dsc2, dkr3, dkc3)
+        report(f"rcda_bwd_v_tc dv {tag}", L.from_split(dv3).view_as(v), v.grad, 5e-5)
+        report(f"rcda_bwd_k dkr {tag}", L.from_split(dkr3).view_as(kr), kr.grad, 5e-5)
+        report(f"rcda_bwd_k dkc {tag}", L.from_split(dkc3).view_as(kc), kc.grad, 5e-5)
         report(f"rcda_bwd_tc dqr {tag}", L.from_split(dqr2).view_as(qr), qr.grad, 5e-5)
         report(f"rcda_bwd_tc dqc {tag}", L.from_split(dqc2).view_as(qc), qc.grad, 5e-5)
         report(f"rcda_bwd_tc dsr {tag}", dsr2, dsr, 5e-5)
