@@ -70,8 +70,24 @@ class Lin:
 
     # dW[rows, :] += scale * dy[M, rows]^T @ a[M, K];  db[rows] += colsum(dy)
     def wgrad(self, dy, a, M, rows=None, bias_grad=True):
+        """Weight/bias gradients only feed the flat gradient buffer, never the dgrad chain, so they are issued on
+        the engine's side stream (forked after dy is ready, joined at the end of backward): they fill SMs the
+        critical-path kernels leave idle.  Inside a CUDA-graph capture this becomes a parallel branch."""
         if not self.trainable:
             return
+        eng = self.eng
+        if eng.side_stream is not None:
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            eng.side_stream.wait_event(ev)
+            with torch.cuda.stream(eng.side_stream):
+                self._wgrad(dy, a, M, rows, bias_grad)
+            eng.side_used = True
+        else:
+            self._wgrad(dy, a, M, rows, bias_grad)
+
+    def _wgrad(self, dy, a, M, rows, bias_grad):
         lo, hi = rows if rows else (0, self.n_out)
         n = hi - lo
         tiles = math.ceil(n / 128) * math.ceil(self.k / 128)
@@ -92,8 +108,14 @@ class Lin:
 
     def finish_grad(self):
         if self.trainable and self.taps > 1:
-            L.call("cdetr_unpack_conv_grad", self.stage, self.n_out, self.cin, self.taps,
-                   self.eng.grad_views[self.wname])
+            eng = self.eng
+            if eng.side_stream is not None:
+                with torch.cuda.stream(eng.side_stream):     # ordered after this conv's wgrad on the side stream
+                    L.call("cdetr_unpack_conv_grad", self.stage, self.n_out, self.cin, self.taps,
+                           eng.grad_views[self.wname])
+            else:
+                L.call("cdetr_unpack_conv_grad", self.stage, self.n_out, self.cin, self.taps,
+                       eng.grad_views[self.wname])
 
 
 class Engine:
@@ -140,6 +162,45 @@ class Engine:
         for l in self.lins.values():
             l.trainable = l.trainable and l.wname in self.grad_views
         self.packed = False
+        self.side_stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        self.side_used = False
+        self.aux_streams = [torch.cuda.Stream(device=device) for _ in range(2)] if device.type == "cuda" else []
+
+    def fork_join(self, fns):
+        """Run independent launch sequences concurrently: fns[0] on the current stream, the rest round-robin on the
+        auxiliary streams, all forked from 'now' and joined back (parallel branches inside a captured graph).
+        Used for the five input projections of an RCDA block (and their dgrads), each of which alone fills
+        only ~0.6 of a wave on 148 SMs."""
+        if not self.aux_streams or len(fns) < 2:
+            for fn in fns:
+                fn()
+            return
+        main = torch.cuda.current_stream()
+        ev0 = torch.cuda.Event()
+        ev0.record(main)
+        used = []
+        for i, fn in enumerate(fns):
+            if i == 0:
+                fn()
+                continue
+            st = self.aux_streams[(i - 1) % len(self.aux_streams)]
+            if st not in used:
+                st.wait_event(ev0)
+                used.append(st)
+            with torch.cuda.stream(st):
+                fn()
+        for st in used:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+
+    def join_side_stream(self):
+        """main stream waits for every weight-gradient kernel issued on the side stream."""
+        if self.side_stream is not None and self.side_used:
+            ev = torch.cuda.Event()
+            ev.record(self.side_stream)
+            torch.cuda.current_stream().wait_event(ev)
+            self.side_used = False
 
     # ------------------------------------------------------------------ infrastructure
     def buf(self, name, shape, dtype=torch.float32, zero=False):
@@ -387,13 +448,16 @@ class Engine:
         kr = self.buf(q + ".kr", (B * W, E)); kc = self.buf(q + ".kc", (B * H, E))
         v = self.buf(q + ".v", (N, E))
         lin = self.lins[lin_in]
-        lin.fwd(qr_in, M, rows=(0, E), out_f32=qr)
-        lin.fwd(qc_in, M, rows=(E, 2 * E), out_f32=qc)
-        lin.fwd(kr_in, B * W, rows=(2 * E, 3 * E), out_f32=kr)
-        lin.fwd(kc_in, B * H, rows=(3 * E, 4 * E), out_f32=kc)
         use_tc = H <= 32 and W <= 32      # tcgen05 kernel; larger feature maps use the CUDA-core kernel
         v_s = self.sbuf(q + ".v_s", N, E) if use_tc else None
-        lin.fwd(v_in, N, rows=(4 * E, 5 * E), out_f32=v, out_split=v_s)
+
+        def small():
+            lin.fwd(kr_in, B * W, rows=(2 * E, 3 * E), out_f32=kr)
+            lin.fwd(kc_in, B * H, rows=(3 * E, 4 * E), out_f32=kc)
+            lin.fwd(qc_in, M, rows=(E, 2 * E), out_f32=qc)
+
+        self.fork_join([lambda: lin.fwd(qr_in, M, rows=(0, E), out_f32=qr), small,
+                        lambda: lin.fwd(v_in, N, rows=(4 * E, 5 * E), out_f32=v, out_split=v_s)])
         ar = self.buf(q + ".ar", (B, self.nh, W, Lq)); ac = self.buf(q + ".ac", (B, self.nh, H, Lq))
         o = self.sbuf(q + ".o", M, E)
         if use_tc:
@@ -436,11 +500,14 @@ class Engine:
         g_qr = self.buf(q + ".g_qr", (M, E)); g_qc = self.buf(q + ".g_qc", (M, E))
         g_kr = self.buf(q + ".g_kr", (B * W, E)); g_kc = self.buf(q + ".g_kc", (B * H, E))
         g_v = self.buf(q + ".g_v", (N, E))
-        lin.dgrad(dqr, M, rows=(0, E), out_f32=g_qr)
-        lin.dgrad(dqc, M, rows=(E, 2 * E), out_f32=g_qc)
-        lin.dgrad(dkr, B * W, rows=(2 * E, 3 * E), out_f32=g_kr)
-        lin.dgrad(dkc, B * H, rows=(3 * E, 4 * E), out_f32=g_kc)
-        lin.dgrad(dv, N, rows=(4 * E, 5 * E), out_f32=g_v, add_f32=dv_add)
+
+        def small():
+            lin.dgrad(dkr, B * W, rows=(2 * E, 3 * E), out_f32=g_kr)
+            lin.dgrad(dkc, B * H, rows=(3 * E, 4 * E), out_f32=g_kc)
+            lin.dgrad(dqc, M, rows=(E, 2 * E), out_f32=g_qc)
+
+        self.fork_join([lambda: lin.dgrad(dqr, M, rows=(0, E), out_f32=g_qr), small,
+                        lambda: lin.dgrad(dv, N, rows=(4 * E, 5 * E), out_f32=g_v, add_f32=dv_add)])
         return g_qr, g_qc, g_kr, g_kc, g_v
 
     # ------------------------------------------------------------------ forward
@@ -761,6 +828,7 @@ class Engine:
         lin = self.lins["proj"]
         lin.wgrad(dpre, pj["proj_in"], M)
         if not any(blk["train"] for blk in self.blocks):
+            self.join_side_stream()
             return
         ex = sv["ex"]
         if cfg.stage == 2:
@@ -774,3 +842,4 @@ class Engine:
             g = self.sbuf("dfeat", M, 2048)
             lin.dgrad(dpre, M, out_split=g, mask=ex["feat"])
         self._backbone_bwd(g, B)
+        self.join_side_stream()
