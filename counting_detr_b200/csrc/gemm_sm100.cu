@@ -3,12 +3,13 @@
 //   mode 0 (TN): D[M,N] = A[M,K] * B[N,K]^T    both operands K-major   (forward / dgrad)
 //   mode 1 (NT): D[M,N] = A[K,M]^T * B[K,N]    both operands MN-major  (wgrad)
 //
-// One CTA computes one 128 x BN output tile (optionally one K-split of it):
+// Persistent CTAs (<= 2 per SM) walk a static round-robin list of 128 x BN output tiles (x K-splits):
 //   warp 0     TMA producer  : cp.async.bulk.tensor (SWIZZLE_128B) of the hi+lo planes of A and B
 //   warp 1     MMA issuer    : per 64-wide k block, 4 k-steps x 3 tcgen05.mma (hi*lo, lo*hi, hi*hi)
 //   warps 2-9  epilogue      : tcgen05.ld of the fp32 accumulator (one TMEM lane = one row per thread)
 //                              -> row-scale / bias / residual / ReLU / ReLU-mask -> fp32 and/or split-bf16
-// smem stages are recycled through full/empty mbarriers; the accumulator lives in TMEM.
+// smem stages are recycled through full/empty mbarriers across tiles; the accumulator is double buffered in
+// TMEM (tmem_full/tmem_empty barriers) so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
 //
 // Replaces the ATen GEMM call sites listed in include/cdetr.h (cdetr_gemm).
 #include "common.cuh"
@@ -45,15 +46,16 @@ struct KernelArgs {
   int M, N, K;
   int block_n;
   int stages;
-  int kb_per_split;  // k blocks (of 64) handled by one blockIdx.z
+  int kb_per_split;  // k blocks (of 64) handled by one K-split
   int num_kb;
+  int tiles_m, tiles_n, total_tiles;  // tile index = (split * tiles_m + mt) * tiles_n + nt
   uint32_t idesc;
-  uint32_t tmem_cols;
+  uint32_t tmem_cols;  // columns of ONE accumulator buffer (two are allocated)
   EpilogueArgs ep;
 };
 
 template <bool NT>
-__global__ void __launch_bounds__(NUM_THREADS, 3)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const KernelArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -64,17 +66,16 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t a_bytes = 2u * BM * 128u;               // hi+lo planes, 128 B per row/k-row
   const uint32_t b_bytes = NT ? (uint32_t)((BN + 63) / 64) * 16384u : 2u * (uint32_t)BN * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)args.stages * stage_bytes);
+  constexpr int STG_LD = 33;                             // epilogue staging: 8 warps x [32][33] floats
+  float* staging = reinterpret_cast<float*>(smem + (size_t)args.stages * stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 8 * 32 * STG_LD);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
-  const int kb_begin = blockIdx.z * args.kb_per_split;
-  const int kb_end = min(args.num_kb, kb_begin + args.kb_per_split);
   const int stages = args.stages;
 
   if (warp == 0 && lane == 0) {
@@ -86,11 +87,14 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 8);   // one elected lane of each epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_holder, args.tmem_cols);
+    tmem_alloc(tmem_holder, 2 * args.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -102,86 +106,106 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int it = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (uint32_t)(it / stages) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        uint8_t* a_s = smem + (size_t)s * stage_bytes;
-        uint8_t* b_s = a_s + a_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        if (!NT) {
-          tma_load_3d(a_s, &tmA, &full_bar[s], kb * BK, m0, 0);  // box {64, BM, 2}
-          tma_load_3d(b_s, &tmB, &full_bar[s], kb * BK, n0, 0);  // box {64, BN, 2}
-        } else {
-          for (int c = 0; c < BM / 64; ++c)                       // box {64(mn), 64(k), 2}
-            tma_load_3d(a_s + c * 16384, &tmA, &full_bar[s], m0 + 64 * c, kb * BK, 0);
-          for (int c = 0; c < (BN + 63) / 64; ++c)
-            tma_load_3d(b_s + c * 16384, &tmB, &full_bar[s], n0 + 64 * c, kb * BK, 0);
+      for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % args.tiles_n) * BN;
+        const int m0 = ((tile / args.tiles_n) % args.tiles_m) * BM;
+        const int kb_begin = (tile / (args.tiles_n * args.tiles_m)) * args.kb_per_split;
+        const int kb_end = min(args.num_kb, kb_begin + args.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (uint32_t)(it / stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* a_s = smem + (size_t)s * stage_bytes;
+          uint8_t* b_s = a_s + a_bytes;
+          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          if (!NT) {
+            tma_load_3d(a_s, &tmA, &full_bar[s], kb * BK, m0, 0);  // box {64, BM, 2}
+            tma_load_3d(b_s, &tmB, &full_bar[s], kb * BK, n0, 0);  // box {64, BN, 2}
+          } else {
+            for (int c = 0; c < BM / 64; ++c)                       // box {64(mn), 64(k), 2}
+              tma_load_3d(a_s + c * 16384, &tmA, &full_bar[s], m0 + 64 * c, kb * BK, 0);
+            for (int c = 0; c < (BN + 63) / 64; ++c)
+              tma_load_3d(b_s + c * 16384, &tmB, &full_bar[s], n0 + 64 * c, kb * BK, 0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
     if (lane == 0) {
-      int it = 0;
-      uint32_t acc = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (uint32_t)(it / stages) & 1u;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_base = a_base + a_bytes;
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          uint64_t a_hi, a_lo, b_hi, b_lo;
-          if (!NT) {
-            // K-major SW128: rows at 128 B pitch, 8-row groups 1024 B apart, k-step = +32 B.
-            a_hi = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
-            a_lo = make_smem_desc_sw128(a_base + BM * 128 + k * 32, 16, 1024);
-            b_hi = make_smem_desc_sw128(b_base + k * 32, 16, 1024);
-            b_lo = make_smem_desc_sw128(b_base + BN * 128 + k * 32, 16, 1024);
-          } else {
-            // MN-major SW128: 64-wide MN chunks 16 KB apart (LBO), 8-k groups 1024 B apart (SBO),
-            // one k-step (16) = two k groups = +2048 B; lo plane 8 KB after hi inside a chunk.
-            a_hi = make_smem_desc_sw128(a_base + k * 2048, 16384, 1024);
-            a_lo = make_smem_desc_sw128(a_base + 8192 + k * 2048, 16384, 1024);
-            b_hi = make_smem_desc_sw128(b_base + k * 2048, 16384, 1024);
-            b_lo = make_smem_desc_sw128(b_base + 8192 + k * 2048, 16384, 1024);
-          }
-          umma_bf16_ss(tmem_base, a_hi, b_lo, args.idesc, acc);
-          acc = 1;
-          umma_bf16_ss(tmem_base, a_lo, b_hi, args.idesc, 1);
-          umma_bf16_ss(tmem_base, a_hi, b_hi, args.idesc, 1);
+      int it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x, ++ti) {
+        const int kb_begin = (tile / (args.tiles_n * args.tiles_m)) * args.kb_per_split;
+        const int kb_end = min(args.num_kb, kb_begin + args.kb_per_split);
+        const int ab = ti & 1;
+        if (ti >= 2) {  // the epilogue must have drained this accumulator buffer (used by tile ti-2)
+          mbar_wait(&tmem_empty_bar[ab], (uint32_t)((ti >> 1) - 1) & 1u);
+          tc_fence_after();
         }
-        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+        const uint32_t tmem_d = tmem_base + (uint32_t)ab * args.tmem_cols;
+        uint32_t acc = 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % stages;
+          const uint32_t ph = (uint32_t)(it / stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t b_base = a_base + a_bytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            uint64_t a_hi, a_lo, b_hi, b_lo;
+            if (!NT) {
+              // K-major SW128: rows at 128 B pitch, 8-row groups 1024 B apart, k-step = +32 B.
+              a_hi = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
+              a_lo = make_smem_desc_sw128(a_base + BM * 128 + k * 32, 16, 1024);
+              b_hi = make_smem_desc_sw128(b_base + k * 32, 16, 1024);
+              b_lo = make_smem_desc_sw128(b_base + BN * 128 + k * 32, 16, 1024);
+            } else {
+              // MN-major SW128: 64-wide MN chunks 16 KB apart (LBO), 8-k groups 1024 B apart (SBO),
+              // one k-step (16) = two k groups = +2048 B; lo plane 8 KB after hi inside a chunk.
+              a_hi = make_smem_desc_sw128(a_base + k * 2048, 16384, 1024);
+              a_lo = make_smem_desc_sw128(a_base + 8192 + k * 2048, 16384, 1024);
+              b_hi = make_smem_desc_sw128(b_base + k * 2048, 16384, 1024);
+              b_lo = make_smem_desc_sw128(b_base + 8192 + k * 2048, 16384, 1024);
+            }
+            umma_bf16_ss(tmem_d, a_hi, b_lo, args.idesc, acc);
+            acc = 1;
+            umma_bf16_ss(tmem_d, a_lo, b_hi, args.idesc, 1);
+            umma_bf16_ss(tmem_d, a_hi, b_hi, args.idesc, 1);
+          }
+          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+        }
+        umma_commit(&tmem_full_bar[ab]);  // accumulator of this tile complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ------------------------------ epilogue ----------------------------------
     // Each warp owns 32 accumulator rows (its TMEM lane quarter) and half of the tile's columns.  Per
-    // 32-column chunk: TMEM -> registers (one row per thread) -> per-warp shared-memory staging (the
-    // pipeline stages are idle once the accumulator is complete) -> re-read with 4 lanes per row so that
+    // 32-column chunk: TMEM -> registers (one row per thread) -> per-warp shared-memory staging
+    // -> re-read with 4 lanes per row so that
     // every global access of the warp covers 8 rows x 128 contiguous bytes (fp32) / 64 bytes (bf16 plane).
     const EpilogueArgs& ep = args.ep;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;  // two warps share a quarter and split the tile's columns
     const int nchunks = BN / 16;
     const int c_begin = half == 0 ? 0 : ((nchunks + 1) / 2) * 16;
     const int c_end = half == 0 ? ((nchunks + 1) / 2) * 16 : BN;
-    constexpr int STG_LD = 33;
-    float* stg = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * STG_LD);
-    const int row_t = m0 + q * 32 + lane;  // row held by this thread in the TMEM phase
-    const float rs = (ep.row_scale != nullptr && row_t < args.M) ? ep.row_scale[row_t] : 1.0f;
-    const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* stg = staging + (warp - 2) * (32 * STG_LD);
     const bool vec_ok = ((ep.ld_out_f32 & 3) == 0) && ((ep.ld_out_split & 7) == 0) &&
                         ((ep.ld_add & 7) == 0) && ((ep.ld_add_f32 & 3) == 0) &&
                         ((ep.ld_mask & 7) == 0);
     const int g8 = (lane & 3) * 8;  // column group of this lane in the coalesced phase
     const int rr = lane >> 2;       // row sub-index 0..7
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x, ++ti) {
+    const int n0 = (tile % args.tiles_n) * BN;
+    const int m0 = ((tile / args.tiles_n) % args.tiles_m) * BM;
+    const int ab = ti & 1;
+    mbar_wait(&tmem_full_bar[ab], (uint32_t)(ti >> 1) & 1u);
+    tc_fence_after();
+    const int row_t = m0 + q * 32 + lane;  // row held by this thread in the TMEM phase
+    const float rs = (ep.row_scale != nullptr && row_t < args.M) ? ep.row_scale[row_t] : 1.0f;
+    const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * args.tmem_cols;
     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -299,13 +323,18 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       __syncwarp();
     }
+    // all tcgen05.ld of this warp for this accumulator buffer are complete: hand it back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty_bar[ab]);
+    }  // tile loop
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, args.tmem_cols);
+    tmem_dealloc(tmem_base, 2 * args.tmem_cols);
   }
 }
 
@@ -414,26 +443,31 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   const uint32_t a_bytes = 2u * BM * 128u;
   const uint32_t b_bytes = nt ? (uint32_t)((bn + 63) / 64) * 16384u : 2u * (uint32_t)bn * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  const uint32_t tail_bytes = (2 * MAX_STAGES + 1) * 8 + 16;
+  const uint32_t staging_bytes = 8u * 32u * 33u * 4u;
+  const uint32_t tail_bytes = staging_bytes + (2 * MAX_STAGES + 4) * 8 + 16;
   const uint32_t smem_budget = 227u * 1024u - 1024u - tail_bytes;
-  int stages = (int)(smem_budget / stage_bytes);
+  // Two accumulator buffers per CTA: tiles up to 128 wide leave TMEM (512 columns) for two CTAs per SM, and two
+  // co-resident CTAs (possibly of different kernels: the weight-gradient stream) hide each other's TMA latency;
+  // 256-wide tiles own the SM and get a deeper pipeline instead.
+  int ctas_per_sm = (2 * cols <= 256) ? 2 : 1;
+  const uint32_t per_cta = ctas_per_sm == 2 ? (113u * 1024u - tail_bytes) : smem_budget;
+  int stages = (int)(per_cta / stage_bytes);
+  if (stages < 1) { stages = 1; ctas_per_sm = 1; }
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  {
-    // One tile per CTA means a CTA's epilogue cannot overlap its own main loop, so co-resident CTAs do the
-    // overlapping: keep the CTA at <= ~113 KB so 2-3 fit per SM (TMEM: each holds <= 256 of the 512 columns).
-    // Measured (tools/gemm_sweep.py): 2 CTAs x 1 stage beats 1 CTA x 2-3 stages on every shape of the step.
-    int s2 = (int)((113u * 1024u) / stage_bytes);
-    if (s2 < 1) s2 = 1;
-    if (stages > s2) stages = s2;
-  }
-  if (stages > kb_per_split) stages = kb_per_split;
-  if (stages < 1) stages = 1;
-  if (const char* e = getenv("CDETR_GEMM_STAGES")) {  // tuning hook (tools/gemm_sweep.py)
+  if (const char* e = getenv("CDETR_GEMM_STAGES")) {  // tuning hooks (tools/gemm_sweep.py)
     const int f = atoi(e);
-    if (f >= 1 && f <= MAX_STAGES && (uint32_t)f * stage_bytes <= smem_budget) stages = f < kb_per_split ? f : kb_per_split;
+    if (f >= 1 && f <= MAX_STAGES && (uint32_t)f * stage_bytes <= smem_budget) stages = f;
   }
-  CDETR_CHECK_ARG(stages >= 1, "gemm: tile does not fit shared memory");
+  if (const char* e = getenv("CDETR_GEMM_CTAS")) {
+    const int f = atoi(e);
+    if (f == 1 || (f == 2 && 2 * cols <= 256)) ctas_per_sm = f;
+  }
+  if ((uint32_t)stages * stage_bytes + tail_bytes + 1024 > 113u * 1024u) ctas_per_sm = 1;
+  CDETR_CHECK_ARG((uint32_t)stages * stage_bytes <= smem_budget, "gemm: tile does not fit shared memory");
   ka.stages = stages;
+  ka.tiles_m = cdiv(g->M, BM);
+  ka.tiles_n = cdiv(g->N, bn);
+  ka.total_tiles = ka.tiles_m * ka.tiles_n * splits;
   const size_t smem_bytes = (size_t)stages * stage_bytes + tail_bytes + 1024;
 
   EpilogueArgs& ep = ka.ep;
@@ -461,7 +495,15 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
     return CDETR_ERR_ARG;
   }
 
-  dim3 grid(cdiv(g->N, bn), cdiv(g->M, BM), splits);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    CDETR_CHECK_CUDA(cudaGetDevice(&dev));
+    CDETR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int nctas = num_sms * ctas_per_sm;
+  if (nctas > ka.total_tiles) nctas = ka.total_tiles;
+  dim3 grid(nctas);
   auto kern = nt ? gemm_split_kernel<true> : gemm_split_kernel<false>;
   static size_t configured[2] = {0, 0};
   if (configured[nt] < smem_bytes) {
