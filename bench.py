@@ -217,7 +217,7 @@ def run_ours(args):
     graph, use_graph, g_loss = None, not args.no_graph, None
     if use_graph:
         try:
-            s = torch.cuda.Stream()
+            s = torch.cuda.Stream(priority=-1)     # critical path at high priority; wgrad side stream is low
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):
@@ -225,7 +225,7 @@ def run_ours(args):
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=s):
                 g_loss = step()
             graph.replay()
             torch.cuda.synchronize()

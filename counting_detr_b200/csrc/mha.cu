@@ -1,6 +1,6 @@
 // Decoder self-attention core (nn.MultiheadAttention over the Q object queries), forward + backward,
-// head dim 32, one query (or key) per thread with K/V (or Q/dO) tiles staged in shared memory and an
-// online softmax; the Q x Q logits never touch HBM.  Q <= ~1000 so the whole problem is a few MFLOP per
+// head dim 32, four threads per query (or key), each walking every 4th key of the K/V (or Q/dO) tiles staged
+// in shared memory with an online softmax, partials merged with warp shuffles; the Q x Q logits never touch HBM.  Q <= ~1000 so the whole problem is a few MFLOP per
 // (sample, head): latency, not throughput, is what matters here.
 // Reference: A2/models/transformer.py:366-372 (decoder self-attention), torch F.multi_head_attention_forward.
 #include "common.cuh"
@@ -68,22 +68,35 @@ __device__ __forceinline__ void store_split32(__nv_bfloat16* hi, __nv_bfloat16* 
     reinterpret_cast<uint4*>(lo)[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
   }
 }
+// K/V (or Q/dO) tiles are staged with a padded pitch so that the 4 key-split lanes of a query read 4
+// different rows without bank conflicts.
+constexpr int PITCH = HD + 4;
+constexpr int QPB = 32;    // queries (or keys) per CTA
+constexpr int SPLIT = 4;   // threads per query: each walks every 4th key; partials merged with shuffles
+
 __device__ __forceinline__ void stage_rows(const float* src, int64_t ld, int64_t row0, int nrows, int col0,
                                            float* dst) {
   for (int i = threadIdx.x; i < TK * 8; i += blockDim.x) {
     const int r = i >> 3, c4 = i & 7;
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < nrows) t = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * ld + col0 + c4 * 4));
-    reinterpret_cast<float4*>(dst)[i] = t;
+    *reinterpret_cast<float4*>(dst + r * PITCH + c4 * 4) = t;
   }
 }
+__device__ __forceinline__ void shfl_add32(float* v) {
+#pragma unroll
+  for (int o = 1; o < SPLIT; o <<= 1)
+#pragma unroll
+    for (int c = 0; c < HD; ++c) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+}
 
-// grid (ceil(L/TK), nh, B), block TK
-__global__ void mha_fwd_kernel(const MhaArgs a) {
-  __shared__ __align__(16) float Ks[TK * HD];
-  __shared__ __align__(16) float Vs[TK * HD];
+// grid (ceil(L/QPB), nh, B), block QPB*SPLIT: thread = (query tid/4, key split tid%4)
+__global__ void __launch_bounds__(QPB * SPLIT) mha_fwd_kernel(const MhaArgs a) {
+  __shared__ __align__(16) float Ks[TK * PITCH];
+  __shared__ __align__(16) float Vs[TK * PITCH];
   const int head = blockIdx.y, b = blockIdx.z;
-  const int i = blockIdx.x * TK + threadIdx.x;
+  const int i = blockIdx.x * QPB + (threadIdx.x >> 2);
+  const int ks = threadIdx.x & 3;
   const bool ok = i < a.L;
   const float scale = rsqrtf((float)HD);
   float q[HD], acc[HD];
@@ -101,19 +114,34 @@ __global__ void mha_fwd_kernel(const MhaArgs a) {
     stage_rows(a.k, a.ldq, (int64_t)b * a.L + j0, nk, head * HD, Ks);
     stage_rows(a.v, a.ldq, (int64_t)b * a.L + j0, nk, head * HD, Vs);
     __syncthreads();
-    for (int j = 0; j < nk; ++j) {
-      const float s = dot32(q, Ks + j * HD);
-      const float mn = fmaxf(m, s);
+    for (int j = ks; j < nk; j += 2 * SPLIT) {   // two keys per iteration: independent dot products
+      const int j2 = j + SPLIT;
+      const float s0 = dot32(q, Ks + j * PITCH);
+      const float s1 = j2 < nk ? dot32(q, Ks + j2 * PITCH) : -INFINITY;
+      const float mn = fmaxf(m, fmaxf(s0, s1));
       const float corr = expf(m - mn);
-      const float p = expf(s - mn);
-      l = l * corr + p;
+      const float p0 = expf(s0 - mn), p1 = expf(s1 - mn);
+      l = l * corr + p0 + p1;
 #pragma unroll
       for (int c = 0; c < HD; ++c) acc[c] *= corr;
-      axpy32(acc, p, Vs + j * HD);
+      axpy32(acc, p0, Vs + j * PITCH);
+      if (j2 < nk) axpy32(acc, p1, Vs + j2 * PITCH);
       m = mn;
     }
   }
-  if (ok) {
+  // merge the 4 key-split partials of each query (adjacent lanes)
+#pragma unroll
+  for (int o = 1; o < SPLIT; o <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+    const float l2 = __shfl_xor_sync(0xffffffffu, l, o);
+    const float mn = fmaxf(m, m2);
+    const float c1 = mn == -INFINITY ? 0.0f : expf(m - mn), c2 = mn == -INFINITY ? 0.0f : expf(m2 - mn);
+    l = l * c1 + l2 * c2;
+#pragma unroll
+    for (int c = 0; c < HD; ++c) acc[c] = acc[c] * c1 + __shfl_xor_sync(0xffffffffu, acc[c], o) * c2;
+    m = mn;
+  }
+  if (ok && ks == 0) {
     const float inv = 1.0f / l;
 #pragma unroll
     for (int c = 0; c < HD; ++c) acc[c] *= inv;
@@ -124,11 +152,12 @@ __global__ void mha_fwd_kernel(const MhaArgs a) {
 }
 
 // backward, per query: D_i, dq_i.   O is re-read from its split copy.
-__global__ void mha_bwd_q_kernel(const MhaArgs a) {
-  __shared__ __align__(16) float Ks[TK * HD];
-  __shared__ __align__(16) float Vs[TK * HD];
+__global__ void __launch_bounds__(QPB * SPLIT) mha_bwd_q_kernel(const MhaArgs a) {
+  __shared__ __align__(16) float Ks[TK * PITCH];
+  __shared__ __align__(16) float Vs[TK * PITCH];
   const int head = blockIdx.y, b = blockIdx.z;
-  const int i = blockIdx.x * TK + threadIdx.x;
+  const int i = blockIdx.x * QPB + (threadIdx.x >> 2);
+  const int ks = threadIdx.x & 3;
   const bool ok = i < a.L;
   const float scale = rsqrtf((float)HD);
   float q[HD], dov[HD], dq[HD];
@@ -144,7 +173,7 @@ __global__ void mha_bwd_q_kernel(const MhaArgs a) {
 #pragma unroll
     for (int c = 0; c < HD; ++c) D += dov[c] * join_bf16(a.o_hi[off + c], a.o_lo[off + c]);
     lse = a.lse[((int64_t)b * a.nh + head) * a.L + i];
-    a.dsum[((int64_t)b * a.nh + head) * a.L + i] = D;
+    if (ks == 0) a.dsum[((int64_t)b * a.nh + head) * a.L + i] = D;
   }
   for (int j0 = 0; j0 < a.L; j0 += TK) {
     const int nk = min(TK, a.L - j0);
@@ -152,13 +181,16 @@ __global__ void mha_bwd_q_kernel(const MhaArgs a) {
     stage_rows(a.k, a.ldq, (int64_t)b * a.L + j0, nk, head * HD, Ks);
     stage_rows(a.v, a.ldq, (int64_t)b * a.L + j0, nk, head * HD, Vs);
     __syncthreads();
-    for (int j = 0; j < nk; ++j) {
-      const float p = expf(dot32(q, Ks + j * HD) - lse);
-      const float ds = p * (dot32(dov, Vs + j * HD) - D);
-      axpy32(dq, ds, Ks + j * HD);
+    if (ok) {
+      for (int j = ks; j < nk; j += SPLIT) {
+        const float p = expf(dot32(q, Ks + j * PITCH) - lse);
+        const float ds = p * (dot32(dov, Vs + j * PITCH) - D);
+        axpy32(dq, ds, Ks + j * PITCH);
+      }
     }
   }
-  if (ok) {
+  shfl_add32(dq);
+  if (ok && ks == 0) {
 #pragma unroll
     for (int c = 0; c < HD; ++c) dq[c] *= scale;
     const int64_t off = ((int64_t)b * a.L + i) * a.ld_g + head * HD;
@@ -166,13 +198,14 @@ __global__ void mha_bwd_q_kernel(const MhaArgs a) {
   }
 }
 
-// backward, per key: dk_j, dv_j (queries staged in tiles)
-__global__ void mha_bwd_kv_kernel(const MhaArgs a) {
-  __shared__ __align__(16) float Qs[TK * HD];
-  __shared__ __align__(16) float Ds[TK * HD];   // dO tile
+// backward, per key: dk_j, dv_j (queries staged in tiles; the 4 lanes of a key walk every 4th query)
+__global__ void __launch_bounds__(QPB * SPLIT) mha_bwd_kv_kernel(const MhaArgs a) {
+  __shared__ __align__(16) float Qs[TK * PITCH];
+  __shared__ __align__(16) float Ds[TK * PITCH];   // dO tile
   __shared__ float lses[TK], dsums[TK];
   const int head = blockIdx.y, b = blockIdx.z;
-  const int j = blockIdx.x * TK + threadIdx.x;
+  const int j = blockIdx.x * QPB + (threadIdx.x >> 2);
+  const int qs = threadIdx.x & 3;
   const bool ok = j < a.L;
   const float scale = rsqrtf((float)HD);
   float kk[HD], vv[HD], dk[HD], dv[HD];
@@ -195,14 +228,18 @@ __global__ void mha_bwd_kv_kernel(const MhaArgs a) {
       dsums[threadIdx.x] = a.dsum[bh * a.L + i0 + threadIdx.x];
     }
     __syncthreads();
-    for (int i = 0; i < nq; ++i) {
-      const float p = expf(dot32(kk, Qs + i * HD) - lses[i]);
-      axpy32(dv, p, Ds + i * HD);
-      const float ds = p * (dot32(vv, Ds + i * HD) - dsums[i]);
-      axpy32(dk, ds * scale, Qs + i * HD);
+    if (ok) {
+      for (int i = qs; i < nq; i += SPLIT) {
+        const float p = expf(dot32(kk, Qs + i * PITCH) - lses[i]);
+        axpy32(dv, p, Ds + i * PITCH);
+        const float ds = p * (dot32(vv, Ds + i * PITCH) - dsums[i]);
+        axpy32(dk, ds * scale, Qs + i * PITCH);
+      }
     }
   }
-  if (ok) {
+  shfl_add32(dk);
+  shfl_add32(dv);
+  if (ok && qs == 0) {
     const int64_t off = ((int64_t)b * a.L + j) * a.ld_g + head * HD;
     store_split32(a.dk_hi + off, a.dk_lo + off, dk);
     store_split32(a.dv_hi + off, a.dv_lo + off, dv);
@@ -218,7 +255,7 @@ extern "C" int cdetr_mha_fwd(int B, int L, int E, int nh, const float* q, const 
   a.B = B; a.L = L; a.E = E; a.nh = nh; a.q = q; a.k = k; a.v = v; a.ldq = ldq;
   a.o_hi = reinterpret_cast<__nv_bfloat16*>(o.base); a.o_lo = a.o_hi + o.plane; a.ld_o = o.ld;
   a.lse = lse;
-  mha_fwd_kernel<<<dim3(cdiv(L, TK), nh, B), TK, 0, reinterpret_cast<cudaStream_t>(s)>>>(a);
+  mha_fwd_kernel<<<dim3(cdiv(L, QPB), nh, B), QPB * SPLIT, 0, reinterpret_cast<cudaStream_t>(s)>>>(a);
   CDETR_CHECK_LAUNCH();
   return 0;
 }
@@ -239,9 +276,9 @@ extern "C" int cdetr_mha_bwd(int B, int L, int E, int nh, const float* q, const 
   a.dk_hi = hi(dk); a.dk_lo = hi(dk) + dk.plane;
   a.dv_hi = hi(dv); a.dv_lo = hi(dv) + dv.plane;
   a.ld_g = dq.ld;
-  mha_bwd_q_kernel<<<dim3(cdiv(L, TK), nh, B), TK, 0, s>>>(a);
+  mha_bwd_q_kernel<<<dim3(cdiv(L, QPB), nh, B), QPB * SPLIT, 0, s>>>(a);
   CDETR_CHECK_LAUNCH();
-  mha_bwd_kv_kernel<<<dim3(cdiv(L, TK), nh, B), TK, 0, s>>>(a);
+  mha_bwd_kv_kernel<<<dim3(cdiv(L, QPB), nh, B), QPB * SPLIT, 0, s>>>(a);
   CDETR_CHECK_LAUNCH();
   return 0;
 }

@@ -96,9 +96,9 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
     tma_prefetch_desc(&tmV);
     mbar_init(v_full, 1);
     for (int g = 0; g < 2; ++g) {
-      mbar_init(&a_ready[g], 128);
+      mbar_init(&a_ready[g], 4);      // one elected lane per warp of the group
       mbar_init(&t_full[g], 1);
-      mbar_init(&t_empty[g], 128);
+      mbar_init(&t_empty[g], 4);
     }
     fence_barrier_init();
   }
@@ -201,7 +201,8 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
           *reinterpret_cast<uint4*>(Ag + A_PLANE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
         fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core (async proxy)
-        mbar_arrive(&a_ready[g]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[g]);
         if (ok) {
           const float4* qp = reinterpret_cast<const float4*>(a.qc + ((int64_t)b * a.L + q) * a.E + head * HD);
 #pragma unroll
@@ -237,7 +238,8 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
             for (int c = 0; c < HD; ++c) acc[c] += coef * __uint_as_float(t[c]);
           }
           tc_fence_before();
-          mbar_arrive(&t_empty[g]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[g]);
         }
       }
       if (ok) {
@@ -309,9 +311,9 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
     tma_prefetch_desc(&tmV);
     mbar_init(v_full, 1);
     for (int g = 0; g < 2; ++g) {
-      mbar_init(&a_ready[g], 128);
+      mbar_init(&a_ready[g], 4);      // one elected lane per warp of the group
       mbar_init(&t_full[g], 1);
-      mbar_init(&t_empty[g], 128);
+      mbar_init(&t_empty[g], 4);
     }
     fence_barrier_init();
   }
@@ -401,7 +403,8 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
           *reinterpret_cast<uint4*>(Ag + A_PLANE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
         fence_proxy_async();
-        mbar_arrive(&a_ready[g]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[g]);
       }
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
@@ -434,7 +437,8 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
             dacg[(p * 8 + hi) * TQ + r] = s0 + s1;
           }
           tc_fence_before();
-          mbar_arrive(&t_empty[g]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[g]);
         }
       }
     }
@@ -538,7 +542,7 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
 constexpr int VK = 64;                                   // queries per k block
 constexpr uint32_t P_TILE_BYTES = 128 * VK * 2;          // one plane of the P tile: 16 KB
 constexpr uint32_t DO_PLANE_BYTES = VK * HD * 2;         // 4 KB
-constexpr int MAP_LD = 68;                               // padded pitch of the staged attention maps
+constexpr int MAP_LD = 72;                               // map row = two 32-query halves at +0 / +36: conflict-free float4 reads
 
 struct TcBwdVArgs {
   int B, L, H, W, E, nh;
@@ -574,7 +578,7 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
     for (int i = 0; i < 2; ++i) {
       mbar_init(&d_full[i], 1);
       mbar_init(&d_empty[i], 1);
-      mbar_init(&p_full[i], 256);
+      mbar_init(&p_full[i], 8);        // one elected lane per compute warp
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(acc_full, 1);
@@ -640,8 +644,9 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
       for (int i = ct; i < 32 * VK; i += 256) {
         const int k = i / VK, qq = i % VK;
         const bool qok = q0 + qq < a.L;
-        ars[k * MAP_LD + qq] = (qok && k < a.W) ? __ldg(a.ar + (bh * a.W + k) * a.L + q0 + qq) : 0.0f;
-        acs[k * MAP_LD + qq] = (qok && k < a.H) ? __ldg(a.ac + (bh * a.H + k) * a.L + q0 + qq) : 0.0f;
+        const int mo = k * MAP_LD + (qq >> 5) * 36 + (qq & 31);
+        ars[mo] = (qok && k < a.W) ? __ldg(a.ar + (bh * a.W + k) * a.L + q0 + qq) : 0.0f;
+        acs[mo] = (qok && k < a.H) ? __ldg(a.ac + (bh * a.H + k) * a.L + q0 + qq) : 0.0f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int mt = 0; mt < ntile; ++mt, ++u) {
@@ -650,8 +655,8 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
         const int m = mt * 128 + ml;
         const bool mok = m < HW;
         const int h = mok ? m / a.W : 0, w = mok ? m % a.W : 0;
-        const float4* cr = reinterpret_cast<const float4*>(acs + h * MAP_LD + qh * 32);
-        const float4* rr = reinterpret_cast<const float4*>(ars + w * MAP_LD + qh * 32);
+        const float4* cr = reinterpret_cast<const float4*>(acs + h * MAP_LD + qh * 36);
+        const float4* rr = reinterpret_cast<const float4*>(ars + w * MAP_LD + qh * 36);
         uint8_t* Pb = Ps + (size_t)pb * 2 * P_TILE_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {        // 4 chunks of 8 queries
@@ -673,7 +678,8 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
           *reinterpret_cast<uint4*>(Pb + P_TILE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
         fence_proxy_async();
-        mbar_arrive(&p_full[pb]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[pb]);
       }
     }
     // ---- epilogue: accumulators -> dV (split)

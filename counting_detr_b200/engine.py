@@ -162,9 +162,14 @@ class Engine:
         for l in self.lins.values():
             l.trainable = l.trainable and l.wname in self.grad_views
         self.packed = False
-        self.side_stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        # weight-gradient work runs at the LOWEST stream priority: its CTAs only take SM slots the critical path
+        # (forward / dgrad chain, ideally issued from a high-priority stream) leaves free
+        self.side_stream = torch.cuda.Stream(device=device, priority=0) if device.type == "cuda" else None
         self.side_used = False
-        self.aux_streams = [torch.cuda.Stream(device=device) for _ in range(2)] if device.type == "cuda" else []
+        import os
+        if os.environ.get("CDETR_NO_SIDE"):      # debugging / A-B measurements
+            self.side_stream = None
+        self.aux_streams = [torch.cuda.Stream(device=device, priority=-1) for _ in range(2)] if device.type == "cuda" else []
 
     def fork_join(self, fns):
         """Run independent launch sequences concurrently: fns[0] on the current stream, the rest round-robin on the

@@ -1,4 +1,4 @@
-for cfg in "" "CDETR_GEMM_CTAS=1 CDETR_GEMM_STAGES=3" "CDETR_GEMM_CTAS=1 CDETR_GEMM_STAGES=2" "CDETR_GEMM_CTAS=1 CDETR_GEMM_STAGES=1"; do
+for cfg in "X=1" "CDETR_NO_SIDE=1" ; do
   echo "== $cfg"
   env $cfg timeout 200 python bench.py --steps 10 --warmup 3 --skip-cpu 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['gemm_ms_per_step'])"
 done
