@@ -64,6 +64,8 @@ class GemmT(C.Structure):
         ("relu", C.c_int32), ("accumulate", C.c_int32),
         ("out_f32", C.c_void_p), ("ld_out_f32", C.c_int64),
         ("out_split", SplitT),
+        ("conv_taps", C.c_int32), ("conv_H", C.c_int32), ("conv_W", C.c_int32), ("conv_C", C.c_int32),
+        ("conv_dil", C.c_int32), ("conv_sign", C.c_int32),
     ]
 
 
@@ -78,9 +80,13 @@ GEMM_TRACE = None
 
 
 def gemm(a, b, M, N, K, mode=0, out_f32=None, out_split=None, bias=None, row_scale=None,
-         add_split=None, add_f32=None, mask=None, relu=False, accumulate=False, block_n=0, split_k=1):
-    """cdetr_gemm: see include/cdetr.h. a, b, add_split, mask, out_split are split tensors [2, rows, ld]."""
+         add_split=None, add_f32=None, mask=None, relu=False, accumulate=False, block_n=0, split_k=1, conv=None):
+    """cdetr_gemm: see include/cdetr.h. a, b, add_split, mask, out_split are split tensors [2, rows, ld].
+    conv = (H, W, C, dil, sign) turns the conv operand (a in mode 0, b in mode 1) into an implicit 3x3 im2col."""
     g = GemmT()
+    if conv is not None:
+        g.conv_taps = 9
+        g.conv_H, g.conv_W, g.conv_C, g.conv_dil, g.conv_sign = conv
     g.mode, g.M, g.N, g.K = mode, M, N, K
     g.a, g.b = split_view(a), split_view(b)
     g.block_n, g.split_k = block_n, split_k
@@ -122,6 +128,7 @@ def from_split(s):
 _SIGS = {
     "cdetr_bn_fold": "ppppfipp",
     "cdetr_pack_weight": "piiipSS",
+    "cdetr_pack_weight_dgrad": "piiipS",
     "cdetr_unpack_conv_grad": "piiip",
     "cdetr_to_split": "plilS",
     "cdetr_from_split": "Slipl",

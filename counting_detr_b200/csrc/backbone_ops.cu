@@ -89,6 +89,25 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
   }
 }
 
+// dst[cin, taps*cout]: element (c, t*cout + o) = w[o, c, t] * row_scale[o]   (implicit-conv dgrad weights)
+__global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, int cout, int cin, int taps,
+                                         const float* __restrict__ row_scale, SplitPtr dst) {
+  const int64_t n = (int64_t)cout * cin * taps;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const int c = (int)((i / taps) % cin);
+    const int o = (int)(i / ((int64_t)taps * cin));
+    float x = w[i];
+    if (row_scale) x *= row_scale[o];
+    __nv_bfloat16 h, l;
+    split_bf16(x, h, l);
+    const int64_t k = (int64_t)t * cout + o;
+    dst.hi[(int64_t)c * dst.ld + k] = h;
+    dst.lo[(int64_t)c * dst.ld + k] = l;
+  }
+}
+
 // grad[cout, cin, taps] += g[cout, taps*cin]
 __global__ void unpack_conv_grad_kernel(const float* __restrict__ g, int cout, int cin, int taps,
                                         float* __restrict__ grad) {
@@ -320,6 +339,16 @@ extern "C" int cdetr_pack_weight(const float* w, int cout, int cin, int taps, co
   CDETR_CHECK_ARG(dst.base || dst_t.base, "pack_weight: no destination");
   pack_weight_kernel<<<grid_for((int64_t)cout * cin * taps), 256, 0, STREAM(s)>>>(
       w, cout, cin, taps, row_scale, sp(dst), sp(dst_t));
+  CDETR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cdetr_pack_weight_dgrad(const float* w, int cout, int cin, int taps, const float* row_scale,
+                                       cdetr_split_t dst, cdetr_stream_t s) {
+  CDETR_CHECK_ARG(w && cout > 0 && cin > 0 && taps > 0 && dst.base, "pack_weight_dgrad: bad args");
+  CDETR_CHECK_ARG(dst.ld >= (int64_t)taps * cout, "pack_weight_dgrad: dst ld too small");
+  pack_weight_dgrad_kernel<<<grid_for((int64_t)cout * cin * taps), 256, 0, STREAM(s)>>>(
+      w, cout, cin, taps, row_scale, sp(dst));
   CDETR_CHECK_LAUNCH();
   return 0;
 }

@@ -51,6 +51,9 @@ struct KernelArgs {
   int tiles_m, tiles_n, total_tiles;  // tile index = (split * tiles_m + mt) * tiles_n + nt
   uint32_t idesc;
   uint32_t tmem_cols;  // columns of ONE accumulator buffer (two are allocated)
+  // implicit 3x3 convolution (conv != 0): the conv operand (A in mode 0, B in mode 1) is an NHWC activation read
+  // through a 5-D map {C, W, H, B, plane} with per-tap shifted windows; TMA zero-fills the out-of-image part
+  int conv, cH, cW, cC, cdil, csign;
   EpilogueArgs ep;
 };
 
@@ -111,6 +114,12 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int m0 = ((tile / args.tiles_n) % args.tiles_m) * BM;
         const int kb_begin = (tile / (args.tiles_n * args.tiles_m)) * args.kb_per_split;
         const int kb_end = min(args.num_kb, kb_begin + args.kb_per_split);
+        const int hw = args.cH * args.cW;
+        int cb = 0, ch0 = 0;             // mode 0 conv: image and first pixel row of this 128-pixel tile
+        if (!NT && args.conv) {
+          cb = m0 / hw;
+          ch0 = (m0 - cb * hw) / args.cW;
+        }
         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t ph = (uint32_t)(it / stages) & 1u;
@@ -119,8 +128,28 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint8_t* b_s = a_s + a_bytes;
           mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
           if (!NT) {
-            tma_load_3d(a_s, &tmA, &full_bar[s], kb * BK, m0, 0);  // box {64, BM, 2}
+            if (args.conv) {   // box {64 c, W, 128/W, 1, 2}: rows of the tile = pixels (h, w) of image cb, shifted by the tap
+              const int k0 = kb * BK;
+              const int tap = k0 / args.cC;
+              const int dh = (tap / 3 - 1) * args.cdil * args.csign, dw = (tap % 3 - 1) * args.cdil * args.csign;
+              tma_load_5d(a_s, &tmA, &full_bar[s], k0 - tap * args.cC, dw, ch0 + dh, cb, 0);
+            } else {
+              tma_load_3d(a_s, &tmA, &full_bar[s], kb * BK, m0, 0);  // box {64, BM, 2}
+            }
             tma_load_3d(b_s, &tmB, &full_bar[s], kb * BK, n0, 0);  // box {64, BN, 2}
+          } else if (args.conv) {
+            for (int c = 0; c < BM / 64; ++c)                       // box {64(mn), 64(k), 2}
+              tma_load_3d(a_s + c * 16384, &tmA, &full_bar[s], m0 + 64 * c, kb * BK, 0);
+            // k block = 64 consecutive pixels of one image: box {64 c, min(W,64), 64/min(W,64), 1, 2}
+            const int p0 = kb * BK;
+            const int pb = p0 / hw, rem = p0 - pb * hw;
+            const int ph0 = rem / args.cW, pw0 = rem - ph0 * args.cW;
+            for (int c = 0; c < (BN + 63) / 64; ++c) {
+              const int nn = n0 + 64 * c;
+              const int tap = nn / args.cC;
+              const int dh = (tap / 3 - 1) * args.cdil, dw = (tap % 3 - 1) * args.cdil;
+              tma_load_5d(b_s + c * 16384, &tmB, &full_bar[s], nn - tap * args.cC, pw0 + dw, ph0 + dh, pb, 0);
+            }
           } else {
             for (int c = 0; c < BM / 64; ++c)                       // box {64(mn), 64(k), 2}
               tma_load_3d(a_s + c * 16384, &tmA, &full_bar[s], m0 + 64 * c, kb * BK, 0);
@@ -385,6 +414,33 @@ int make_split_map(CUtensorMap* map, const cdetr_split_t& t, int64_t inner, int6
   return CDETR_OK;
 }
 
+// 5-D map over an NHWC split activation [B*H*W, C]: dims {C, W, H, B, plane}; box {64, box_w, box_h, 1, 2}.
+int make_conv_map(CUtensorMap* map, const cdetr_split_t& t, int C, int W, int H, int B, int box_w, int box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    cdetr_set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return CDETR_ERR_CUDA;
+  }
+  CDETR_CHECK_ARG(t.base != nullptr, "gemm: null conv operand");
+  CDETR_CHECK_ARG((reinterpret_cast<uintptr_t>(t.base) & 15) == 0, "gemm: conv operand not 16B aligned");
+  CDETR_CHECK_ARG(t.ld % 8 == 0 && t.plane % 8 == 0 && t.ld >= C && t.plane > 0,
+                  "gemm: conv operand ld/plane must be multiples of 8 elements");
+  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 2};
+  cuuint64_t gstride[4] = {(cuuint64_t)t.ld * 2, (cuuint64_t)W * t.ld * 2, (cuuint64_t)H * W * t.ld * 2,
+                           (cuuint64_t)t.plane * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 2};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, t.base, gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    cdetr_set_error("cuTensorMapEncodeTiled (conv) failed (%d) C=%d W=%d H=%d B=%d ld=%lld box=%dx%d", (int)r, C, W,
+                    H, B, (long long)t.ld, box_w, box_h);
+    return CDETR_ERR_CUDA;
+  }
+  return CDETR_OK;
+}
+
 }  // namespace
 
 extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
@@ -421,14 +477,44 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
                     "gemm: split_k only supports (row_scale, atomic out_f32) epilogues");
   if (g->accumulate) CDETR_CHECK_ARG(g->out_f32 != nullptr, "gemm: accumulate needs out_f32");
 
+  const bool conv = g->conv_taps != 0;
+  int conv_B = 0;
+  if (conv) {
+    const int H = g->conv_H, W = g->conv_W, C = g->conv_C;
+    CDETR_CHECK_ARG(g->conv_taps == 9 && H > 0 && W > 0 && C > 0 && C % 64 == 0 && g->conv_dil >= 1,
+                    "gemm: implicit conv needs 9 taps and C %% 64 == 0 (C=%d)", C);
+    CDETR_CHECK_ARG(g->conv_sign == 1 || g->conv_sign == -1, "gemm: conv_sign must be +1 or -1");
+    const int64_t pixels = nt ? g->K : g->M;
+    CDETR_CHECK_ARG(pixels % ((int64_t)H * W) == 0, "gemm: conv pixel count %lld is not a multiple of H*W",
+                    (long long)pixels);
+    conv_B = (int)(pixels / ((int64_t)H * W));
+    if (!nt) {
+      CDETR_CHECK_ARG(g->K == 9 * C, "gemm: conv mode 0 needs K == 9*C");
+      CDETR_CHECK_ARG(W <= BM && BM % W == 0 && (H * W) % BM == 0,
+                      "gemm: implicit conv needs W | 128 and 128 | H*W (H=%d W=%d)", H, W);
+    } else {
+      CDETR_CHECK_ARG(g->N == 9 * C && g->conv_sign == 1, "gemm: conv mode 1 needs N == 9*C, conv_sign == 1");
+      const int bw = W < 64 ? W : 64;
+      CDETR_CHECK_ARG(64 % bw == 0 && W % bw == 0 && (H * W) % 64 == 0,
+                      "gemm: implicit conv wgrad needs W | 64 or 64 | W (H=%d W=%d)", H, W);
+      CDETR_CHECK_ARG((9 * C) % bn == 0 && C % (bn < 64 ? bn : 64) == 0, "gemm: conv mode 1 needs block_n | 9*C");
+    }
+  }
+
   CUtensorMap tmA, tmB;
   int rc;
   if (!nt) {
-    if ((rc = make_split_map(&tmA, g->a, g->K, g->M, BK, BM)) != 0) return rc;
+    if (conv) {
+      if ((rc = make_conv_map(&tmA, g->a, g->conv_C, g->conv_W, g->conv_H, conv_B, g->conv_W, BM / g->conv_W)) != 0)
+        return rc;
+    } else if ((rc = make_split_map(&tmA, g->a, g->K, g->M, BK, BM)) != 0) return rc;
     if ((rc = make_split_map(&tmB, g->b, g->K, g->N, BK, bn)) != 0) return rc;
   } else {
     if ((rc = make_split_map(&tmA, g->a, g->M, g->K, 64, BK)) != 0) return rc;
-    if ((rc = make_split_map(&tmB, g->b, g->N, g->K, 64, BK)) != 0) return rc;
+    if (conv) {
+      const int bw = g->conv_W < 64 ? g->conv_W : 64;
+      if ((rc = make_conv_map(&tmB, g->b, g->conv_C, g->conv_W, g->conv_H, conv_B, bw, 64 / bw)) != 0) return rc;
+    } else if ((rc = make_split_map(&tmB, g->b, g->N, g->K, 64, BK)) != 0) return rc;
   }
 
   KernelArgs ka;
@@ -436,6 +522,9 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   ka.block_n = bn;
   ka.kb_per_split = kb_per_split;
   ka.num_kb = num_kb;
+  ka.conv = conv ? 1 : 0;
+  ka.cH = conv ? g->conv_H : 1; ka.cW = conv ? g->conv_W : 1; ka.cC = conv ? g->conv_C : 1;
+  ka.cdil = g->conv_dil; ka.csign = g->conv_sign;
   ka.idesc = make_idesc_bf16_f32(BM, bn, nt ? 1 : 0, nt ? 1 : 0);
   uint32_t cols = 32;
   while ((int)cols < bn) cols <<= 1;

@@ -40,6 +40,9 @@ class Lin:
         dev = w.device
         self.w = torch.zeros(2, self.n_out, _r8(self.k), device=dev, dtype=torch.bfloat16)
         self.wt = torch.zeros(2, self.k, _r8(self.n_out), device=dev, dtype=torch.bfloat16) if self.need_t else None
+        # 3x3 convs lowered as implicit GEMMs (Engine._plan_backbone) use [cin, taps*cout] weights for dgrad instead
+        self.implicit = False
+        self.wd = None
         self.scale = torch.empty(self.n_out, device=dev) if bn else None
         self.shift = torch.empty(self.n_out, device=dev) if bn else None
         self.bias = None
@@ -55,7 +58,13 @@ class Lin:
             b = p[self.bname]
             # stage-1 cls bias has shape [1] and broadcasts over the two logits (A1/models/transformer.py:84-88)
             self.bias = b if b.numel() == self.n_out else b.expand(self.n_out).contiguous()
-        L.call("cdetr_pack_weight", p[self.wname], self.n_out, self.cin, self.taps, self.scale, self.w, self.wt)
+        if self.implicit and self.need_t:
+            if self.wd is None:
+                self.wd = torch.zeros(2, self.cin, _r8(self.taps * self.n_out), device=self.w.device, dtype=torch.bfloat16)
+            L.call("cdetr_pack_weight", p[self.wname], self.n_out, self.cin, self.taps, self.scale, self.w, None)
+            L.call("cdetr_pack_weight_dgrad", p[self.wname], self.n_out, self.cin, self.taps, self.scale, self.wd)
+        else:
+            L.call("cdetr_pack_weight", p[self.wname], self.n_out, self.cin, self.taps, self.scale, self.w, self.wt)
 
     # y[M, rows] = a[M, K] @ W[rows, :]^T + bias[rows]
     def fwd(self, a, M, rows=None, **kw):
@@ -68,8 +77,12 @@ class Lin:
         lo, hi = rows if rows else (0, self.n_out)
         L.gemm(dy, self.wt[:, :, lo:hi], M, self.k, hi - lo, mode=0, **kw)
 
+    # implicit 3x3 conv dgrad: dx[M, cin] = sum_tap dy[pixel - off(tap), :] @ W[:, :, tap]   (dy: [M, n_out])
+    def dgrad_conv(self, dy, M, H, W, dil, **kw):
+        L.gemm(dy, self.wd, M, self.cin, self.taps * self.n_out, mode=0, conv=(H, W, self.n_out, dil, -1), **kw)
+
     # dW[rows, :] += scale * dy[M, rows]^T @ a[M, K];  db[rows] += colsum(dy)
-    def wgrad(self, dy, a, M, rows=None, bias_grad=True):
+    def wgrad(self, dy, a, M, rows=None, bias_grad=True, conv=None):
         """Weight/bias gradients only feed the flat gradient buffer, never the dgrad chain, so they are issued on
         the engine's side stream (forked after dy is ready, joined at the end of backward): they fill SMs the
         critical-path kernels leave idle.  Inside a CUDA-graph capture this becomes a parallel branch."""
@@ -82,12 +95,12 @@ class Lin:
             ev.record(main)
             eng.side_stream.wait_event(ev)
             with torch.cuda.stream(eng.side_stream):
-                self._wgrad(dy, a, M, rows, bias_grad)
+                self._wgrad(dy, a, M, rows, bias_grad, conv)
             eng.side_used = True
         else:
-            self._wgrad(dy, a, M, rows, bias_grad)
+            self._wgrad(dy, a, M, rows, bias_grad, conv)
 
-    def _wgrad(self, dy, a, M, rows, bias_grad):
+    def _wgrad(self, dy, a, M, rows, bias_grad, conv=None):
         lo, hi = rows if rows else (0, self.n_out)
         n = hi - lo
         tiles = math.ceil(n / 128) * math.ceil(self.k / 128)
@@ -99,7 +112,7 @@ class Lin:
             out = self.stage[lo:hi]
         L.gemm(dy, a, n, self.k, M, mode=1, out_f32=out, accumulate=True, split_k=split_k,
                row_scale=self.scale[lo:hi] if self.scale is not None else None,
-               block_n=128 if self.k > 64 else 64)
+               block_n=128 if (self.k > 64 and (conv is None or self.cin % 128 == 0)) else 64, conv=conv)
         if bias_grad and self.bname and self.bname in self.eng.grad_views:
             g = self.eng.grad_views[self.bname]
             if g.numel() != self.n_out:
@@ -284,6 +297,21 @@ class Engine:
         self.grad_flat.zero_()
 
     # ------------------------------------------------------------------ backbone
+    def _plan_backbone(self, S1, S2):
+        """Choose the lowering of every 3x3 conv for this input size: implicit GEMM (TMA reads shifted windows of the
+        NHWC activation, no im2col matrix) when the conv has stride 1 and 128-pixel tiles are whole image rows,
+        else explicit im2col.  Re-packs the weights if a choice changed."""
+        H, W = ((S1 + 6 - 7) // 2 + 1 + 2 - 3) // 2 + 1, ((S2 + 6 - 7) // 2 + 1 + 2 - 3) // 2 + 1
+        import os
+        off = bool(os.environ.get("CDETR_NO_IMPLICIT_CONV"))
+        for blk in self.blocks:
+            s = blk["stride"]
+            ok = (not off and s == 1 and W in (16, 32, 64, 128) and (H * W) % 128 == 0 and blk["planes"] % 64 == 0)
+            if blk["c2"].implicit != ok:
+                blk["c2"].implicit = ok
+                self.packed = False
+            H, W = (H - 1) // s + 1, (W - 1) // s + 1
+
     def _backbone_fwd(self, image):
         B, _, S1, S2 = image.shape
         sv = self.saved
@@ -298,8 +326,9 @@ class Engine:
         max_col, Hs, Ws = 0, H, W
         for blk in self.blocks:
             Hs, Ws = (Hs - 1) // blk["stride"] + 1, (Ws - 1) // blk["stride"] + 1
-            max_col = max(max_col, B * Hs * Ws * _r8(9 * blk["planes"]))
-        colbuf = self.buf("col_scratch", (2, max_col), torch.bfloat16)
+            if not blk["c2"].implicit:
+                max_col = max(max_col, B * Hs * Ws * _r8(9 * blk["planes"]))
+        colbuf = self.buf("col_scratch", (2, max(max_col, 8)), torch.bfloat16)
         for blk in self.blocks:
             n, p_, s, d = blk["name"], blk["planes"], blk["stride"], blk["dil"]
             Min = B * H * W
@@ -307,13 +336,17 @@ class Engine:
             Mo = B * Ho * Wo
             a = self.sbuf(n + ".a", Min, p_)
             blk["c1"].fwd(x, Min, out_split=a, relu=True)
-            if blk["train"]:     # kept for the wgrad GEMM of the backward pass (3 GB at C3; saves the re-gather)
-                col = self.sbuf(n + ".col", Mo, 9 * p_)
-            else:
-                col = colbuf[:, : Mo * 9 * p_].view(2, Mo, 9 * p_)
-            L.call("cdetr_im2col3x3", a, B, H, W, p_, s, d, col)
             b = self.sbuf(n + ".b", Mo, p_)
-            blk["c2"].fwd(col, Mo, out_split=b, relu=True)
+            if blk["c2"].implicit:
+                col = None
+                blk["c2"].fwd(a, Mo, out_split=b, relu=True, conv=(H, W, p_, d, 1))
+            else:
+                if blk["train"]:     # kept for the wgrad GEMM of the backward pass (saves the re-gather)
+                    col = self.sbuf(n + ".col", Mo, 9 * p_)
+                else:
+                    col = colbuf[:, : Mo * 9 * p_].view(2, Mo, 9 * p_)
+                L.call("cdetr_im2col3x3", a, B, H, W, p_, s, d, col)
+                blk["c2"].fwd(col, Mo, out_split=b, relu=True)
             if blk["ds"] is not None:
                 if s == 2:
                     xs = self.sbuf(n + ".xs", Mo, blk["cin"])
@@ -345,11 +378,15 @@ class Engine:
             blk["c3"].wgrad(g, t["b"], Mo)
             db = self.sbuf(n + ".db", Mo, p_)
             blk["c3"].dgrad(g, Mo, out_split=db, mask=t["b"])
-            blk["c2"].wgrad(db, t["col"], Mo)
-            dcol = col2buf[:, : Mo * 9 * p_].view(2, Mo, 9 * p_)
-            blk["c2"].dgrad(db, Mo, out_split=dcol)
             da = self.sbuf(n + ".da", Min, p_)
-            L.call("cdetr_col2im3x3", dcol, B, H, W, p_, s, d, t["a"], da)
+            if blk["c2"].implicit:
+                blk["c2"].wgrad(db, t["a"], Mo, conv=(H, W, p_, d, 1))
+                blk["c2"].dgrad_conv(db, Mo, H, W, d, out_split=da, mask=t["a"])
+            else:
+                blk["c2"].wgrad(db, t["col"], Mo)
+                dcol = col2buf[:, : Mo * 9 * p_].view(2, Mo, 9 * p_)
+                blk["c2"].dgrad(db, Mo, out_split=dcol)
+                L.call("cdetr_col2im3x3", dcol, B, H, W, p_, s, d, t["a"], da)
             blk["c1"].wgrad(da, t["x"], Min)
             if blk["ds"] is not None:
                 blk["ds"].wgrad(g, t["xs"], Mo)
@@ -534,6 +571,7 @@ class Engine:
 
     def forward(self, image, centres_yx=None, points=None, mask=None):
         """image [B,3,S,S] fp32 cuda; centres_yx int32 [n_ex,2] (stage 2); returns dict of fp32 outputs."""
+        self._plan_backbone(image.shape[2], image.shape[3])
         if not self.packed:
             self.pack_weights()
         cfg, E, sv = self.cfg, self.E, self.saved

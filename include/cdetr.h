@@ -67,6 +67,18 @@ typedef struct {
   float* out_f32;
   int64_t ld_out_f32;
   cdetr_split_t out_split; /* base NULL = none */
+  /* Implicit 3x3 convolution (stride 1, padding = dilation), conv_taps = 9 (0 = plain GEMM).  The "conv operand"
+   * is an NHWC split activation x [B*H*W, C] read with shifted TMA windows (out-of-image taps zero-filled by the
+   * TMA unit) instead of an im2col matrix; replaces F.conv2d at A2/models/resnet.py:147-149 and its autograd:
+   *   mode 0: conv operand = a.  K = 9*C ordered (tap, c); row m of D is pixel m:
+   *           D[m, n] = sum_{tap,c} x[pixel m + conv_sign * off(tap), c] * B[n, tap*C + c]
+   *           (conv_sign = +1: forward with weights [N, 9C];  -1: dgrad with dy as x and weights [Cin, 9*Cout])
+   *   mode 1: conv operand = b.  N = 9*C ordered (tap, c); K = B*H*W pixels:
+   *           D[m, tap*C + c] = sum_p A[p, m] * x[pixel p + off(tap), c]            (wgrad, staged as [Cout, 9*Cin])
+   * off(tap) = ((tap/3 - 1) * dil rows, (tap%3 - 1) * dil columns).  Needs C % 64 == 0, W a divisor of 128 and
+   * H*W a multiple of 128 (a 128-row tile = whole image rows); callers lower other shapes through cdetr_im2col3x3. */
+  int32_t conv_taps;
+  int32_t conv_H, conv_W, conv_C, conv_dil, conv_sign;
 } cdetr_gemm_t;
 
 int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream);
@@ -81,6 +93,9 @@ int cdetr_bn_fold(const float* w, const float* b, const float* rm, const float* 
 /* w [cout, cin, taps] fp32 -> dst [cout, taps*cin] and/or dst_t [taps*cin, cout] (row_scale folded) */
 int cdetr_pack_weight(const float* w, int cout, int cin, int taps, const float* row_scale,
                       cdetr_split_t dst, cdetr_split_t dst_t, cdetr_stream_t s);
+/* w [cout, cin, taps] fp32 -> dst [cin, taps*cout] (row_scale[cout] folded): B operand of the implicit-conv dgrad */
+int cdetr_pack_weight_dgrad(const float* w, int cout, int cin, int taps, const float* row_scale,
+                            cdetr_split_t dst, cdetr_stream_t s);
 /* grad [cout, cin, taps] += g [cout, taps*cin] */
 int cdetr_unpack_conv_grad(const float* g, int cout, int cin, int taps, float* grad, cdetr_stream_t s);
 int cdetr_to_split(const float* x, int64_t rows, int cols, int64_t ld_x, cdetr_split_t dst, cdetr_stream_t s);

@@ -1,4 +1,9 @@
-"""Per-shape time of every GEMM launch in one C3 train step (CUDA events around each launch)."""
+"""Per-shape time of every GEMM launch in one train step.
+
+Pass 1 records every cdetr_gemm call of one eager step (shape + epilogue flavour, CUDA events around each launch:
+includes launch gaps, so tiny GEMMs look slower than they are).  Pass 2 replays each distinct call REPS times
+back-to-back between two events (no launch gaps; operands of small GEMMs become L2-resident, as they mostly are
+in the real step where the producer kernel has just written them)."""
 import os, sys, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,6 +12,7 @@ from counting_detr_b200 import _lib as L, synthetic as SY
 from counting_detr_b200.models import build_model
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
+REPS = 10
 st, B, S, Q, T = bench.WORKLOADS[name]
 dev = torch.device("cuda", 0)
 model, crit, _ = build_model(SY.default_args(st, num_query_position=Q, device="cuda"))
@@ -14,33 +20,59 @@ model.load_state_dict(SY.make_state_dict(SY.SynthCfg(stage=st, num_query_positio
 model.to(dev).train()
 inp = SY.make_inputs(B, S, T=T, stage=st, Q=Q)
 img = inp["image"].to(dev)
-targets = [{k: v.to(dev) for k, v in t.items()} for t in inp["targets"]]
+targets = [{k: v.to(dev) for k, v in t.items()} for t in inp["targets"]] if st == 2 else {"points": inp["points"].to(dev), "whs": inp["whs"].to(dev)}
 
 def step():
     model.zero_grad(set_to_none=True)
-    out, _ = model(img, None, inp["rects"])
+    if st == 2:
+        out, _ = model(img, None, inp["rects"])
+    else:
+        out = model(img, targets["points"])
     ld = crit(out, targets)
     sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict).backward()
 
+eng = model.engine()
+eng.side_stream, eng.aux_streams = None, []
 for _ in range(2): step()
 torch.cuda.synchronize()
-# record mode per call too
 orig = L.gemm
-modes = []
+calls = []
 def traced(a, b, M, N, K, mode=0, **kw):
-    modes.append((mode, kw.get("split_k", 1), kw.get("block_n", 0), "split" if kw.get("out_split") is not None else "f32",
-                  "+add" if kw.get("add_split") is not None or kw.get("add_f32") is not None else "", "+mask" if kw.get("mask") is not None else ""))
+    calls.append((a, b, M, N, K, mode, dict(kw)))
     return orig(a, b, M, N, K, mode=mode, **kw)
 L.gemm = traced
 import counting_detr_b200.engine as EN
 EN.L.gemm = traced
 L.GEMM_TRACE = []
 step(); torch.cuda.synchronize()
-agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
-for (M, N, K, e0, e1), md in zip(L.GEMM_TRACE, modes):
-    key = (md[0], M, N, K) + md[1:]
-    agg[key][0] += 1; agg[key][1] += e0.elapsed_time(e1) * 1e3; agg[key][2] += 2.0 * M * N * K
-tot = sum(v[1] for v in agg.values())
-print(f"total gemm {tot/1e3:.2f} ms, {sum(v[2] for v in agg.values())/1e9:.0f} GF")
-for key, (n, us, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
-    print(f"{us:8.0f} us {100*us/tot:5.1f}% n={n:3d} avg={us/n:7.1f} us  {fl/us/1e6:7.1f} TF/s alg  mode={key[0]} M={key[1]} N={key[2]} K={key[3]} splitk={key[4]} bn={key[5]} out={key[6]}{key[7]}{key[8]}")
+trace, L.GEMM_TRACE = L.GEMM_TRACE, None
+L.gemm = orig; EN.L.gemm = orig
+
+def flavour(mode, kw):
+    return (mode, kw.get("split_k", 1), kw.get("block_n", 0),
+            ("split" if kw.get("out_split") is not None else "") + ("f32" if kw.get("out_f32") is not None else ""),
+            "+add" if kw.get("add_split") is not None or kw.get("add_f32") is not None else "",
+            "+mask" if kw.get("mask") is not None else "", "+acc" if kw.get("accumulate") else "")
+
+agg = collections.OrderedDict()
+for (a, b, M, N, K, mode, kw), (_, _, _, e0, e1) in zip(calls, trace):
+    key = (M, N, K) + flavour(mode, kw)
+    ent = agg.setdefault(key, dict(n=0, us_eager=0.0, call=(a, b, M, N, K, mode, kw)))
+    ent["n"] += 1; ent["us_eager"] += e0.elapsed_time(e1) * 1e3
+for key, ent in agg.items():
+    a, b, M, N, K, mode, kw = ent["call"]
+    for _ in range(2): orig(a, b, M, N, K, mode=mode, **kw)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(REPS): orig(a, b, M, N, K, mode=mode, **kw)
+    e1.record(); torch.cuda.synchronize()
+    ent["us"] = e0.elapsed_time(e1) * 1e3 / REPS
+tot = sum(e["us"] * e["n"] for e in agg.values()); tot_e = sum(e["us_eager"] for e in agg.values())
+fl_tot = sum(2.0 * k[0] * k[1] * k[2] * e["n"] for k, e in agg.items())
+print(f"{name}: {sum(e['n'] for e in agg.values())} gemm launches, {len(agg)} distinct; back-to-back total {tot/1e3:.2f} ms "
+      f"(eager per-launch events {tot_e/1e3:.2f} ms), {fl_tot/1e9:.0f} GF algorithmic -> {fl_tot/tot/1e6:.1f} TF/s alg")
+for key, e in sorted(agg.items(), key=lambda kv: -kv[1]["us"] * kv[1]["n"])[:70]:
+    M, N, K = key[:3]; fl = 2.0 * M * N * K
+    byt = 4.0 * (M * K + N * K) + (4.0 * M * N * (("split" in key[6]) + ("f32" in key[6]) + (key[7] != "") + 0.5 * (key[8] != "")))
+    print(f"{e['us']*e['n']:8.0f} us {100*e['us']*e['n']/tot:5.1f}% n={e['n']:3d} avg={e['us']:7.1f} us (eager {e['us_eager']/e['n']:6.1f}) "
+          f"{fl/e['us']/1e6:7.1f} TF/s alg {byt/e['us']/1e3:6.0f} GB/s  mode={key[3]} M={M} N={N} K={K} splitk={key[4]} bn={key[5]} out={key[6]}{key[7]}{key[8]}{key[9]}")

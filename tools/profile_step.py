@@ -9,9 +9,10 @@ from counting_detr_b200 import synthetic as SY
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
 st, B, S, Q, T = bench.WORKLOADS[name]
 dev = torch.device("cuda", 0)
-args = SY.default_args(st, num_query_position=Q, device="cuda")
+nl = int(os.environ.get("PROFILE_LAYERS", "6"))   # 1 = one encoder + one decoder layer (same shapes, every kernel type once)
+args = SY.default_args(st, num_query_position=Q, device="cuda", enc_layers=nl, dec_layers=nl)
 model, crit, _ = build_model(args)
-model.load_state_dict(SY.make_state_dict(SY.SynthCfg(stage=st, num_query_position=Q), 0), strict=True)
+model.load_state_dict(SY.make_state_dict(SY.SynthCfg(stage=st, num_query_position=Q, enc_layers=nl, dec_layers=nl), 0), strict=True)
 model.to(dev).train()
 inp = SY.make_inputs(B, S, T=T, stage=st, Q=Q)
 img = inp["image"].to(dev)
