@@ -75,7 +75,8 @@ def _ptr(t):
 
 # kernel-launch accounting (bench.py's gpu_launches) and optional per-GEMM event trace (bench.py's roofline)
 COUNTER = {"launches": 0}
-_LAUNCHES = {"cdetr_exemplar_concat": 2, "cdetr_exemplar_concat_bwd": 2, "cdetr_rcda_bwd": 3, "cdetr_rcda_bwd_kv": 2, "cdetr_mha_bwd": 2}
+_LAUNCHES = {"cdetr_exemplar_concat": 2, "cdetr_exemplar_concat_bwd": 2, "cdetr_rcda_bwd": 3, "cdetr_rcda_bwd_kv": 2, "cdetr_mha_bwd": 2,
+             "cdetr_mt_grad_norm": 2, "cdetr_mt_adamw": 2}
 GEMM_TRACE = None
 
 
@@ -168,6 +169,9 @@ _SIGS = {
     "cdetr_set_loss_bwd": "pppppplppp",
     "cdetr_bbox_loss_fwd": "ppplppp",
     "cdetr_bbox_loss_bwd": "ppplp",
+    "cdetr_mt_grad_norm": "ppiifpp",
+    "cdetr_mt_clip_scale": "ppiip",
+    "cdetr_mt_adamw": "ppiipfffpp",
 }
 _CT = {"p": C.c_void_p, "i": C.c_int32, "l": C.c_int64, "f": C.c_float, "S": SplitT}
 _bound = {}

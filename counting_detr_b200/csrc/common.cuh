@@ -53,9 +53,21 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // reference while running on the bf16 tensor pipe.
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+// Two values at once through the packed convert (cvt.rn.bf16x2.f32 -> F2FP.BF16.F32.PACK_AB, FMA-rate pipe) instead
+// of two scalar F2F.BF16.F32 (XU pipe, 16 lanes/clk/SM): the scalar form made the XU pipe the limiter of every
+// kernel that writes split tensors (ncu: 40 % XU in rcda_bwd_v_tc).  Same round-to-nearest-even results.
+//   hi_pair / lo_pair = {x1 in the upper 16 bits, x0 in the lower 16 bits}
+__device__ __forceinline__ void split_bf16_pair(float x0, float x1, uint32_t& hi_pair, uint32_t& lo_pair) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi_pair) : "f"(x1), "f"(x0));
+  const float r0 = x0 - __uint_as_float(hi_pair << 16);
+  const float r1 = x1 - __uint_as_float(hi_pair & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo_pair) : "f"(r1), "f"(r0));
+}
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+  uint32_t h, l;
+  split_bf16_pair(x, 0.0f, h, l);
+  hi = __ushort_as_bfloat16((unsigned short)(h & 0xffffu));
+  lo = __ushort_as_bfloat16((unsigned short)(l & 0xffffu));
 }
 __device__ __forceinline__ float join_bf16(__nv_bfloat16 hi, __nv_bfloat16 lo) {
   return __bfloat162float(hi) + __bfloat162float(lo);

@@ -164,11 +164,7 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(o[2 * j], h0, l0);
-      split_bf16(o[2 * j + 1], h1, l1);
-      hw[j] = pack_bf16x2(h0, h1);
-      lw[j] = pack_bf16x2(l0, l1);
+      split_bf16_pair(o[2 * j], o[2 * j + 1], hw[j], lw[j]);
     }
     *reinterpret_cast<uint4*>(y_hi + row * ld_split + lane * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     *reinterpret_cast<uint4*>(y_lo + row * ld_split + lane * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -238,11 +234,7 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
       uint32_t hw[4], lw[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(o[2 * j], h0, l0);
-        split_bf16(o[2 * j + 1], h1, l1);
-        hw[j] = pack_bf16x2(h0, h1);
-        lw[j] = pack_bf16x2(l0, l1);
+        split_bf16_pair(o[2 * j], o[2 * j + 1], hw[j], lw[j]);
       }
       *reinterpret_cast<uint4*>(dz_hi + row * ld_split + lane * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
       *reinterpret_cast<uint4*>(dz_lo + row * ld_split + lane * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);

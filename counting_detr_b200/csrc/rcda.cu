@@ -48,11 +48,7 @@ __device__ __forceinline__ void store_split32(__nv_bfloat16* hi, __nv_bfloat16* 
     uint32_t hw[4], lw[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v[g * 8 + 2 * j], h0, l0);
-      split_bf16(v[g * 8 + 2 * j + 1], h1, l1);
-      hw[j] = pack_bf16x2(h0, h1);
-      lw[j] = pack_bf16x2(l0, l1);
+      split_bf16_pair(v[g * 8 + 2 * j], v[g * 8 + 2 * j + 1], hw[j], lw[j]);
     }
     reinterpret_cast<uint4*>(hi)[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     reinterpret_cast<uint4*>(lo)[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);

@@ -190,11 +190,7 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(ar[8 * j + 2 * i], h0, l0);
-            split_bf16(ar[8 * j + 2 * i + 1], h1, l1);
-            hw[i] = pack_bf16x2(h0, h1);
-            lw[i] = pack_bf16x2(l0, l1);
+            split_bf16_pair(ar[8 * j + 2 * i], ar[8 * j + 2 * i + 1], hw[i], lw[i]);
           }
           const uint32_t off = (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4);
           *reinterpret_cast<uint4*>(Ag + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -249,11 +245,7 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(acc[gg * 8 + 2 * j], h0, l0);
-            split_bf16(acc[gg * 8 + 2 * j + 1], h1, l1);
-            hw[j] = pack_bf16x2(h0, h1);
-            lw[j] = pack_bf16x2(l0, l1);
+            split_bf16_pair(acc[gg * 8 + 2 * j], acc[gg * 8 + 2 * j + 1], hw[j], lw[j]);
           }
           reinterpret_cast<uint4*>(a.o_hi + off)[gg] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           reinterpret_cast<uint4*>(a.o_lo + off)[gg] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -392,11 +384,7 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(dov[8 * j + 2 * i], h0, l0);
-            split_bf16(dov[8 * j + 2 * i + 1], h1, l1);
-            hw[i] = pack_bf16x2(h0, h1);
-            lw[i] = pack_bf16x2(l0, l1);
+            split_bf16_pair(dov[8 * j + 2 * i], dov[8 * j + 2 * i + 1], hw[i], lw[i]);
           }
           const uint32_t off = (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4);
           *reinterpret_cast<uint4*>(Ag + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -478,11 +466,7 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(dq[gg * 8 + 2 * j] * scale, h0, l0);
-            split_bf16(dq[gg * 8 + 2 * j + 1] * scale, h1, l1);
-            hw[j] = pack_bf16x2(h0, h1);
-            lw[j] = pack_bf16x2(l0, l1);
+            split_bf16_pair(dq[gg * 8 + 2 * j] * scale, dq[gg * 8 + 2 * j + 1] * scale, hw[j], lw[j]);
           }
           reinterpret_cast<uint4*>(a.dqr_hi + off)[gg] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           reinterpret_cast<uint4*>(a.dqr_lo + off)[gg] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -512,11 +496,7 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(dq[gg * 8 + 2 * j] * scale, h0, l0);
-            split_bf16(dq[gg * 8 + 2 * j + 1] * scale, h1, l1);
-            hw[j] = pack_bf16x2(h0, h1);
-            lw[j] = pack_bf16x2(l0, l1);
+            split_bf16_pair(dq[gg * 8 + 2 * j] * scale, dq[gg * 8 + 2 * j + 1] * scale, hw[j], lw[j]);
           }
           reinterpret_cast<uint4*>(a.dqc_hi + off)[gg] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           reinterpret_cast<uint4*>(a.dqc_lo + off)[gg] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -667,11 +647,7 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(mok ? pv[2 * i] : 0.0f, h0, l0);
-            split_bf16(mok ? pv[2 * i + 1] : 0.0f, h1, l1);
-            hw[i] = pack_bf16x2(h0, h1);
-            lw[i] = pack_bf16x2(l0, l1);
+            split_bf16_pair(mok ? pv[2 * i] : 0.0f, mok ? pv[2 * i + 1] : 0.0f, hw[i], lw[i]);
           }
           const uint32_t off = (uint32_t)ml * 128u + (uint32_t)(((qh * 4 + j) ^ (ml & 7)) << 4);
           *reinterpret_cast<uint4*>(Pb + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -699,11 +675,7 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(__uint_as_float(t[gg * 8 + 2 * j]), h0, l0);
-            split_bf16(__uint_as_float(t[gg * 8 + 2 * j + 1]), h1, l1);
-            hw[j] = pack_bf16x2(h0, h1);
-            lw[j] = pack_bf16x2(l0, l1);
+            split_bf16_pair(__uint_as_float(t[gg * 8 + 2 * j]), __uint_as_float(t[gg * 8 + 2 * j + 1]), hw[j], lw[j]);
           }
           reinterpret_cast<uint4*>(a.dv_hi + off)[gg] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           reinterpret_cast<uint4*>(a.dv_lo + off)[gg] = make_uint4(lw[0], lw[1], lw[2], lw[3]);

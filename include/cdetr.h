@@ -218,6 +218,32 @@ int cdetr_bbox_loss_fwd(const float* pred_wh, const float* points, const float* 
 int cdetr_bbox_loss_bwd(const float* upstream2, const float* g_wh, const float* g_giou, int64_t n, float* d_wh,
                         cdetr_stream_t s);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer tail: multi-tensor gradient-norm clipping + AdamW.  Replace
+ *   A2/engine.py:53-56  torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
+ *   A2/engine.py:57 / A2/main.py:188  torch.optim.AdamW(param_dicts, lr, weight_decay).step()
+ * table: device array of tensors; blocks: device int32 [nblocks][2] = (tensor index, chunk index), every block
+ * handles elements [chunk_index*chunk, +chunk) of its tensor.  hyper: device float [ngroups][4] = {lr, weight_decay,
+ * 0, 0}.  norm_out: device float[3] = {sum of squares, total L2 norm, clip coefficient min(1, max_norm/(norm+1e-6))}.
+ * cdetr_mt_adamw applies norm_out[2] to the gradients on the fly when norm_out != NULL (fused clip) and increments
+ * the device step counter.  Update order follows torch.optim.adamw._single_tensor_adamw.
+ * --------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* p;       /* parameter */
+  float* g;       /* gradient */
+  float* m;       /* exp_avg */
+  float* v;       /* exp_avg_sq */
+  int64_t n;      /* elements */
+  int32_t group;  /* row of `hyper` */
+  int32_t pad_;
+} cdetr_mt_tensor_t;
+int cdetr_mt_grad_norm(const cdetr_mt_tensor_t* table, const int32_t* blocks, int nblocks, int chunk, float max_norm,
+                       float* partial /* [nblocks] scratch */, float* norm_out, cdetr_stream_t s);
+int cdetr_mt_clip_scale(const cdetr_mt_tensor_t* table, const int32_t* blocks, int nblocks, int chunk,
+                        const float* norm_out, cdetr_stream_t s);
+int cdetr_mt_adamw(const cdetr_mt_tensor_t* table, const int32_t* blocks, int nblocks, int chunk, const float* hyper,
+                   float beta1, float beta2, float eps, int* step, const float* norm_out, cdetr_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif
