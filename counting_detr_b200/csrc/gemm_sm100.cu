@@ -236,6 +236,34 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const float rs = (ep.row_scale != nullptr && row_t < args.M) ? ep.row_scale[row_t] : 1.0f;
     const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * args.tmem_cols;
     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+      const int cl = c0 + g8;     // tile-local first column of this lane's 8-vector in the coalesced phase
+      const int nb = n0 + cl;
+      const bool col_ok = cl < c_end && nb < args.N;
+      const bool full = vec_ok && (nb + 8 <= args.N);
+      // Prefetch this chunk's residual / mask vectors (global memory, L2 or HBM latency) BEFORE the TMEM reads and
+      // the shared-memory transpose so that their latency overlaps that work instead of serialising after it.
+      uint4 pa0[4], pa1[4], pm[4];
+      const bool pre = col_ok && full;
+      const bool pre_add = pre && (ep.add_hi != nullptr || ep.add_f32 != nullptr);
+      const bool pre_mask = pre && ep.mask_hi != nullptr;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = m0 + q * 32 + rr + 8 * i;
+        pa0[i] = make_uint4(0, 0, 0, 0); pa1[i] = pa0[i]; pm[i] = pa0[i];
+        if (row < args.M) {
+          if (pre_add) {
+            if (ep.add_hi != nullptr) {
+              pa0[i] = __ldg(reinterpret_cast<const uint4*>(ep.add_hi + (int64_t)row * ep.ld_add + nb));
+              pa1[i] = __ldg(reinterpret_cast<const uint4*>(ep.add_lo + (int64_t)row * ep.ld_add + nb));
+            } else {
+              const uint4* pf = reinterpret_cast<const uint4*>(ep.add_f32 + (int64_t)row * ep.ld_add_f32 + nb);
+              pa0[i] = __ldg(pf);
+              pa1[i] = __ldg(pf + 1);
+            }
+          }
+          if (pre_mask) pm[i] = __ldg(reinterpret_cast<const uint4*>(ep.mask_hi + (int64_t)row * ep.ld_mask + nb));
+        }
+      }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         if (c0 + 16 * u < c_end) {  // warp-uniform
@@ -247,10 +275,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       __syncwarp();
-      const int cl = c0 + g8;     // tile-local first column of this lane's 8-vector
-      const int nb = n0 + cl;
-      if (cl < c_end && nb < args.N) {
-        const bool full = vec_ok && (nb + 8 <= args.N);
+      if (col_ok) {
         float bias8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) bias8[j] = (ep.bias != nullptr && nb + j < args.N) ? __ldg(ep.bias + nb + j) : 0.0f;
@@ -263,25 +288,28 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = stg[rl * STG_LD + g8 + j] + bias8[j];
           if (ep.add_hi != nullptr) {
-            const __nv_bfloat16* ph = ep.add_hi + (int64_t)row * ep.ld_add + nb;
-            const __nv_bfloat16* pl = ep.add_lo + (int64_t)row * ep.ld_add + nb;
             if (full) {
-              const uint4 h = __ldg(reinterpret_cast<const uint4*>(ph));
-              const uint4 l = __ldg(reinterpret_cast<const uint4*>(pl));
-              const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+              const uint32_t hw[4] = {pa0[i].x, pa0[i].y, pa0[i].z, pa0[i].w}, lw[4] = {pa1[i].x, pa1[i].y, pa1[i].z, pa1[i].w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 v[2 * j] += bf16_bits_to_float(hw[j] & 0xffffu) + bf16_bits_to_float(lw[j] & 0xffffu);
                 v[2 * j + 1] += bf16_bits_to_float(hw[j] >> 16) + bf16_bits_to_float(lw[j] >> 16);
               }
             } else {
+              const __nv_bfloat16* ph = ep.add_hi + (int64_t)row * ep.ld_add + nb;
+              const __nv_bfloat16* pl = ep.add_lo + (int64_t)row * ep.ld_add + nb;
               for (int j = 0; j < 8; ++j)
                 if (nb + j < args.N) v[j] += join_bf16(ph[j], pl[j]);
             }
           }
           if (ep.add_f32 != nullptr) {
             const float* pa = ep.add_f32 + (int64_t)row * ep.ld_add_f32 + nb;
-            if (full) {
+            if (full && ep.add_hi == nullptr) {   // prefetched
+              v[0] += __uint_as_float(pa0[i].x); v[1] += __uint_as_float(pa0[i].y);
+              v[2] += __uint_as_float(pa0[i].z); v[3] += __uint_as_float(pa0[i].w);
+              v[4] += __uint_as_float(pa1[i].x); v[5] += __uint_as_float(pa1[i].y);
+              v[6] += __uint_as_float(pa1[i].z); v[7] += __uint_as_float(pa1[i].w);
+            } else if (full) {
               const float4 t0 = __ldg(reinterpret_cast<const float4*>(pa));
               const float4 t1 = __ldg(reinterpret_cast<const float4*>(pa) + 1);
               v[0] += t0.x; v[1] += t0.y; v[2] += t0.z; v[3] += t0.w;
@@ -296,10 +324,9 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
           }
           if (ep.mask_hi != nullptr) {
-            const __nv_bfloat16* pm = ep.mask_hi + (int64_t)row * ep.ld_mask + nb;
+            const __nv_bfloat16* pmk = ep.mask_hi + (int64_t)row * ep.ld_mask + nb;
             if (full) {
-              const uint4 h = __ldg(reinterpret_cast<const uint4*>(pm));
-              const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+              const uint32_t hw[4] = {pm[i].x, pm[i].y, pm[i].z, pm[i].w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 if (!(bf16_bits_to_float(hw[j] & 0xffffu) > 0.0f)) v[2 * j] = 0.0f;
@@ -307,7 +334,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               }
             } else {
               for (int j = 0; j < 8; ++j)
-                if (nb + j < args.N && !(__bfloat162float(pm[j]) > 0.0f)) v[j] = 0.0f;
+                if (nb + j < args.N && !(__bfloat162float(pmk[j]) > 0.0f)) v[j] = 0.0f;
             }
           }
           if (ep.out_f32 != nullptr) {
@@ -447,14 +474,26 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   CDETR_CHECK_ARG(g->out_f32 != nullptr || g->out_split.base != nullptr, "gemm: no output");
   const bool nt = g->mode == 1;
 
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    CDETR_CHECK_CUDA(cudaGetDevice(&dev));
+    CDETR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   int bn = g->block_n;
   if (bn <= 0) {
-    // measured on B200 (tools/gemm_sweep.py): 256-wide tiles only pay for long K loops on wide outputs
-    if (!nt && g->N >= 512 && g->K >= 1024) bn = 256;
+    // measured on B200 (tools/gemm_sweep.py, profiles/r01_gemm_sweep_v8.txt).  The GEMM family is bound by the
+    // L2 -> SM operand traffic (~8.5 TB/s aggregate for 4-byte split operands), so wide tiles pay whenever the K
+    // loop is long enough to amortise them and there are enough tiles to fill the machine
+    const int tiles_m = cdiv(g->M, BM);
+    if (!nt && g->N >= 256 && g->K >= 1024 && (g->N >= 512 || tiles_m * cdiv(g->N, 256) >= (3 * num_sms) / 4)) bn = 256;
     else if (g->N > 64) bn = 128;
     else if (g->N > 32) bn = 64;
     else if (g->N > 16) bn = 32;
     else bn = 16;
+    // short-K problems with fewer tiles than SMs are latency-bound: spread them over more CTAs
+    if (!nt && g->K <= 256)
+      while (bn > 32 && tiles_m * cdiv(g->N, bn) < num_sms) bn >>= 1;
     if (nt && bn < 64) bn = 64;
   }
   CDETR_CHECK_ARG(bn >= 16 && bn <= 256 && bn % 16 == 0, "gemm: bad block_n %d", bn);
@@ -535,6 +574,9 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   // co-resident CTAs (possibly of different kernels: the weight-gradient stream) hide each other's TMA latency;
   // 256-wide tiles own the SM and get a deeper pipeline instead.
   int ctas_per_sm = (2 * cols <= 256) ? 2 : 1;
+  // long K loops on narrow outputs (A streamed once, light epilogue): one CTA with a deep TMA pipeline beats two
+  // single-stage CTAs (sweep: 10-15 % on N<=256, K>=512)
+  if (!nt && g->N <= 256 && kb_per_split >= 8) ctas_per_sm = 1;
   const uint32_t per_cta = ctas_per_sm == 2 ? (113u * 1024u - tail_bytes) : smem_budget;
   int stages = (int)(per_cta / stage_bytes);
   if (stages < 1) { stages = 1; ctas_per_sm = 1; }
@@ -580,12 +622,6 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
     return CDETR_ERR_ARG;
   }
 
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    CDETR_CHECK_CUDA(cudaGetDevice(&dev));
-    CDETR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
   int nctas = num_sms * ctas_per_sm;
   if (nctas > ka.total_tiles) nctas = ka.total_tiles;
   dim3 grid(nctas);
