@@ -54,8 +54,31 @@ struct KernelArgs {
   // implicit 3x3 convolution (conv != 0): the conv operand (A in mode 0, B in mode 1) is an NHWC activation read
   // through a 5-D map {C, W, H, B, plane} with per-tap shifted windows; TMA zero-fills the out-of-image part
   int conv, cH, cW, cC, cdil, csign;
+  // resident-B schedule (mode 0, K <= 256): the whole [BN x K] weight slab of an n-tile stays in shared memory while
+  // the CTA walks a contiguous run of m-tiles, so only A streams through the TMA ring (half the L2 -> SM bytes)
+  int resident_b, tiles_per_cta;
+  uint32_t staging_off;  // byte offset of the epilogue staging area (after the operand stages)
   EpilogueArgs ep;
 };
+
+struct TileCoord {
+  int m0, n0, kb_begin, kb_end;
+};
+__device__ __forceinline__ TileCoord decode_tile(const KernelArgs& a, int tile) {
+  TileCoord t;
+  if (a.resident_b) {  // n-major: consecutive tiles of a CTA share the n-tile
+    t.n0 = (tile / a.tiles_m) * a.block_n;
+    t.m0 = (tile % a.tiles_m) * BM;
+    t.kb_begin = 0;
+    t.kb_end = a.num_kb;
+  } else {
+    t.n0 = (tile % a.tiles_n) * a.block_n;
+    t.m0 = ((tile / a.tiles_n) % a.tiles_m) * BM;
+    t.kb_begin = (tile / (a.tiles_n * a.tiles_m)) * a.kb_per_split;
+    t.kb_end = min(a.num_kb, t.kb_begin + a.kb_per_split);
+  }
+  return t;
+}
 
 template <bool NT>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
@@ -70,12 +93,20 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t b_bytes = NT ? (uint32_t)((BN + 63) / 64) * 16384u : 2u * (uint32_t)BN * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   constexpr int STG_LD = 33;                             // epilogue staging: 8 warps x [32][33] floats
-  float* staging = reinterpret_cast<float*>(smem + (size_t)args.stages * stage_bytes);
+  float* staging = reinterpret_cast<float*>(smem + args.staging_off);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 8 * 32 * STG_LD);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* slab_full_bar = tmem_empty_bar + 2;          // resident-B slab loaded / free to overwrite
+  uint64_t* slab_empty_bar = slab_full_bar + 1;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(slab_empty_bar + 1);
+  const bool RB = !NT && args.resident_b != 0;
+  const uint32_t slab_bytes = RB ? (uint32_t)args.num_kb * b_bytes : 0u;
+  // tile walk of this CTA: strided round-robin, or a contiguous run in the resident-B schedule
+  const int t_begin = RB ? blockIdx.x * args.tiles_per_cta : blockIdx.x;
+  const int t_end = RB ? min(args.total_tiles, t_begin + args.tiles_per_cta) : args.total_tiles;
+  const int t_step = RB ? 1 : gridDim.x;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,6 +125,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], 8);   // one elected lane of each epilogue warp
     }
+    mbar_init(slab_full_bar, 1);
+    mbar_init(slab_empty_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -109,11 +142,19 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % args.tiles_n) * BN;
-        const int m0 = ((tile / args.tiles_n) % args.tiles_m) * BM;
-        const int kb_begin = (tile / (args.tiles_n * args.tiles_m)) * args.kb_per_split;
-        const int kb_end = min(args.num_kb, kb_begin + args.kb_per_split);
+      int cur_n0 = -1;
+      uint32_t slab_gen = 0;
+      for (int tile = t_begin; tile < t_end; tile += t_step) {
+        const TileCoord tc = decode_tile(args, tile);
+        const int n0 = tc.n0, m0 = tc.m0, kb_begin = tc.kb_begin, kb_end = tc.kb_end;
+        if (RB && n0 != cur_n0) {   // new n-tile: (re)load the weight slab once every MMA on the old one is done
+          if (slab_gen > 0) mbar_wait(slab_empty_bar, (slab_gen - 1) & 1u);
+          mbar_arrive_expect_tx(slab_full_bar, slab_bytes);
+          for (int kb = 0; kb < args.num_kb; ++kb)
+            tma_load_3d(smem + (size_t)kb * b_bytes, &tmB, slab_full_bar, kb * BK, n0, 0);
+          cur_n0 = n0;
+          ++slab_gen;
+        }
         const int hw = args.cH * args.cW;
         int cb = 0, ch0 = 0;             // mode 0 conv: image and first pixel row of this 128-pixel tile
         if (!NT && args.conv) {
@@ -124,8 +165,13 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int s = it % stages;
           const uint32_t ph = (uint32_t)(it / stages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          uint8_t* a_s = smem + (size_t)s * stage_bytes;
+          uint8_t* a_s = RB ? smem + slab_bytes + (size_t)s * a_bytes : smem + (size_t)s * stage_bytes;
           uint8_t* b_s = a_s + a_bytes;
+          if (RB) {
+            mbar_arrive_expect_tx(&full_bar[s], a_bytes);
+            tma_load_3d(a_s, &tmA, &full_bar[s], kb * BK, m0, 0);  // box {64, BM, 2}
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
           if (!NT) {
             if (args.conv) {   // box {64 c, W, 128/W, 1, 2}: rows of the tile = pixels (h, w) of image cb, shifted by the tap
@@ -163,9 +209,17 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ------------------------------ MMA issuer --------------------------------
     if (lane == 0) {
       int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x, ++ti) {
-        const int kb_begin = (tile / (args.tiles_n * args.tiles_m)) * args.kb_per_split;
-        const int kb_end = min(args.num_kb, kb_begin + args.kb_per_split);
+      int cur_n0 = -1;
+      uint32_t slab_gen = 0;
+      for (int tile = t_begin; tile < t_end; tile += t_step, ++ti) {
+        const TileCoord tc = decode_tile(args, tile);
+        const int kb_begin = tc.kb_begin, kb_end = tc.kb_end;
+        if (RB && tc.n0 != cur_n0) {
+          mbar_wait(slab_full_bar, slab_gen & 1u);
+          tc_fence_after();
+          cur_n0 = tc.n0;
+          ++slab_gen;
+        }
         const int ab = ti & 1;
         if (ti >= 2) {  // the epilogue must have drained this accumulator buffer (used by tile ti-2)
           mbar_wait(&tmem_empty_bar[ab], (uint32_t)((ti >> 1) - 1) & 1u);
@@ -178,8 +232,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t ph = (uint32_t)(it / stages) & 1u;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t b_base = a_base + a_bytes;
+          const uint32_t a_base = smem_u32(RB ? smem + slab_bytes + (size_t)s * a_bytes : smem + (size_t)s * stage_bytes);
+          const uint32_t b_base = RB ? smem_u32(smem + (size_t)kb * b_bytes) : a_base + a_bytes;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             uint64_t a_hi, a_lo, b_hi, b_lo;
@@ -204,6 +258,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
         }
+        if (RB && (tile + 1 >= t_end || decode_tile(args, tile + 1).n0 != tc.n0))
+          umma_commit(slab_empty_bar);    // last MMA reading this weight slab: the producer may overwrite it
         umma_commit(&tmem_full_bar[ab]);  // accumulator of this tile complete
       }
     }
@@ -226,9 +282,9 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int g8 = (lane & 3) * 8;  // column group of this lane in the coalesced phase
     const int rr = lane >> 2;       // row sub-index 0..7
     int ti = 0;
-    for (int tile = blockIdx.x; tile < args.total_tiles; tile += gridDim.x, ++ti) {
-    const int n0 = (tile % args.tiles_n) * BN;
-    const int m0 = ((tile / args.tiles_n) % args.tiles_m) * BM;
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++ti) {
+    const TileCoord tc = decode_tile(args, tile);
+    const int n0 = tc.n0, m0 = tc.m0;
     const int ab = ti & 1;
     mbar_wait(&tmem_full_bar[ab], (uint32_t)(ti >> 1) & 1u);
     tc_fence_after();
@@ -568,7 +624,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   const uint32_t b_bytes = nt ? (uint32_t)((bn + 63) / 64) * 16384u : 2u * (uint32_t)bn * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t staging_bytes = 8u * 32u * 33u * 4u;
-  const uint32_t tail_bytes = staging_bytes + (2 * MAX_STAGES + 4) * 8 + 16;
+  const uint32_t tail_bytes = staging_bytes + (2 * MAX_STAGES + 6) * 8 + 16;
   const uint32_t smem_budget = 227u * 1024u - 1024u - tail_bytes;
   // Two accumulator buffers per CTA: tiles up to 128 wide leave TMEM (512 columns) for two CTAs per SM, and two
   // co-resident CTAs (possibly of different kernels: the weight-gradient stream) hide each other's TMA latency;
@@ -591,11 +647,39 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   }
   if ((uint32_t)stages * stage_bytes + tail_bytes + 1024 > 113u * 1024u) ctas_per_sm = 1;
   CDETR_CHECK_ARG((uint32_t)stages * stage_bytes <= smem_budget, "gemm: tile does not fit shared memory");
-  ka.stages = stages;
   ka.tiles_m = cdiv(g->M, BM);
   ka.tiles_n = cdiv(g->N, bn);
   ka.total_tiles = ka.tiles_m * ka.tiles_n * splits;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + tail_bytes + 1024;
+  // Resident-B schedule: short-K problems with many m-tiles per n-tile keep the [bn x K] weight slab in shared memory
+  // and stream only A (the L2 -> SM operand traffic, the limiter of these shapes, halves).  One CTA per SM.
+  bool resident = !nt && !conv && splits == 1 && num_kb <= 4 && bn <= 128 && ka.total_tiles >= 2 * num_sms &&
+                  (uint32_t)num_kb * b_bytes + 2 * a_bytes <= smem_budget;
+  if (const char* e = getenv("CDETR_GEMM_RESIDENT")) {
+    const int f = atoi(e);
+    if (f == 0) resident = false;
+    if (f == 1) resident = !nt && !conv && splits == 1 && (uint32_t)num_kb * b_bytes + 2 * a_bytes <= smem_budget;
+  }
+  ka.resident_b = 0;
+  ka.tiles_per_cta = 0;
+  size_t operand_bytes = (size_t)stages * stage_bytes;
+  if (resident) {
+    const uint32_t slab = (uint32_t)num_kb * b_bytes;
+    int st = (int)((smem_budget - slab) / a_bytes);
+    if (st > MAX_STAGES) st = MAX_STAGES;
+    if (const char* e = getenv("CDETR_GEMM_STAGES")) {
+      const int f = atoi(e);
+      if (f >= 1 && f <= st) st = f;
+    }
+    if (st >= 2) {
+      stages = st;
+      ctas_per_sm = 1;
+      ka.resident_b = 1;
+      operand_bytes = (size_t)slab + (size_t)stages * a_bytes;
+    }
+  }
+  ka.stages = stages;
+  ka.staging_off = (uint32_t)operand_bytes;
+  const size_t smem_bytes = operand_bytes + tail_bytes + 1024;
 
   EpilogueArgs& ep = ka.ep;
   ep.row_scale = g->row_scale;
@@ -624,6 +708,10 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
 
   int nctas = num_sms * ctas_per_sm;
   if (nctas > ka.total_tiles) nctas = ka.total_tiles;
+  if (ka.resident_b) {   // contiguous runs of tiles_per_cta tiles (n-major order)
+    ka.tiles_per_cta = cdiv(ka.total_tiles, nctas);
+    nctas = cdiv(ka.total_tiles, ka.tiles_per_cta);
+  }
   dim3 grid(nctas);
   auto kern = nt ? gemm_split_kernel<true> : gemm_split_kernel<false>;
   static size_t configured[2] = {0, 0};

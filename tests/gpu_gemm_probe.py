@@ -87,6 +87,23 @@ L.gemm(Xs[:, :, 256:], Ws[:, 512:768], 700, 256, 256, out_f32=out)
 torch.cuda.synchronize()
 report("subview", out, X[:, 256:].double() @ Wbig[512:768].double().t())
 
+# ---- resident-B schedule (weight slab kept in shared memory; K <= 256, many m-tiles): forced and automatic
+os.environ["CDETR_GEMM_RESIDENT"] = "1"
+run_tn(4096, 256, 256)
+run_tn(5000, 384, 192)         # ragged M / K tail, several slab reloads per CTA
+run_tn(40000, 128, 64)
+run_tn(3000, 200, 256, block_n=64)
+os.environ.pop("CDETR_GEMM_RESIDENT")
+run_tn(65536, 512, 128)        # automatic (>= 2 tiles per SM)
+M, N, K = 38000, 256, 256
+A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev)
+bias = torch.randn(N, device=dev); res = torch.randn(M, N, device=dev); mk = torch.randn(M, N, device=dev)
+ref = (A.double() @ B.double().t() + bias.double() + L.from_split(L.to_split(res)).double()) * (mk > 0).double()
+outs = torch.zeros(2, M, N, device=dev, dtype=torch.bfloat16)
+L.gemm(L.to_split(A), L.to_split(B), M, N, K, out_split=outs, bias=bias, add_split=L.to_split(res), mask=L.to_split(torch.relu(mk)))
+torch.cuda.synchronize()
+report("resident-B auto, bias+res+mask split", L.from_split(outs), ref)
+
 # ---- implicit 3x3 convolution (TMA shifted windows, no im2col matrix) vs torch conv2d in fp64
 import torch.nn.functional as F
 

@@ -53,17 +53,24 @@ for (M, N, K, ep) in shapes:
     for bn in (32, 64, 128, 256):
         if bn > max(N, 32):
             continue
-        for ctas in (1, 2):
+        for ctas in (1, 2, "R"):          # "R" = resident-B schedule (K <= 256 only)
+            if ctas == "R" and (K > 256 or bn > 128):
+                continue
             for st in (1, 2, 3, 4, 6):
-                os.environ["CDETR_GEMM_STAGES"] = str(st); os.environ["CDETR_GEMM_CTAS"] = str(ctas)
+                os.environ["CDETR_GEMM_STAGES"] = str(st)
+                os.environ["CDETR_GEMM_CTAS"] = "1" if ctas == "R" else str(ctas)
+                os.environ["CDETR_GEMM_RESIDENT"] = "1" if ctas == "R" else "0"
                 try:
                     t = timed(lambda: L.gemm(A, B, M, N, K, block_n=bn, **kw))
                     res.append((t, bn, ctas, st))
                 except Exception:
                     pass
-    os.environ.pop("CDETR_GEMM_STAGES", None); os.environ.pop("CDETR_GEMM_CTAS", None)
+    for k in ("CDETR_GEMM_STAGES", "CDETR_GEMM_CTAS", "CDETR_GEMM_RESIDENT"):
+        os.environ.pop(k, None)
     auto = timed(lambda: L.gemm(A, B, M, N, K, **kw))
     res.sort()
     fl = 2.0 * M * N * K
     print(f"M={M} N={N} K={K} {ep}: auto={auto:.1f}us ({fl/auto/1e6:.0f} TF/s alg) | best "
           + "  ".join(f"bn{bn}/c{c}/s{st}:{t:.1f}" for t, bn, c, st in res[:6]) + f" | worst {res[-1][0]:.1f}", flush=True)
+    if os.environ.get("SWEEP_FULL"):
+        print("      " + " ".join(f"bn{bn}/c{c}/s{st}:{t:.1f}" for t, bn, c, st in sorted(res, key=lambda r: (r[1], str(r[2]), r[3]))), flush=True)
