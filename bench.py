@@ -149,6 +149,50 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ attention roofline
+def attention_macs(name, a):
+    """Algorithmic MACs of one attention-core call (RCDA core = L*W*E + L*H*E + L*H*W*E +
+    L*min(H,W)*E per sample forward, backward = 2x split over the query / value / key kernels; MHA core = 2*L^2*E)."""
+    if "mha" in name:
+        B, Lq, E = a[0], a[1], a[2]
+        return B * 2 * Lq * Lq * E * (2 if "bwd" in name else 1)
+    B, Lq, H, W, E = a[:5]
+    logits, contract = Lq * (W + H) * E, Lq * H * W * E + Lq * min(H, W) * E
+    if name in ("cdetr_rcda_fwd", "cdetr_rcda_fwd_tc"):
+        return B * (logits + contract)
+    if name == "cdetr_rcda_bwd_q_tc":      # G = dO V^T, dA_r/dA_c, dq = dS K
+        return B * (contract + logits)
+    if name == "cdetr_rcda_bwd_v_tc":      # dV = sum_q A_c A_r dO
+        return B * contract
+    if name == "cdetr_rcda_bwd_k":         # dK = dS^T q
+        return B * logits
+    if name == "cdetr_rcda_bwd_kv":
+        return B * (contract + logits)
+    if name == "cdetr_rcda_bwd":
+        return B * 2 * (logits + contract)
+    return 0
+
+
+def attention_roofline(atrace, peak, ms_step):
+    """North-star figure: the encoder-decoder attention cores (RCDA fwd/bwd + decoder self-attention) against the
+    tensor-pipe roofline.  Each call timed alone with CUDA events (same instrumented step as the GEMM trace)."""
+    fam = {}
+    for name, a, e0, e1 in atrace:
+        f = fam.setdefault(name.replace("cdetr_", ""), [0, 0.0, 0.0])
+        f[0] += 1
+        f[1] += e0.elapsed_time(e1)
+        f[2] += 2.0 * attention_macs(name, a)
+    tot_ms = sum(f[1] for f in fam.values())
+    tot_fl = sum(f[2] for f in fam.values())
+    ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+    return {"bound": "tensor", "kernel": "attention cores (rcda_fwd_tc, rcda_bwd_{q,v}_tc, rcda_bwd_k, mha_fwd/bwd)",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "algorithmic_gflop_per_step": tot_fl / 1e9, "ms_per_step": tot_ms, "share_of_step": tot_ms / ms_step,
+            "per_kernel": {k: {"launches": f[0], "ms": round(f[1], 4), "tflops": round(f[2] / (f[1] * 1e-3) / 1e12, 2) if f[1] > 0 else None}
+                           for k, f in sorted(fam.items())},
+            "note": "algorithmic fp32-equivalent FLOPs; tensor-core kernels issue 3 bf16 MMAs per product (split operands)"}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
@@ -330,10 +374,11 @@ def run_ours(args):
         eng = model.engine()
         saved_streams = (eng.side_stream, eng.aux_streams)
         eng.side_stream, eng.aux_streams = None, []      # serialise: each GEMM timed alone on one stream
-        L.GEMM_TRACE = []
+        L.GEMM_TRACE, L.CALL_TRACE = [], []
         step()
         torch.cuda.synchronize()
         trace, L.GEMM_TRACE = L.GEMM_TRACE, None
+        atrace, L.CALL_TRACE = L.CALL_TRACE, None
         eng.side_stream, eng.aux_streams = saved_streams
         flops = sum(2.0 * m * n * k for (m, n, k, _, _) in trace)
         gemm_ms = sum(a.elapsed_time(b) for (_, _, _, a, b) in trace)
@@ -353,6 +398,7 @@ def run_ours(args):
                     "gemm_serial_ms_over_step_ms": gemm_ms / ms_step,
                     "timing": "CUDA events around every GEMM launch of one extra step with the side/aux streams disabled "
                               "(in the timed step weight-gradient GEMMs overlap the dgrad chain on a second stream)"}
+        roofline_attention = attention_roofline(atrace, peak, ms_step)
         cb, _ = cpu_arm(args.workload, 2, 1, batch=1) if not args.skip_cpu else ({"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": "skipped"}, 0)
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -363,7 +409,8 @@ def run_ours(args):
                            "launch": "CUDA graph replay of the whole step" if use_graph else "eager launches",
                            "l2": "per-step working set (~20 GB of activations, 50 MB image batch) >> 126 MB L2, no flush needed"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-                "launches_per_step": launches_per_step, "roofline": roofline, "cpu_baseline": cb,
+                "launches_per_step": launches_per_step, "roofline": roofline, "roofline_attention": roofline_attention,
+                "cpu_baseline": cb,
                 "loss": loss_val}
         print(json.dumps(line), flush=True)
     if world > 1:

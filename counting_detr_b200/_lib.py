@@ -78,6 +78,7 @@ COUNTER = {"launches": 0}
 _LAUNCHES = {"cdetr_exemplar_concat": 2, "cdetr_exemplar_concat_bwd": 2, "cdetr_rcda_bwd": 3, "cdetr_rcda_bwd_kv": 2, "cdetr_mha_bwd": 2,
              "cdetr_mt_grad_norm": 2, "cdetr_mt_adamw": 2}
 GEMM_TRACE = None
+CALL_TRACE = None      # when a list: (name, leading int args, start event, end event) of every attention-core call
 
 
 def gemm(a, b, M, N, K, mode=0, out_f32=None, out_split=None, bias=None, row_scale=None,
@@ -202,6 +203,13 @@ def call(name, *args):
         else:
             conv.append(int(a))
     COUNTER["launches"] += _LAUNCHES.get(name, 1)
+    if CALL_TRACE is not None and name.startswith(("cdetr_rcda", "cdetr_mha")):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_bind(name)(*conv, torch.cuda.current_stream().cuda_stream), name)
+        e1.record()
+        CALL_TRACE.append((name, tuple(conv[:6]), e0, e1))
+        return
     check(_bind(name)(*conv, torch.cuda.current_stream().cuda_stream), name)
 
 

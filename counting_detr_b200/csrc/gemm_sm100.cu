@@ -652,8 +652,10 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   ka.total_tiles = ka.tiles_m * ka.tiles_n * splits;
   // Resident-B schedule: short-K problems with many m-tiles per n-tile keep the [bn x K] weight slab in shared memory
   // and stream only A (the L2 -> SM operand traffic, the limiter of these shapes, halves).  One CTA per SM.
-  bool resident = !nt && !conv && splits == 1 && num_kb <= 4 && bn <= 128 && ka.total_tiles >= 2 * num_sms &&
-                  (uint32_t)num_kb * b_bytes + 2 * a_bytes <= smem_budget;
+  // Measured (profiles/r01_bench_c3_v11*.json): with the epilogue as the limiter of short-K tiles, one resident-B CTA
+  // per SM (8 epilogue warps) loses to two streaming CTAs (16 epilogue warps): 23.0 vs 21.6 ms of GEMM per C3 step.
+  // Off unless CDETR_GEMM_RESIDENT=1.
+  bool resident = false;
   if (const char* e = getenv("CDETR_GEMM_RESIDENT")) {
     const int f = atoi(e);
     if (f == 0) resident = false;
