@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "../../include/cdetr.h"
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -58,6 +59,14 @@ struct KernelArgs {
   // the CTA walks a contiguous run of m-tiles, so only A streams through the TMA ring (half the L2 -> SM bytes)
   int resident_b, tiles_per_cta;
   uint32_t staging_off;  // byte offset of the epilogue staging area (after the operand stages)
+  uint32_t staging_bytes;
+  // TMA epilogue: residual / mask tiles arrive by TMA loads, outputs leave by TMA stores (or TMA reduce-add), one
+  // [32 rows x 32 columns] chunk per epilogue warp at a time through per-warp swizzled staging buffers
+  int epi_tma;
+  int epi_nb;                // staging buffers per epilogue warp (2: inputs of chunk i+1 prefetched during chunk i)
+  uint32_t epi_buf_bytes;    // bytes of one staging buffer: [io 4096][mask 2048]?[second output 4096]?
+  uint32_t epi_off_mask, epi_off_out2;
+  int epi_add_kind;          // 0 none, 1 split residual, 2 fp32 residual
   EpilogueArgs ep;
 };
 
@@ -81,8 +90,10 @@ __device__ __forceinline__ TileCoord decode_tile(const KernelArgs& a, int tile) 
 }
 
 template <bool NT>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmOutF, const __grid_constant__ CUtensorMap tmOutS,
+                  const __grid_constant__ CUtensorMap tmAdd, const __grid_constant__ CUtensorMap tmMask,
                   const KernelArgs args) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-byte alignment of every tile base.
@@ -94,13 +105,14 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t stage_bytes = a_bytes + b_bytes;
   constexpr int STG_LD = 33;                             // epilogue staging: 8 warps x [32][33] floats
   float* staging = reinterpret_cast<float*>(smem + args.staging_off);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 8 * 32 * STG_LD);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + args.staging_off + args.staging_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
   uint64_t* slab_full_bar = tmem_empty_bar + 2;          // resident-B slab loaded / free to overwrite
   uint64_t* slab_empty_bar = slab_full_bar + 1;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(slab_empty_bar + 1);
+  uint64_t* epi_bar = slab_empty_bar + 1;                // [8 epilogue warps][2 staging buffers]: inputs landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(epi_bar + 16);
   const bool RB = !NT && args.resident_b != 0;
   const uint32_t slab_bytes = RB ? (uint32_t)args.num_kb * b_bytes : 0u;
   // tile walk of this CTA: strided round-robin, or a contiguous run in the resident-B schedule
@@ -116,6 +128,12 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
+  if (warp == 2 && lane == 0 && args.epi_tma) {
+    if (args.ep.out_f32 != nullptr) tma_prefetch_desc(&tmOutF);
+    if (args.ep.out_hi != nullptr) tma_prefetch_desc(&tmOutS);
+    if (args.epi_add_kind != 0) tma_prefetch_desc(&tmAdd);
+    if (args.ep.mask_hi != nullptr) tma_prefetch_desc(&tmMask);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -127,6 +145,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     mbar_init(slab_full_bar, 1);
     mbar_init(slab_empty_bar, 1);
+    for (int i = 0; i < 16; ++i) mbar_init(&epi_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -263,8 +282,212 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         umma_commit(&tmem_full_bar[ab]);  // accumulator of this tile complete
       }
     }
+  } else if (args.epi_tma) {
+    // ------------------------------ epilogue (TMA staged) ----------------------
+    // Each warp owns 32 accumulator rows (its TMEM lane quarter) and half of the tile's columns, processed in chunks
+    // of 32 columns with ONE ROW PER THREAD end to end (no transposition): tcgen05.ld.x32 -> registers; residual /
+    // ReLU-mask chunks were fetched by TMA into the warp's swizzled staging buffer (prefetched one chunk ahead);
+    // results are written back into the same buffer (16-byte st.shared, conflict-free under the TMA swizzle) and
+    // leave by one TMA store (or TMA reduce-add for split-K / accumulate) issued by lane 0.  Global memory is only
+    // touched by the TMA unit, in full 32 B sectors, with no address arithmetic or exposed load latency in the warp.
+    const EpilogueArgs& ep = args.ep;
+    const int w = warp - 2;
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = w >> 2;
+    const int cols_half = BN >> 1;      // multiple of 32 (BN % 64 == 0 on this path)
+    const int nch = cols_half >> 5;
+    const int nb = args.epi_nb;
+    uint8_t* wbuf = smem + args.staging_off + (uint32_t)(w * nb) * args.epi_buf_bytes;
+    uint64_t* in_bar = epi_bar + 2 * w;
+    const int add_kind = args.epi_add_kind;
+    const bool has_mask = ep.mask_hi != nullptr;
+    const bool has_in = add_kind != 0 || has_mask;
+    const uint32_t in_bytes = (add_kind != 0 ? 4096u : 0u) + (has_mask ? 2048u : 0u);
+    // byte offset of 16-byte chunk c of this thread's row: 64 B rows (bf16, SWIZZLE_64B) / 128 B rows (fp32, SWIZZLE_128B)
+    const uint32_t row64 = (uint32_t)lane * 64u, sw64 = (uint32_t)((lane >> 1) & 3);
+    const uint32_t row128 = (uint32_t)lane * 128u, sw128 = (uint32_t)(lane & 7);
+
+    auto chunk_valid = [&](int tile, int ch) -> bool {
+      const TileCoord tc = decode_tile(args, tile);
+      return tc.m0 + q * 32 < args.M && tc.n0 + half * cols_half + ch * 32 < args.N;
+    };
+    auto advance = [&](int& tile, int& ch) {   // next chunk of this warp that touches the output at all
+      do {
+        if (++ch == nch) { ch = 0; tile += t_step; }
+      } while (tile < t_end && !chunk_valid(tile, ch));
+    };
+    auto issue_in = [&](int tile, int ch, int b) {   // lane 0: TMA loads of one chunk's residual / mask
+      const TileCoord tc = decode_tile(args, tile);
+      const int mr = tc.m0 + q * 32, nc = tc.n0 + half * cols_half + ch * 32;
+      uint8_t* buf = wbuf + (uint32_t)b * args.epi_buf_bytes;
+      mbar_arrive_expect_tx(&in_bar[b], in_bytes);
+      if (add_kind == 1) tma_load_3d(buf, &tmAdd, &in_bar[b], nc, mr, 0);
+      else if (add_kind == 2) tma_load_2d(buf, &tmAdd, &in_bar[b], nc, mr);
+      if (has_mask) tma_load_2d(buf + args.epi_off_mask, &tmMask, &in_bar[b], nc, mr);
+    };
+
+    int ci = 0;   // chunks processed so far by this warp (buffer = ci & 1, barrier parity from ci)
+    if (has_in && nb == 2 && lane == 0) {
+      int t0 = t_begin, c0 = -1;
+      if (t0 < t_end) {
+        advance(t0, c0);
+        if (t0 < t_end) issue_in(t0, c0, 0);
+      }
+    }
+    int ti = 0;
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++ti) {
+      const TileCoord tc = decode_tile(args, tile);
+      const int n0 = tc.n0, m0 = tc.m0;
+      const int ab = ti & 1;
+      mbar_wait(&tmem_full_bar[ab], (uint32_t)(ti >> 1) & 1u);
+      tc_fence_after();
+      const int mrow = m0 + q * 32;
+      const int row_t = mrow + lane;
+      const float rs = (ep.row_scale != nullptr && row_t < args.M) ? ep.row_scale[row_t] : 1.0f;
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * args.tmem_cols;
+      for (int ch = 0; ch < nch; ++ch) {
+        const int cl = half * cols_half + ch * 32;
+        const int nbase = n0 + cl;
+        if (mrow >= args.M || nbase >= args.N) continue;   // warp-uniform, same predicate as chunk_valid
+        const int b = nb == 2 ? (ci & 1) : 0;
+        uint8_t* buf = wbuf + (uint32_t)b * args.epi_buf_bytes;
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr_row + (uint32_t)cl, r);
+        if (nb == 1) {   // single buffer: the previous chunk's store must have drained before its inputs may land
+          if (lane == 0) {
+            bulk_wait_group_read<0>();
+            if (has_in) issue_in(tile, ch, 0);
+          }
+          __syncwarp();
+        }
+        uint4 ain[8], amk[4];
+        if (has_in) {
+          mbar_wait(&in_bar[b], (uint32_t)(nb == 2 ? (ci >> 1) : ci) & 1u);
+          if (add_kind == 1) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t off = row64 + (((uint32_t)c ^ sw64) << 4);
+              ain[c] = *reinterpret_cast<const uint4*>(buf + off);
+              ain[4 + c] = *reinterpret_cast<const uint4*>(buf + 2048 + off);
+            }
+          } else if (add_kind == 2) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              ain[c] = *reinterpret_cast<const uint4*>(buf + row128 + (((uint32_t)c ^ sw128) << 4));
+          }
+          if (has_mask) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              amk[c] = *reinterpret_cast<const uint4*>(buf + args.epi_off_mask + row64 + (((uint32_t)c ^ sw64) << 4));
+          }
+        }
+        if (nb == 2) {
+          if (lane == 0) {
+            if (has_in) {
+              bulk_wait_group_read<0>();   // the store of chunk ci-1 has drained buffer b^1
+              int t1 = tile, c1 = ch;
+              advance(t1, c1);
+              if (t1 < t_end) issue_in(t1, c1, b ^ 1);
+            } else {
+              bulk_wait_group_read<1>();   // the store of chunk ci-2 has drained buffer b
+            }
+          }
+          __syncwarp();
+        }
+        tmem_ld_wait();
+        float v[32];
+        if (ep.row_scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rs;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        }
+        if (ep.bias != nullptr) {
+          if (nbase + 32 <= args.N && (reinterpret_cast<uintptr_t>(ep.bias + nbase) & 15) == 0) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(ep.bias + nbase) + c);
+              v[4 * c] += bv.x; v[4 * c + 1] += bv.y; v[4 * c + 2] += bv.z; v[4 * c + 3] += bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nbase + j < args.N) v[j] += __ldg(ep.bias + nbase + j);
+          }
+        }
+        if (add_kind == 1) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t hw[4] = {ain[c].x, ain[c].y, ain[c].z, ain[c].w};
+            const uint32_t lw[4] = {ain[4 + c].x, ain[4 + c].y, ain[4 + c].z, ain[4 + c].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[8 * c + 2 * j] += bf16_bits_to_float(hw[j] & 0xffffu) + bf16_bits_to_float(lw[j] & 0xffffu);
+              v[8 * c + 2 * j + 1] += __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
+            }
+          }
+        } else if (add_kind == 2) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            v[4 * c] += __uint_as_float(ain[c].x); v[4 * c + 1] += __uint_as_float(ain[c].y);
+            v[4 * c + 2] += __uint_as_float(ain[c].z); v[4 * c + 3] += __uint_as_float(ain[c].w);
+          }
+        }
+        if (ep.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        }
+        if (has_mask) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t mw[4] = {amk[c].x, amk[c].y, amk[c].z, amk[c].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (!(bf16_bits_to_float(mw[j] & 0xffffu) > 0.0f)) v[8 * c + 2 * j] = 0.0f;
+              if (!(__uint_as_float(mw[j] & 0xffff0000u) > 0.0f)) v[8 * c + 2 * j + 1] = 0.0f;
+            }
+          }
+        }
+        uint8_t* sdst = buf;
+        if (ep.out_f32 != nullptr) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(buf + row128 + (((uint32_t)c ^ sw128) << 4)) =
+                make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          sdst = buf + args.epi_off_out2;
+        }
+        if (ep.out_hi != nullptr) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_bf16_pair(v[8 * c + 2 * j], v[8 * c + 2 * j + 1], hw[j], lw[j]);
+            const uint32_t off = row64 + (((uint32_t)c ^ sw64) << 4);
+            *reinterpret_cast<uint4*>(sdst + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(sdst + 2048 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+        fence_proxy_async();   // generic-proxy writes above -> visible to the TMA unit
+        __syncwarp();
+        if (lane == 0) {
+          if (ep.out_f32 != nullptr) {
+            if (ep.atomic) tma_reduce_add_2d(&tmOutF, buf, nbase, mrow);
+            else tma_store_2d(&tmOutF, buf, nbase, mrow);
+          }
+          if (ep.out_hi != nullptr) tma_store_3d(&tmOutS, sdst, nbase, mrow, 0);
+          bulk_commit_group();
+        }
+        ++ci;
+      }
+      // all tcgen05.ld of this warp for this accumulator buffer are complete: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[ab]);
+    }
+    if (lane == 0) bulk_wait_group<0>();   // every store has been performed before the CTA retires
   } else {
-    // ------------------------------ epilogue ----------------------------------
+    // ------------------------------ epilogue (generic fallback) ----------------
     // Each warp owns 32 accumulator rows (its TMEM lane quarter) and half of the tile's columns.  Per
     // 32-column chunk: TMEM -> registers (one row per thread) -> per-warp shared-memory staging
     // -> re-read with 4 lanes per row so that
@@ -520,6 +743,49 @@ int make_conv_map(CUtensorMap* map, const cdetr_split_t& t, int C, int W, int H,
   return CDETR_OK;
 }
 
+// Epilogue maps: one [32 rows x 32 columns] chunk per TMA operation.  fp32 matrix: 2-D {N, M}, 128 B inner box,
+// SWIZZLE_128B.  split matrix: 3-D {N, M, plane} bf16, 64 B inner box, SWIZZLE_64B (planes = 2: hi+lo in one box;
+// planes = 1 as a 2-D map over plane 0: the ReLU mask).
+int make_epi_map_f32(CUtensorMap* map, const float* base, int64_t ld, int N, int M) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    cdetr_set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return CDETR_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    cdetr_set_error("cuTensorMapEncodeTiled (epilogue f32) failed (%d) N=%d M=%d ld=%lld", (int)r, N, M, (long long)ld);
+    return CDETR_ERR_CUDA;
+  }
+  return CDETR_OK;
+}
+int make_epi_map_bf16(CUtensorMap* map, const void* base, int64_t ld, int64_t plane, int N, int M, int planes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    cdetr_set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return CDETR_ERR_CUDA;
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)N, (cuuint64_t)M, 2};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
+  cuuint32_t box[3] = {32, 32, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, planes == 2 ? 3 : 2, const_cast<void*>(base), gdim, gstride,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    cdetr_set_error("cuTensorMapEncodeTiled (epilogue bf16) failed (%d) N=%d M=%d ld=%lld plane=%lld", (int)r, N, M,
+                    (long long)ld, (long long)plane);
+    return CDETR_ERR_CUDA;
+  }
+  return CDETR_OK;
+}
+
 }  // namespace
 
 extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
@@ -623,17 +889,43 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   const uint32_t a_bytes = 2u * BM * 128u;
   const uint32_t b_bytes = nt ? (uint32_t)((bn + 63) / 64) * 16384u : 2u * (uint32_t)bn * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  const uint32_t staging_bytes = 8u * 32u * 33u * 4u;
-  const uint32_t tail_bytes = staging_bytes + (2 * MAX_STAGES + 6) * 8 + 16;
-  const uint32_t smem_budget = 227u * 1024u - 1024u - tail_bytes;
-  // Two accumulator buffers per CTA: tiles up to 128 wide leave TMEM (512 columns) for two CTAs per SM, and two
-  // co-resident CTAs (possibly of different kernels: the weight-gradient stream) hide each other's TMA latency;
-  // 256-wide tiles own the SM and get a deeper pipeline instead.
-  int ctas_per_sm = (2 * cols <= 256) ? 2 : 1;
+  const uint32_t tail_bytes = (2 * MAX_STAGES + 6 + 16) * 8 + 16;
+  const uint32_t smem_max = 227u * 1024u - 1024u - tail_bytes;   // dynamic smem minus alignment slack and barriers
+
+  // ---- epilogue flavour.  TMA-staged (see the kernel) whenever every epilogue tensor is TMA-addressable; the generic
+  // per-thread epilogue remains for tiny / unaligned outputs (heads with N = 2, 4) and block_n < 64.
+  auto tma_ok_f32 = [](const float* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ld % 4 == 0; };
+  auto tma_ok_split = [](const cdetr_split_t& t) {
+    return (reinterpret_cast<uintptr_t>(t.base) & 15) == 0 && t.ld % 8 == 0 && t.plane % 8 == 0 && t.plane > 0;
+  };
+  const bool has_of = g->out_f32 != nullptr, has_os = g->out_split.base != nullptr;
+  const bool has_as = g->add_split.base != nullptr, has_af = g->add_f32 != nullptr, has_mk = g->mask.base != nullptr;
+  bool tma_epi = bn % 64 == 0 && !(has_as && has_af) && (!has_of || tma_ok_f32(g->out_f32, g->ld_out_f32)) &&
+                 (!has_os || tma_ok_split(g->out_split)) && (!has_as || tma_ok_split(g->add_split)) &&
+                 (!has_af || tma_ok_f32(g->add_f32, g->ld_add_f32)) &&
+                 (!has_mk || ((reinterpret_cast<uintptr_t>(g->mask.base) & 15) == 0 && g->mask.ld % 8 == 0));
+  if (const char* e = getenv("CDETR_GEMM_TMA_EPI"))
+    if (atoi(e) == 0) tma_epi = false;
+  const uint32_t old_staging = 8u * 32u * 33u * 4u;
+  uint32_t epi_buf = 4096u + (has_mk ? 2048u : 0u) + ((has_of && has_os) ? 4096u : 0u);
+  int epi_nb = 2;
+  uint32_t staging_bytes = tma_epi ? 8u * (uint32_t)epi_nb * epi_buf : old_staging;
+  if (tma_epi && (smem_max - staging_bytes) / stage_bytes < 2) {   // keep two operand stages: single staging buffer
+    epi_nb = 1;
+    staging_bytes = 8u * epi_buf;
+  }
+  if (tma_epi && smem_max < staging_bytes + stage_bytes) {
+    tma_epi = false;
+    staging_bytes = old_staging;
+  }
+  const uint32_t smem_budget = smem_max - staging_bytes;
+  // Two accumulator buffers per CTA.  The generic epilogue is latency-bound, so narrow tiles run two co-resident CTAs
+  // per SM; the TMA epilogue keeps up with the tensor pipe from one persistent CTA per SM with a deeper TMA ring.
+  int ctas_per_sm = (!tma_epi && 2 * cols <= 256) ? 2 : 1;
   // long K loops on narrow outputs (A streamed once, light epilogue): one CTA with a deep TMA pipeline beats two
   // single-stage CTAs (sweep: 10-15 % on N<=256, K>=512)
   if (!nt && g->N <= 256 && kb_per_split >= 8) ctas_per_sm = 1;
-  const uint32_t per_cta = ctas_per_sm == 2 ? (113u * 1024u - tail_bytes) : smem_budget;
+  const uint32_t per_cta = ctas_per_sm == 2 ? (113u * 1024u - tail_bytes - staging_bytes) : smem_budget;
   int stages = (int)(per_cta / stage_bytes);
   if (stages < 1) { stages = 1; ctas_per_sm = 1; }
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -645,20 +937,19 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
     const int f = atoi(e);
     if (f == 1 || (f == 2 && 2 * cols <= 256)) ctas_per_sm = f;
   }
-  if ((uint32_t)stages * stage_bytes + tail_bytes + 1024 > 113u * 1024u) ctas_per_sm = 1;
+  if ((uint32_t)stages * stage_bytes + staging_bytes + tail_bytes + 1024 > 113u * 1024u) ctas_per_sm = 1;
   CDETR_CHECK_ARG((uint32_t)stages * stage_bytes <= smem_budget, "gemm: tile does not fit shared memory");
   ka.tiles_m = cdiv(g->M, BM);
   ka.tiles_n = cdiv(g->N, bn);
   ka.total_tiles = ka.tiles_m * ka.tiles_n * splits;
   // Resident-B schedule: short-K problems with many m-tiles per n-tile keep the [bn x K] weight slab in shared memory
-  // and stream only A (the L2 -> SM operand traffic, the limiter of these shapes, halves).  One CTA per SM.
-  // Measured (profiles/r01_bench_c3_v11*.json): with the epilogue as the limiter of short-K tiles, one resident-B CTA
-  // per SM (8 epilogue warps) loses to two streaming CTAs (16 epilogue warps): 23.0 vs 21.6 ms of GEMM per C3 step.
-  // Off unless CDETR_GEMM_RESIDENT=1.
+  // and stream only A (the L2 -> SM operand traffic halves).  One CTA per SM.
+  // Measured (profiles/r01_bench_c3_v11*.json): with the generic epilogue as the limiter of short-K tiles, one
+  // resident-B CTA per SM (8 epilogue warps) lost to two streaming CTAs (16 epilogue warps): 23.0 vs 21.6 ms of GEMM
+  // per C3 step.  Off unless CDETR_GEMM_RESIDENT=1.
   bool resident = false;
   if (const char* e = getenv("CDETR_GEMM_RESIDENT")) {
     const int f = atoi(e);
-    if (f == 0) resident = false;
     if (f == 1) resident = !nt && !conv && splits == 1 && (uint32_t)num_kb * b_bytes + 2 * a_bytes <= smem_budget;
   }
   ka.resident_b = 0;
@@ -681,7 +972,27 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   }
   ka.stages = stages;
   ka.staging_off = (uint32_t)operand_bytes;
-  const size_t smem_bytes = operand_bytes + tail_bytes + 1024;
+  ka.staging_bytes = staging_bytes;
+  ka.epi_tma = tma_epi ? 1 : 0;
+  ka.epi_nb = epi_nb;
+  ka.epi_buf_bytes = epi_buf;
+  ka.epi_off_mask = 4096u;
+  ka.epi_off_out2 = 4096u + (has_mk ? 2048u : 0u);
+  ka.epi_add_kind = has_as ? 1 : (has_af ? 2 : 0);
+  const size_t smem_bytes = operand_bytes + staging_bytes + tail_bytes + 1024;
+
+  CUtensorMap tmOutF, tmOutS, tmAdd, tmMask;
+  memset(&tmOutF, 0, sizeof(tmOutF)); memset(&tmOutS, 0, sizeof(tmOutS));
+  memset(&tmAdd, 0, sizeof(tmAdd)); memset(&tmMask, 0, sizeof(tmMask));
+  if (tma_epi) {
+    if (has_of && (rc = make_epi_map_f32(&tmOutF, g->out_f32, g->ld_out_f32, g->N, g->M)) != 0) return rc;
+    if (has_os && (rc = make_epi_map_bf16(&tmOutS, g->out_split.base, g->out_split.ld, g->out_split.plane, g->N, g->M, 2)) != 0)
+      return rc;
+    if (has_as && (rc = make_epi_map_bf16(&tmAdd, g->add_split.base, g->add_split.ld, g->add_split.plane, g->N, g->M, 2)) != 0)
+      return rc;
+    if (has_af && (rc = make_epi_map_f32(&tmAdd, g->add_f32, g->ld_add_f32, g->N, g->M)) != 0) return rc;
+    if (has_mk && (rc = make_epi_map_bf16(&tmMask, g->mask.base, g->mask.ld, 8, g->N, g->M, 1)) != 0) return rc;
+  }
 
   EpilogueArgs& ep = ka.ep;
   ep.row_scale = g->row_scale;
@@ -722,7 +1033,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
                                           227 * 1024));
     configured[nt] = 227 * 1024;
   }
-  kern<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, ka);
+  kern<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, tmOutF, tmOutS, tmAdd, tmMask, ka);
   CDETR_CHECK_LAUNCH();
   return CDETR_OK;
 }

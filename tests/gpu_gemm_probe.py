@@ -104,6 +104,32 @@ L.gemm(L.to_split(A), L.to_split(B), M, N, K, out_split=outs, bias=bias, add_spl
 torch.cuda.synchronize()
 report("resident-B auto, bias+res+mask split", L.from_split(outs), ref)
 
+# ---- TMA-staged epilogue on ragged shapes (explicit block_n >= 64 keeps it on the TMA path): column / row tails are
+# clipped by the TMA unit, chunks entirely outside the matrix are skipped
+run_tn(300, 200, 200, block_n=128)
+run_tn(1000, 300, 512, block_n=64)
+run_tn(700, 328, 1104, block_n=256)
+for (M, N, K, bn) in [(4800, 264, 256, 128), (333, 72, 128, 64), (20000, 512, 64, 256)]:
+    A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev)
+    bias = torch.randn(N, device=dev); res = torch.randn(M, N, device=dev); mk = torch.randn(M, N, device=dev)
+    addf = torch.randn(M, N, device=dev)
+    acc = A.double() @ B.double().t()
+    outs = torch.zeros(2, M, N, device=dev, dtype=torch.bfloat16); out = torch.full((M, N), float("nan"), device=dev)
+    L.gemm(L.to_split(A), L.to_split(B), M, N, K, out_split=outs, out_f32=out, bias=bias, add_split=L.to_split(res),
+           mask=L.to_split(torch.relu(mk)), block_n=bn)
+    torch.cuda.synchronize()
+    ref = (acc + bias.double() + L.from_split(L.to_split(res)).double()) * (mk > 0).double()
+    report(f"tma-epi M={M} N={N} K={K} bn={bn} bias+res+mask -> split", L.from_split(outs), ref)
+    report(f"tma-epi M={M} N={N} K={K} bn={bn} bias+res+mask -> f32", out, ref)
+    out = torch.full((M, N), float("nan"), device=dev)
+    L.gemm(L.to_split(A), L.to_split(B), M, N, K, out_f32=out, add_f32=addf, relu=True, block_n=bn)
+    torch.cuda.synchronize()
+    report(f"tma-epi M={M} N={N} K={K} bn={bn} add_f32+relu -> f32", out, torch.relu(acc + addf.double()))
+    out = addf.clone()
+    L.gemm(L.to_split(A), L.to_split(B), M, N, K, out_f32=out, accumulate=True, block_n=bn)
+    torch.cuda.synchronize()
+    report(f"tma-epi M={M} N={N} K={K} bn={bn} accumulate (TMA reduce-add)", out, acc + addf.double())
+
 # ---- implicit 3x3 convolution (TMA shifted windows, no im2col matrix) vs torch conv2d in fp64
 import torch.nn.functional as F
 
@@ -147,6 +173,34 @@ run_conv(2, 32, 32, 256, 256, 2)
 run_conv(1, 64, 64, 128, 128, 1)
 run_conv(1, 128, 128, 64, 64, 1)
 run_conv(3, 32, 32, 512, 512, 2)
+
+# timing of the epilogue-bound shapes of the C3 step (split output unless noted)
+def timeit(fn, reps=20):
+    for _ in range(3):
+        fn()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+for (M, N, K, flav) in [(16384, 1024, 256, "bias+relu"), (16384, 1024, 256, "res+mask"), (16384, 256, 256, "f32"),
+                        (4800, 256, 256, "f32"), (262144, 256, 64, "res+relu"), (65536, 512, 128, "res+relu"),
+                        (16384, 2048, 512, "res+relu"), (16384, 256, 1024, "f32+addf32"), (65536, 128, 512, "mask")]:
+    A = L.to_split(torch.randn(M, K, device=dev)); B = L.to_split(torch.randn(N, K, device=dev))
+    outs = torch.empty(2, M, N, device=dev, dtype=torch.bfloat16); outf = torch.empty(M, N, device=dev)
+    res = L.to_split(torch.randn(M, N, device=dev)); bias = torch.randn(N, device=dev)
+    kw = dict(out_split=outs)
+    if flav == "bias+relu": kw.update(bias=bias, relu=True)
+    elif flav == "res+mask": kw.update(add_split=res, mask=res)
+    elif flav == "res+relu": kw.update(add_split=res, relu=True, bias=bias)
+    elif flav == "mask": kw.update(mask=res)
+    elif flav == "f32": kw = dict(out_f32=outf, bias=bias)
+    elif flav == "f32+addf32": kw = dict(out_f32=outf, add_f32=outf)
+    us = timeit(lambda: L.gemm(A, B, M, N, K, **kw))
+    print(f"time TN M={M} N={N} K={K} {flav}: {us:.1f} us  {2*M*N*K/us/1e6:.1f} TFLOP/s(fp32-equiv)", flush=True)
 
 # timing (rough): big TN GEMM
 for (M, N, K, bn) in [(16384, 2048, 512, 128), (16384, 2048, 512, 256), (16384, 512, 4608, 128), (16384, 512, 4608, 256), (65536, 256, 256, 128), (16384, 1024, 256, 256)]:
