@@ -213,4 +213,4 @@ def call(name, *args):
     check(_bind(name)(*conv, torch.cuda.current_stream().cuda_stream), name)
 
 
-EXPORTED = ["cdetr_version", "cdetr_last_error", "cdetr_gemm"] + list(_SIGS)
+EXPORTED = ["cdetr_version", "cdetr_last_error", "cdetr_gemm", "cdetr_gemm_debug_timeline"] + list(_SIGS)

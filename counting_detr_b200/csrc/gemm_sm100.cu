@@ -67,8 +67,19 @@ struct KernelArgs {
   uint32_t epi_buf_bytes;    // bytes of one staging buffer: [io 4096][mask 2048]?[second output 4096]?
   uint32_t epi_off_mask, epi_off_out2;
   int epi_add_kind;          // 0 none, 1 split residual, 2 fp32 residual
+  long long* dbg;            // debug timeline of CTA 0 (cdetr_gemm_debug_timeline), normally NULL
   EpilogueArgs ep;
 };
+
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define DBG_T(i)                                                       \
+  do {                                                                 \
+    if (args.dbg != nullptr && blockIdx.x == 0) args.dbg[i] = gtimer(); \
+  } while (0)
 
 struct TileCoord {
   int m0, n0, kb_begin, kb_end;
@@ -123,6 +134,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = args.stages;
+  if (threadIdx.x == 0) DBG_T(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -156,6 +168,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  if (threadIdx.x == 0) DBG_T(1);
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -251,6 +264,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t ph = (uint32_t)(it / stages) & 1u;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (it == 0) DBG_T(2);
           const uint32_t a_base = smem_u32(RB ? smem + slab_bytes + (size_t)s * a_bytes : smem + (size_t)s * stage_bytes);
           const uint32_t b_base = RB ? smem_u32(smem + (size_t)kb * b_bytes) : a_base + a_bytes;
 #pragma unroll
@@ -280,6 +294,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (RB && (tile + 1 >= t_end || decode_tile(args, tile + 1).n0 != tc.n0))
           umma_commit(slab_empty_bar);    // last MMA reading this weight slab: the producer may overwrite it
         umma_commit(&tmem_full_bar[ab]);  // accumulator of this tile complete
+        if (ti == 0) DBG_T(3);
       }
     }
   } else if (args.epi_tma) {
@@ -341,6 +356,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int ab = ti & 1;
       mbar_wait(&tmem_full_bar[ab], (uint32_t)(ti >> 1) & 1u);
       tc_fence_after();
+      if (ti == 0 && warp == 2 && lane == 0) DBG_T(4);
       const int mrow = m0 + q * 32;
       const int row_t = mrow + lane;
       const float rs = (ep.row_scale != nullptr && row_t < args.M) ? ep.row_scale[row_t] : 1.0f;
@@ -484,6 +500,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[ab]);
+      if (ti == 0 && warp == 2 && lane == 0) DBG_T(5);
     }
     if (lane == 0) bulk_wait_group<0>();   // every store has been performed before the CTA retires
   } else {
@@ -511,6 +528,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ab = ti & 1;
     mbar_wait(&tmem_full_bar[ab], (uint32_t)(ti >> 1) & 1u);
     tc_fence_after();
+    if (ti == 0 && warp == 2 && lane == 0) DBG_T(4);
     const int row_t = m0 + q * 32 + lane;  // row held by this thread in the TMEM phase
     const float rs = (ep.row_scale != nullptr && row_t < args.M) ? ep.row_scale[row_t] : 1.0f;
     const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * args.tmem_cols;
@@ -658,14 +676,17 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty_bar[ab]);
+    if (ti == 0 && warp == 2 && lane == 0) DBG_T(5);
     }  // tile loop
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) DBG_T(6);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * args.tmem_cols);
+    if (lane == 0) DBG_T(7);
   }
 }
 
@@ -786,7 +807,20 @@ int make_epi_map_bf16(CUtensorMap* map, const void* base, int64_t ld, int64_t pl
   return CDETR_OK;
 }
 
+long long* g_dbg_buf = nullptr;   // debug only: 8 timestamps (ns, %globaltimer) per launch, CTA 0
+int g_dbg_cap = 0, g_dbg_next = 0;
+
 }  // namespace
+
+// Debug hook (not part of the reference-facing API): subsequent cdetr_gemm launches record a CTA-0 timeline
+// {entry, setup done, first operands landed, MMAs of tile 0 issued, accumulator seen by the epilogue, epilogue of
+// tile 0 done, all warps done, TMEM released} into buf[8 * launch]; pass NULL to stop.
+extern "C" int cdetr_gemm_debug_timeline(long long* buf, int capacity_launches) {
+  g_dbg_buf = buf;
+  g_dbg_cap = buf != nullptr ? capacity_launches : 0;
+  g_dbg_next = 0;
+  return CDETR_OK;
+}
 
 extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -979,6 +1013,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   ka.epi_off_mask = 4096u;
   ka.epi_off_out2 = 4096u + (has_mk ? 2048u : 0u);
   ka.epi_add_kind = has_as ? 1 : (has_af ? 2 : 0);
+  ka.dbg = (g_dbg_buf != nullptr && g_dbg_next < g_dbg_cap) ? g_dbg_buf + 8 * (g_dbg_next++) : nullptr;
   const size_t smem_bytes = operand_bytes + staging_bytes + tail_bytes + 1024;
 
   CUtensorMap tmOutF, tmOutS, tmAdd, tmMask;

@@ -82,6 +82,9 @@ typedef struct {
 } cdetr_gemm_t;
 
 int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream);
+/* Debug hook (no reference counterpart): the following cdetr_gemm launches record 8 device timestamps of CTA 0 each
+ * (ns, %globaltimer) into buf[8 * launch]; NULL stops recording. */
+int cdetr_gemm_debug_timeline(long long* buf, int capacity_launches);
 
 /* ---------------------------------------------------------------------------------------------
  * Backbone layout kernels (split-bf16 NHWC).  Replace, together with cdetr_gemm:
