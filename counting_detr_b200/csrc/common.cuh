@@ -197,6 +197,13 @@ __device__ __forceinline__ void bulk_wait_group() {        // <= N groups not ye
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ------------------------------- programmatic dependent launch -------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its stream predecessor
+// is still running; it must execute pdl_wait() before touching anything the predecessor wrote.  pdl_trigger() lets
+// the stream successor (if launched with the attribute) be scheduled early; without it the trigger is implicit at exit.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------- tcgen05 -----------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(

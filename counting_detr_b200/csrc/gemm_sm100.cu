@@ -135,6 +135,9 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int stages = args.stages;
   if (threadIdx.x == 0) DBG_T(0);
+  // PDL: let the next kernel of the stream be scheduled as SMs free up (it waits for this grid to complete before
+  // reading anything); our own set-up below (barriers, TMEM, descriptor prefetch) overlaps the predecessor's tail.
+  pdl_trigger();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -168,6 +171,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();   // everything the stream predecessor wrote (operands, residuals, accumulation targets) is now visible
   if (threadIdx.x == 0) DBG_T(1);
 
   if (warp == 0) {
@@ -953,25 +957,19 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
     staging_bytes = old_staging;
   }
   const uint32_t smem_budget = smem_max - staging_bytes;
-  // Two accumulator buffers per CTA.  The generic epilogue is latency-bound, so narrow tiles run two co-resident CTAs
-  // per SM; the TMA epilogue keeps up with the tensor pipe from one persistent CTA per SM with a deeper TMA ring.
-  int ctas_per_sm = (!tma_epi && 2 * cols <= 256) ? 2 : 1;
-  // long K loops on narrow outputs (A streamed once, light epilogue): one CTA with a deep TMA pipeline beats two
-  // single-stage CTAs (sweep: 10-15 % on N<=256, K>=512)
-  if (!nt && g->N <= 256 && kb_per_split >= 8) ctas_per_sm = 1;
-  const uint32_t per_cta = ctas_per_sm == 2 ? (113u * 1024u - tail_bytes - staging_bytes) : smem_budget;
-  int stages = (int)(per_cta / stage_bytes);
-  if (stages < 1) { stages = 1; ctas_per_sm = 1; }
+  // Two accumulator buffers per CTA (the epilogue of tile i overlaps the main loop of tile i+1).  One persistent CTA
+  // per SM: the kernel's register footprint (168 x 320 threads) does not leave room for a second one, so all of the
+  // shared memory goes to the TMA ring (a single-stage ring serialises the k-blocks on the TMA round trip:
+  // tools/gemm_floor.py measured 0.9 us per k-block).
+  int ctas_per_sm = 1;
+  int stages = (int)(smem_budget / stage_bytes);
+  if (stages < 1) stages = 1;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (const char* e = getenv("CDETR_GEMM_STAGES")) {  // tuning hooks (tools/gemm_sweep.py)
+  if (stages < 2 && smem_budget >= 2 * stage_bytes) stages = 2;
+  if (const char* e = getenv("CDETR_GEMM_STAGES")) {  // tuning hook (tools/gemm_sweep.py)
     const int f = atoi(e);
     if (f >= 1 && f <= MAX_STAGES && (uint32_t)f * stage_bytes <= smem_budget) stages = f;
   }
-  if (const char* e = getenv("CDETR_GEMM_CTAS")) {
-    const int f = atoi(e);
-    if (f == 1 || (f == 2 && 2 * cols <= 256)) ctas_per_sm = f;
-  }
-  if ((uint32_t)stages * stage_bytes + staging_bytes + tail_bytes + 1024 > 113u * 1024u) ctas_per_sm = 1;
   CDETR_CHECK_ARG((uint32_t)stages * stage_bytes <= smem_budget, "gemm: tile does not fit shared memory");
   ka.tiles_m = cdiv(g->M, BM);
   ka.tiles_n = cdiv(g->N, bn);
@@ -1068,7 +1066,22 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
                                           227 * 1024));
     configured[nt] = 227 * 1024;
   }
-  kern<<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, tmOutF, tmOutS, tmAdd, tmMask, ka);
-  CDETR_CHECK_LAUNCH();
+  static int use_pdl = -1;
+  if (use_pdl < 0) {
+    const char* e = getenv("CDETR_PDL");
+    use_pdl = (e != nullptr && atoi(e) != 0) ? 1 : 0;   // opt-in: measured +0.6 ms on the C3 step (early CTAs of the successor crowd the side streams)
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  CDETR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOutF, tmOutS, tmAdd, tmMask, ka));
   return CDETR_OK;
 }

@@ -531,9 +531,10 @@ struct TcBwdVArgs {
   __nv_bfloat16 *dv_hi, *dv_lo;
   int64_t ld_g;
   uint32_t idesc;
+  int tiles_per_cta;   // key-position tiles (of 128) per CTA: blockIdx.z selects the slice of positions
 };
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(320, 2)
 rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -551,7 +552,9 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.x, b = blockIdx.y;
   const int HW = a.H * a.W;
-  const int ntile = (HW + 127) / 128;
+  // positions are split across gridDim.z CTAs (each rebuilds only its own rows of P; dO blocks are re-read from L2)
+  const int mt_begin = blockIdx.z * a.tiles_per_cta;
+  const int mt_end = min((HW + 127) / 128, mt_begin + a.tiles_per_cta);
   const int nkb = (a.L + VK - 1) / VK;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmD);
@@ -590,12 +593,12 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
         const int s = kb & 1;
         mbar_wait(&d_full[s], (uint32_t)(kb >> 1) & 1u);
         const uint32_t d_base = smem_u32(Ds) + (uint32_t)s * 2u * DO_PLANE_BYTES;
-        for (int mt = 0; mt < ntile; ++mt, ++u) {
+        for (int mt = mt_begin; mt < mt_end; ++mt, ++u) {
           const int pb = u & 1;
           mbar_wait(&p_full[pb], (uint32_t)(u >> 1) & 1u);
           tc_fence_after();
           const uint32_t p_base = smem_u32(Ps) + (uint32_t)pb * 2u * P_TILE_BYTES;
-          const uint32_t d = tmem_base + (uint32_t)mt * 32u;
+          const uint32_t d = tmem_base + (uint32_t)(mt - mt_begin) * 32u;
 #pragma unroll
           for (int ks = 0; ks < VK / 16; ++ks) {
             const uint64_t a_hi = make_smem_desc(p_base + ks * 32, 16, 1024, 2);                 // K-major SW128
@@ -629,7 +632,7 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
         acs[mo] = (qok && k < a.H) ? __ldg(a.ac + (bh * a.H + k) * a.L + q0 + qq) : 0.0f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int mt = 0; mt < ntile; ++mt, ++u) {
+      for (int mt = mt_begin; mt < mt_end; ++mt, ++u) {
         const int pb = u & 1;
         if (u >= 2) mbar_wait(&p_empty[pb], (uint32_t)((u >> 1) - 1) & 1u);
         const int m = mt * 128 + ml;
@@ -663,9 +666,9 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
     tc_fence_after();
     const int quarter = warp & 3;
     const int grp = (warp - 2) >> 2;
-    for (int mt = grp; mt < ntile; mt += 2) {
+    for (int mt = mt_begin + grp; mt < mt_end; mt += 2) {
       uint32_t t[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)mt * 32u, t);
+      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt - mt_begin) * 32u, t);
       tmem_ld_wait();
       const int m = mt * 128 + quarter * 32 + lane;
       if (m < HW) {
@@ -821,7 +824,19 @@ extern "C" int cdetr_rcda_bwd_v_tc(int B, int L, int H, int W, int E, int nh, co
     CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_v_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     once = true;
   }
-  rcda_bwd_v_tc_kernel<<<dim3(nh, B), 320, smem, reinterpret_cast<cudaStream_t>(s)>>>(tm, a);
+  // split the key positions over enough CTAs to fill the machine at two CTAs per SM (one wave)
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    CDETR_CHECK_CUDA(cudaGetDevice(&dev));
+    CDETR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int ntile = (H * W + 127) / 128;
+  int nsplit = 1;
+  while (nsplit * 2 <= ntile && nh * B * nsplit * 2 <= 2 * num_sms) nsplit *= 2;
+  a.tiles_per_cta = (ntile + nsplit - 1) / nsplit;
+  nsplit = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
+  rcda_bwd_v_tc_kernel<<<dim3(nh, B, nsplit), 320, smem, reinterpret_cast<cudaStream_t>(s)>>>(tm, a);
   CDETR_CHECK_LAUNCH();
   return 0;
 }

@@ -525,31 +525,43 @@ class Engine:
         dsr = self.buf(q + ".dsr", (B, self.nh, W, Lq)); dsc = self.buf(q + ".dsc", (B, self.nh, H, Lq))
         dqr = self.sbuf(q + ".dqr", M, E); dqc = self.sbuf(q + ".dqc", M, E)
         dkr = self.sbuf(q + ".dkr", B * W, E); dkc = self.sbuf(q + ".dkc", B * H, E); dv = self.sbuf(q + ".dv", N, E)
-        if t["v_s"] is not None:     # tcgen05 query-side kernel + key/value-side kernels
-            L.call("cdetr_rcda_bwd_q_tc", B, Lq, H, W, E, self.nh, t["kr"], t["kc"], t["v_s"], t["ar"], t["ac"], dO,
-                   dsr, dsc, dqr, dqc)
-            L.call("cdetr_rcda_bwd_v_tc", B, Lq, H, W, E, self.nh, t["ar"], t["ac"], dO_s, dv)
-            L.call("cdetr_rcda_bwd_k", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], dsr, dsc, dkr, dkc)
-        else:
-            L.call("cdetr_rcda_bwd", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], t["kr"], t["kc"], t["v"], t["ar"],
-                   t["ac"], dO, dsr, dsc, dqr, dqc, dkr, dkc, dv)
         lin = self.lins[lin_in]
-        lin.wgrad(dqr, t["qr_in"], M, rows=(0, E))
-        lin.wgrad(dqc, t["qc_in"], M, rows=(E, 2 * E))
-        lin.wgrad(dkr, t["kr_in"], B * W, rows=(2 * E, 3 * E))
-        lin.wgrad(dkc, t["kc_in"], B * H, rows=(3 * E, 4 * E))
-        lin.wgrad(dv, t["v_in"], N, rows=(4 * E, 5 * E))
         g_qr = self.buf(q + ".g_qr", (M, E)); g_qc = self.buf(q + ".g_qc", (M, E))
         g_kr = self.buf(q + ".g_kr", (B * W, E)); g_kc = self.buf(q + ".g_kc", (B * H, E))
         g_v = self.buf(q + ".g_v", (N, E))
 
-        def small():
+        def v_dgrad():
+            lin.wgrad(dv, t["v_in"], N, rows=(4 * E, 5 * E))
+            lin.dgrad(dv, N, rows=(4 * E, 5 * E), out_f32=g_v, add_f32=dv_add)
+
+        def qk_dgrads():
+            lin.wgrad(dqr, t["qr_in"], M, rows=(0, E))
+            lin.wgrad(dqc, t["qc_in"], M, rows=(E, 2 * E))
+            lin.wgrad(dkr, t["kr_in"], B * W, rows=(2 * E, 3 * E))
+            lin.wgrad(dkc, t["kc_in"], B * H, rows=(3 * E, 4 * E))
+            lin.dgrad(dqr, M, rows=(0, E), out_f32=g_qr)
+            lin.dgrad(dqc, M, rows=(E, 2 * E), out_f32=g_qc)
             lin.dgrad(dkr, B * W, rows=(2 * E, 3 * E), out_f32=g_kr)
             lin.dgrad(dkc, B * H, rows=(3 * E, 4 * E), out_f32=g_kc)
-            lin.dgrad(dqc, M, rows=(E, 2 * E), out_f32=g_qc)
 
-        self.fork_join([lambda: lin.dgrad(dqr, M, rows=(0, E), out_f32=g_qr), small,
-                        lambda: lin.dgrad(dv, N, rows=(4 * E, 5 * E), out_f32=g_v, add_f32=dv_add)])
+        if t["v_s"] is not None:
+            # tcgen05 kernels.  The value side (dV, then the v-projection dgrad) only needs dO and the saved maps, so
+            # it runs as a parallel branch beside the query side -> key side chain (dS maps feed cdetr_rcda_bwd_k).
+            def query_key_side():
+                L.call("cdetr_rcda_bwd_q_tc", B, Lq, H, W, E, self.nh, t["kr"], t["kc"], t["v_s"], t["ar"], t["ac"], dO,
+                       dsr, dsc, dqr, dqc)
+                L.call("cdetr_rcda_bwd_k", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], dsr, dsc, dkr, dkc)
+                qk_dgrads()
+
+            def value_side():
+                L.call("cdetr_rcda_bwd_v_tc", B, Lq, H, W, E, self.nh, t["ar"], t["ac"], dO_s, dv)
+                v_dgrad()
+
+            self.fork_join([query_key_side, value_side])
+        else:
+            L.call("cdetr_rcda_bwd", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], t["kr"], t["kc"], t["v"], t["ar"],
+                   t["ac"], dO, dsr, dsc, dqr, dqc, dkr, dkc, dv)
+            self.fork_join([qk_dgrads, v_dgrad])
         return g_qr, g_qc, g_kr, g_kc, g_v
 
     # ------------------------------------------------------------------ forward
