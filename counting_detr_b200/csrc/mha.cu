@@ -5,26 +5,13 @@
 // Reference: A2/models/transformer.py:366-372 (decoder self-attention), torch F.multi_head_attention_forward.
 #include "common.cuh"
 #include "../../include/cdetr.h"
+#include "mha_args.cuh"
+#include <stdlib.h>
 
 namespace {
 constexpr int HD = 32;
 constexpr int TK = 128;  // keys / queries per shared-memory tile
 
-struct MhaArgs {
-  int B, L, E, nh;
-  const float* q;  // [B,L,ldq] (projected, bias added, unscaled); q/k/v may be column slices of one buffer
-  const float* k;
-  const float* v;
-  int64_t ldq;     // row pitch of q/k/v in floats
-  __nv_bfloat16 *o_hi, *o_lo;  // [B,L,E] split
-  int64_t ld_o;
-  float* lse;      // [B,nh,L]
-  // backward
-  const float* d_o;  // [B,L,E]
-  float* dsum;       // [B,nh,L]  D_i = dO_i . O_i
-  __nv_bfloat16 *dq_hi, *dq_lo, *dk_hi, *dk_lo, *dv_hi, *dv_lo;  // split, row pitch ld_g
-  int64_t ld_g;
-};
 
 __device__ __forceinline__ void load32(const float* p, float* v) {
 #pragma unroll
@@ -244,6 +231,16 @@ __global__ void __launch_bounds__(QPB * SPLIT) mha_bwd_kv_kernel(const MhaArgs a
 
 }  // namespace
 
+// tensor-core path (mha_tc.cu) whenever one head fits in shared memory; CDETR_MHA_LEGACY=1 forces the CUDA-core kernels
+static bool use_tc(int L) {
+  static int legacy = -1;
+  if (legacy < 0) {
+    const char* e = getenv("CDETR_MHA_LEGACY");
+    legacy = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }
+  return legacy == 0 && mha_tc_fits(L) != 0;
+}
+
 extern "C" int cdetr_mha_fwd(int B, int L, int E, int nh, const float* q, const float* k, const float* v,
                              int64_t ldq, cdetr_split_t o, float* lse, cdetr_stream_t s) {
   CDETR_CHECK_ARG(E == nh * HD && q && k && v && o.base && lse && ldq % 4 == 0, "mha_fwd: bad args");
@@ -251,6 +248,7 @@ extern "C" int cdetr_mha_fwd(int B, int L, int E, int nh, const float* q, const 
   a.B = B; a.L = L; a.E = E; a.nh = nh; a.q = q; a.k = k; a.v = v; a.ldq = ldq;
   a.o_hi = reinterpret_cast<__nv_bfloat16*>(o.base); a.o_lo = a.o_hi + o.plane; a.ld_o = o.ld;
   a.lse = lse;
+  if (use_tc(L)) return mha_fwd_tc_launch(a, reinterpret_cast<cudaStream_t>(s));
   mha_fwd_kernel<<<dim3(cdiv(L, QPB), nh, B), QPB * SPLIT, 0, reinterpret_cast<cudaStream_t>(s)>>>(a);
   CDETR_CHECK_LAUNCH();
   return 0;
@@ -272,6 +270,7 @@ extern "C" int cdetr_mha_bwd(int B, int L, int E, int nh, const float* q, const 
   a.dk_hi = hi(dk); a.dk_lo = hi(dk) + dk.plane;
   a.dv_hi = hi(dv); a.dv_lo = hi(dv) + dv.plane;
   a.ld_g = dq.ld;
+  if (use_tc(L)) return mha_bwd_tc_launch(a, s);
   mha_bwd_q_kernel<<<dim3(cdiv(L, QPB), nh, B), QPB * SPLIT, 0, s>>>(a);
   CDETR_CHECK_LAUNCH();
   mha_bwd_kv_kernel<<<dim3(cdiv(L, QPB), nh, B), QPB * SPLIT, 0, s>>>(a);
