@@ -322,14 +322,22 @@ __global__ void rcda_bwd_v_kernel(const RcdaArgs a) {
 }
 
 // ------------------------------------------------------------------ backward 3: dK_r / dK_c
-// dK[k,d] = s * sum_q dS[k,q] * q[q,d];  grid (nh, B, 2), 256 threads = 8 key groups x 32 channels.
-// Queries are staged in tiles of 64 (dS rows and q rows both load coalesced); warp = key group, so the dS
-// operand is a shared-memory broadcast and the q operand is conflict-free.
-constexpr int KQ = 64;
+// dK[k,d] = s * sum_q dS[k,q] * q[q,d];  grid (nh, B, 2): one CTA per (head, sample, row/column side).
 constexpr int KMAX = 64;   // max keys per side handled by this kernel (H, W <= 64)
-__global__ void __launch_bounds__(256) rcda_bwd_k_kernel(const RcdaArgs a) {
-  __shared__ float dss[KMAX][KQ + 1];
-  __shared__ float qs[KQ][HD];
+// On the tensor cores (mma.sync m16n8k16, split-bf16 3-pass): D[k, d] = sum_q dS[k, q] q[q, d] is a
+// [n x L] x [L x 32] product per (sample, head, side).  The 8 warps of the CTA split the query range in steps of
+// 16; fragments are loaded straight from global memory (dS rows are q-contiguous = row-major A, q rows give the
+// "col" B operand pairwise), converted to hi/lo in registers, and the partial [n x 32] tiles are combined through
+// shared-memory atomics.  ~100 instructions per 16 queries and warp instead of ~1500 FMAs + LDS.
+__device__ __forceinline__ void mma_bf16_k(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <int MT>   // key rows handled = 16 * MT (n <= 16 * MT)
+__global__ void __launch_bounds__(256) rcda_bwd_k_mma_kernel(const RcdaArgs a) {
+  __shared__ float red[16 * MT][HD + 1];
   const int head = blockIdx.x, b = blockIdx.y, which = blockIdx.z;
   const int n = which == 0 ? a.W : a.H;
   const float* ds = which == 0 ? a.dsr : a.dsc;
@@ -337,37 +345,78 @@ __global__ void __launch_bounds__(256) rcda_bwd_k_kernel(const RcdaArgs a) {
   __nv_bfloat16* ohi = which == 0 ? a.dkr_hi : a.dkc_hi;
   __nv_bfloat16* olo = which == 0 ? a.dkr_lo : a.dkc_lo;
   const int64_t bh = (int64_t)b * a.nh + head;
-  const int d = threadIdx.x & 31, kg = threadIdx.x >> 5;
-  float acc[KMAX / 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int i = threadIdx.x; i < 16 * MT * (HD + 1); i += 256) (&red[0][0])[i] = 0.0f;
+  __syncthreads();
+  float acc[MT][4][4];
 #pragma unroll
-  for (int i = 0; i < KMAX / 8; ++i) acc[i] = 0.0f;
-  for (int q0 = 0; q0 < a.L; q0 += KQ) {
-    const int nq = min(KQ, a.L - q0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < n * KQ; i += 256) {
-      const int k = i / KQ, qq = i % KQ;
-      dss[k][qq] = qq < nq ? __ldg(ds + (bh * n + k) * a.L + q0 + qq) : 0.0f;
-    }
-    for (int i = threadIdx.x; i < KQ * HD; i += 256) {
-      const int qq = i / HD, dd = i % HD;
-      qs[qq][dd] = qq < nq ? __ldg(qp + ((int64_t)b * a.L + q0 + qq) * a.E + head * HD + dd) : 0.0f;
-    }
-    __syncthreads();
-    for (int qq = 0; qq < KQ; ++qq) {
-      const float qv = qs[qq][d];
+  for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-      for (int i = 0; i < KMAX / 8; ++i) acc[i] += dss[kg + 8 * i][qq] * qv;
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.0f;
+  const float* dsb = ds + bh * n * a.L;
+  const float* qb = qp + (int64_t)b * a.L * a.E + head * HD;
+  for (int q0 = warp * 16; q0 < a.L; q0 += 8 * 16) {
+    // B fragments: (k = query 2t, 2t+1 [+8]; n = channel g) for the four 8-channel tiles
+    uint32_t bh_[4][2], bl_[4][2];
+    const int qa = q0 + 2 * t;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int c = nt * 8 + g;
+      const float x0 = qa < a.L ? __ldg(qb + (int64_t)qa * a.E + c) : 0.0f;
+      const float x1 = qa + 1 < a.L ? __ldg(qb + (int64_t)(qa + 1) * a.E + c) : 0.0f;
+      const float x2 = qa + 8 < a.L ? __ldg(qb + (int64_t)(qa + 8) * a.E + c) : 0.0f;
+      const float x3 = qa + 9 < a.L ? __ldg(qb + (int64_t)(qa + 9) * a.E + c) : 0.0f;
+      split_bf16_pair(x0, x1, bh_[nt][0], bl_[nt][0]);
+      split_bf16_pair(x2, x3, bh_[nt][1], bl_[nt][1]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
+      const float* p0 = dsb + (int64_t)r0 * a.L;
+      const float* p1 = dsb + (int64_t)r1 * a.L;
+      const bool k0 = r0 < n, k1 = r1 < n;
+      const float y00 = (k0 && qa < a.L) ? __ldg(p0 + qa) : 0.0f, y01 = (k0 && qa + 1 < a.L) ? __ldg(p0 + qa + 1) : 0.0f;
+      const float y10 = (k1 && qa < a.L) ? __ldg(p1 + qa) : 0.0f, y11 = (k1 && qa + 1 < a.L) ? __ldg(p1 + qa + 1) : 0.0f;
+      const float y02 = (k0 && qa + 8 < a.L) ? __ldg(p0 + qa + 8) : 0.0f, y03 = (k0 && qa + 9 < a.L) ? __ldg(p0 + qa + 9) : 0.0f;
+      const float y12 = (k1 && qa + 8 < a.L) ? __ldg(p1 + qa + 8) : 0.0f, y13 = (k1 && qa + 9 < a.L) ? __ldg(p1 + qa + 9) : 0.0f;
+      uint32_t ah[4], al[4];
+      split_bf16_pair(y00, y01, ah[0], al[0]);
+      split_bf16_pair(y10, y11, ah[1], al[1]);
+      split_bf16_pair(y02, y03, ah[2], al[2]);
+      split_bf16_pair(y12, y13, ah[3], al[3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        mma_bf16_k(acc[mt][nt], ah, bl_[nt][0], bl_[nt][1]);
+        mma_bf16_k(acc[mt][nt], al, bh_[nt][0], bh_[nt][1]);
+        mma_bf16_k(acc[mt][nt], ah, bh_[nt][0], bh_[nt][1]);
+      }
     }
   }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int r = mt * 16 + g, c = nt * 8 + 2 * t;
+      atomicAdd(&red[r][c], acc[mt][nt][0]);
+      atomicAdd(&red[r][c + 1], acc[mt][nt][1]);
+      atomicAdd(&red[r + 8][c], acc[mt][nt][2]);
+      atomicAdd(&red[r + 8][c + 1], acc[mt][nt][3]);
+    }
+  __syncthreads();
   const float scale = rsqrtf((float)HD);
-#pragma unroll
-  for (int i = 0; i < KMAX / 8; ++i) {
-    const int k = kg + 8 * i;
-    if (k < n) {
-      const int64_t off = ((int64_t)b * n + k) * a.ld_g + head * HD + d;
-      split_bf16(acc[i] * scale, ohi[off], olo[off]);
-    }
+  for (int i = threadIdx.x; i < n * HD; i += 256) {
+    const int k = i / HD, d = i % HD;
+    const int64_t off = ((int64_t)b * n + k) * a.ld_g + head * HD + d;
+    split_bf16(red[k][d] * scale, ohi[off], olo[off]);
   }
+}
+int launch_bwd_k(const RcdaArgs& a, cudaStream_t s) {
+  const int n = a.H > a.W ? a.H : a.W;
+  if (n <= 32) rcda_bwd_k_mma_kernel<2><<<dim3(a.nh, a.B, 2), 256, 0, s>>>(a);
+  else rcda_bwd_k_mma_kernel<4><<<dim3(a.nh, a.B, 2), 256, 0, s>>>(a);
+  return 0;
 }
 
 size_t fwd_smem(int H, int W, int T, int Hc) {
@@ -446,7 +495,7 @@ extern "C" int cdetr_rcda_bwd(int B, int L, int H, int W, int E, int nh, const f
   { static bool once_rcda_bwd_v_kernel = false; if (!once_rcda_bwd_v_kernel) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); once_rcda_bwd_v_kernel = true; } }
   rcda_bwd_v_kernel<<<dim3(cdiv(H * W, TV), nh, B), TV, smem_v, s>>>(a);
   CDETR_CHECK_LAUNCH();
-  rcda_bwd_k_kernel<<<dim3(nh, B, 2), 256, 0, s>>>(a);
+  launch_bwd_k(a, s);
   CDETR_CHECK_LAUNCH();
   return 0;
 }
@@ -475,7 +524,7 @@ extern "C" int cdetr_rcda_bwd_kv(int B, int L, int H, int W, int E, int nh, cons
   { static bool once = false; if (!once) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); once = true; } }
   rcda_bwd_v_kernel<<<dim3(cdiv(H * W, TV), nh, B), TV, smem_v, s>>>(a);
   CDETR_CHECK_LAUNCH();
-  rcda_bwd_k_kernel<<<dim3(nh, B, 2), 256, 0, s>>>(a);
+  launch_bwd_k(a, s);
   CDETR_CHECK_LAUNCH();
   return 0;
 }
@@ -493,7 +542,7 @@ extern "C" int cdetr_rcda_bwd_k(int B, int L, int H, int W, int E, int nh, const
   a.dkr_hi = reinterpret_cast<__nv_bfloat16*>(dkr.base); a.dkr_lo = a.dkr_hi + dkr.plane;
   a.dkc_hi = reinterpret_cast<__nv_bfloat16*>(dkc.base); a.dkc_lo = a.dkc_hi + dkc.plane;
   a.ld_g = dkr.ld;
-  rcda_bwd_k_kernel<<<dim3(nh, B, 2), 256, 0, reinterpret_cast<cudaStream_t>(s_)>>>(a);
+  launch_bwd_k(a, reinterpret_cast<cudaStream_t>(s_));
   CDETR_CHECK_LAUNCH();
   return 0;
 }

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -x
-TAG=${1:-v15}
+TAG=${1:-v16}
 mkdir -p gpurun_out
 timeout 300 python tests/gpu_ops_probe.py > gpurun_out/ops_probe_$TAG.log 2>&1; grep -c "^OK" gpurun_out/ops_probe_$TAG.log; grep -a "FAIL\|rror" gpurun_out/ops_probe_$TAG.log | head; grep -a "mha" gpurun_out/ops_probe_$TAG.log
 timeout 100 python tools/mha_time.py 2>&1 | grep legacy; CDETR_MHA_LEGACY=1 timeout 100 python tools/mha_time.py 2>&1 | grep legacy
