@@ -846,7 +846,11 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
     // L2 -> SM operand traffic (~8.5 TB/s aggregate for 4-byte split operands), so wide tiles pay whenever the K
     // loop is long enough to amortise them and there are enough tiles to fill the machine
     const int tiles_m = cdiv(g->M, BM);
-    if (!nt && g->N >= 256 && g->K >= 1024 && (g->N >= 512 || tiles_m * cdiv(g->N, 256) >= (3 * num_sms) / 4)) bn = 256;
+    // 256-wide tiles need the small epilogue staging (no ReLU-mask input, one output) to keep two operand stages
+    const bool wide_ok = !nt && g->mask.base == nullptr && !(g->out_f32 != nullptr && g->out_split.base != nullptr);
+    const int tiles256 = tiles_m * cdiv(g->N, 256);
+    if (!nt && g->N >= 256 && g->K >= 1024 && (g->N >= 512 || tiles256 >= (3 * num_sms) / 4)) bn = 256;
+    else if (wide_ok && g->N >= 512 && g->K >= 256 && tiles256 >= 2 * num_sms) bn = 256;   // sweep v16: 8-18 % faster
     else if (g->N > 64) bn = 128;
     else if (g->N > 32) bn = 64;
     else if (g->N > 16) bn = 32;

@@ -160,7 +160,7 @@ def run_conv(Bn, H, W, C, Co, dil):
     report(tag + " dgrad", dx, xd.grad.permute(0, 2, 3, 1).reshape(Mn, C))
     dw = torch.zeros(Co, 9 * C, device=dev)
     L.gemm(dys, xs, Co, 9 * C, Mn, mode=1, out_f32=dw, accumulate=True, split_k=4, row_scale=scale,
-           block_n=128 if C % 128 == 0 else 64, conv=(H, W, C, dil, 1))
+           block_n=(256 if (9 * C) % 256 == 0 else 128) if C % 128 == 0 else 64, conv=(H, W, C, dil, 1))
     torch.cuda.synchronize()
     # staged layout [Co, (tap, c)]; reference grad is wrt the scaled weight -> multiply by scale for the raw weight
     ref_dw = (wd_.grad * scale.double()[:, None, None, None]).permute(0, 2, 3, 1).reshape(Co, 9 * C)

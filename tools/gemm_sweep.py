@@ -50,23 +50,20 @@ for (M, N, K, ep) in shapes:
     if "mask" in ep:
         kw["mask"] = L.to_split(torch.randn(M, N, device=dev))
     res = []
-    for bn in (32, 64, 128, 256):
-        if bn > max(N, 32):
+    for bn in (64, 128, 256):
+        if bn > max(N, 64):
             continue
-        for ctas in (1, 2, "R"):          # "R" = resident-B schedule (K <= 256 only)
-            if ctas == "R" and (K > 256 or bn > 128):
-                continue
-            for st in (1, 2, 3, 4, 6):
+        for st in (0, 2, 3, 4):           # 0 = the library's own choice for this tile width
+            if st:
                 os.environ["CDETR_GEMM_STAGES"] = str(st)
-                os.environ["CDETR_GEMM_CTAS"] = "1" if ctas == "R" else str(ctas)
-                os.environ["CDETR_GEMM_RESIDENT"] = "1" if ctas == "R" else "0"
-                try:
-                    t = timed(lambda: L.gemm(A, B, M, N, K, block_n=bn, **kw))
-                    res.append((t, bn, ctas, st))
-                except Exception:
-                    pass
-    for k in ("CDETR_GEMM_STAGES", "CDETR_GEMM_CTAS", "CDETR_GEMM_RESIDENT"):
-        os.environ.pop(k, None)
+            else:
+                os.environ.pop("CDETR_GEMM_STAGES", None)
+            try:
+                t = timed(lambda: L.gemm(A, B, M, N, K, block_n=bn, **kw))
+                res.append((t, bn, 1, st))
+            except Exception:
+                pass
+    os.environ.pop("CDETR_GEMM_STAGES", None)
     auto = timed(lambda: L.gemm(A, B, M, N, K, **kw))
     res.sort()
     fl = 2.0 * M * N * K
@@ -74,3 +71,24 @@ for (M, N, K, ep) in shapes:
           + "  ".join(f"bn{bn}/c{c}/s{st}:{t:.1f}" for t, bn, c, st in res[:6]) + f" | worst {res[-1][0]:.1f}", flush=True)
     if os.environ.get("SWEEP_FULL"):
         print("      " + " ".join(f"bn{bn}/c{c}/s{st}:{t:.1f}" for t, bn, c, st in sorted(res, key=lambda r: (r[1], str(r[2]), r[3]))), flush=True)
+
+# ---- weight-gradient shapes (mode 1: D[M,N] = A[K,M]^T B[K,N], split-K accumulation through TMA reduce-add)
+nt_shapes = [(512, 4608, 16384, 2), (256, 2304, 16384, 8), (1024, 256, 16384, 18), (256, 1024, 16384, 18), (256, 256, 16384, 64),
+             (2048, 512, 16384, 4), (512, 2048, 16384, 4), (128, 1152, 65536, 32), (512, 128, 65536, 74), (256, 256, 4800, 18)]
+for (M, N, K, sk0) in nt_shapes:
+    A = L.to_split(torch.randn(K, M, device=dev)); B = L.to_split(torch.randn(K, N, device=dev))
+    out = torch.zeros(M, N, device=dev)
+    res = []
+    for bn in (64, 128, 256):
+        if bn > N:
+            continue
+        for sk in sorted({max(1, sk0 // 2), sk0, sk0 * 2}):
+            try:
+                t = timed(lambda: L.gemm(A, B, M, N, K, mode=1, out_f32=out, accumulate=True, split_k=sk, block_n=bn))
+                res.append((t, bn, sk))
+            except Exception:
+                pass
+    res.sort()
+    fl = 2.0 * M * N * K
+    print(f"NT M={M} N={N} K={K}: " + "  ".join(f"bn{bn}/sk{sk}:{t:.1f}" for t, bn, sk in sorted(res, key=lambda r: (r[1], r[2])))
+          + f" | best {fl/res[0][0]/1e6:.0f} TF/s alg", flush=True)
