@@ -50,6 +50,7 @@ struct KernelArgs {
   int kb_per_split;  // k blocks (of 64) handled by one K-split
   int num_kb;
   int tiles_m, tiles_n, total_tiles;  // tile index = (split * tiles_m + mt) * tiles_n + nt
+  int tile_m;                         // output rows per tile: 128, or 256 for a CTA pair (cta_group::2)
   uint32_t idesc;
   uint32_t tmem_cols;  // columns of ONE accumulator buffer (two are allocated)
   // implicit 3x3 convolution (conv != 0): the conv operand (A in mode 0, B in mode 1) is an NHWC activation read
@@ -84,7 +85,7 @@ __device__ __forceinline__ long long gtimer() {
 struct TileCoord {
   int m0, n0, kb_begin, kb_end;
 };
-__device__ __forceinline__ TileCoord decode_tile(const KernelArgs& a, int tile) {
+__device__ __forceinline__ TileCoord decode_tile(const KernelArgs& a, int rank, int tile) {
   TileCoord t;
   if (a.resident_b) {  // n-major: consecutive tiles of a CTA share the n-tile
     t.n0 = (tile / a.tiles_m) * a.block_n;
@@ -93,14 +94,14 @@ __device__ __forceinline__ TileCoord decode_tile(const KernelArgs& a, int tile) 
     t.kb_end = a.num_kb;
   } else {
     t.n0 = (tile % a.tiles_n) * a.block_n;
-    t.m0 = ((tile / a.tiles_n) % a.tiles_m) * BM;
+    t.m0 = ((tile / a.tiles_n) % a.tiles_m) * a.tile_m + rank * BM;   // rank: CTA of the pair (0 otherwise)
     t.kb_begin = (tile / (a.tiles_n * a.tiles_m)) * a.kb_per_split;
     t.kb_end = min(a.num_kb, t.kb_begin + a.kb_per_split);
   }
   return t;
 }
 
-template <bool NT>
+template <bool NT, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOutF, const __grid_constant__ CUtensorMap tmOutS,
@@ -112,7 +113,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                              ~uintptr_t(1023));
   const int BN = args.block_n;
   const uint32_t a_bytes = 2u * BM * 128u;               // hi+lo planes, 128 B per row/k-row
-  const uint32_t b_bytes = NT ? (uint32_t)((BN + 63) / 64) * 16384u : 2u * (uint32_t)BN * 128u;
+  // CTA pair: this CTA stages its own 128 rows of A and BN/2 rows of B; the 256 x BN MMA reads both CTAs' halves
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int BNL = PAIR ? BN / 2 : BN;                    // B rows staged by this CTA
+  const uint32_t b_bytes = NT ? (uint32_t)((BN + 63) / 64) * 16384u : 2u * (uint32_t)BNL * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   constexpr int STG_LD = 33;                             // epilogue staging: 8 warps x [32][33] floats
   float* staging = reinterpret_cast<float*>(smem + args.staging_off);
@@ -127,9 +131,9 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const bool RB = !NT && args.resident_b != 0;
   const uint32_t slab_bytes = RB ? (uint32_t)args.num_kb * b_bytes : 0u;
   // tile walk of this CTA: strided round-robin, or a contiguous run in the resident-B schedule
-  const int t_begin = RB ? blockIdx.x * args.tiles_per_cta : blockIdx.x;
+  const int t_begin = RB ? blockIdx.x * args.tiles_per_cta : (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
   const int t_end = RB ? min(args.total_tiles, t_begin + args.tiles_per_cta) : args.total_tiles;
-  const int t_step = RB ? 1 : gridDim.x;
+  const int t_step = RB ? 1 : (PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -156,7 +160,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 8);   // one elected lane of each epilogue warp
+      mbar_init(&tmem_empty_bar[i], PAIR ? 16 : 8);   // one elected lane of each epilogue warp (of both CTAs)
     }
     mbar_init(slab_full_bar, 1);
     mbar_init(slab_empty_bar, 1);
@@ -164,11 +168,17 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_holder, 2 * args.tmem_cols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_holder, 2 * args.tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_holder, 2 * args.tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / TMA completion
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   pdl_wait();   // everything the stream predecessor wrote (operands, residuals, accumulation targets) is now visible
@@ -181,7 +191,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int cur_n0 = -1;
       uint32_t slab_gen = 0;
       for (int tile = t_begin; tile < t_end; tile += t_step) {
-        const TileCoord tc = decode_tile(args, tile);
+        const TileCoord tc = decode_tile(args, rank, tile);
         const int n0 = tc.n0, m0 = tc.m0, kb_begin = tc.kb_begin, kb_end = tc.kb_end;
         if (RB && n0 != cur_n0) {   // new n-tile: (re)load the weight slab once every MMA on the old one is done
           if (slab_gen > 0) mbar_wait(slab_empty_bar, (slab_gen - 1) & 1u);
@@ -206,6 +216,20 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (RB) {
             mbar_arrive_expect_tx(&full_bar[s], a_bytes);
             tma_load_3d(a_s, &tmA, &full_bar[s], kb * BK, m0, 0);  // box {64, BM, 2}
+            continue;
+          }
+          if (PAIR) {
+            // the leader's barrier collects the bytes of both CTAs' loads (its own arrive carries the expectation)
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
+            if (args.conv) {
+              const int k0 = kb * BK;
+              const int tap = k0 / args.cC;
+              const int dh = (tap / 3 - 1) * args.cdil * args.csign, dw = (tap % 3 - 1) * args.cdil * args.csign;
+              tma_load_5d_pair(a_s, &tmA, &full_bar[s], k0 - tap * args.cC, dw, ch0 + dh, cb, 0);
+            } else {
+              tma_load_3d_pair(a_s, &tmA, &full_bar[s], kb * BK, m0, 0);           // box {64, 128, 2}
+            }
+            tma_load_3d_pair(b_s, &tmB, &full_bar[s], kb * BK, n0 + rank * BNL, 0);  // box {64, BN/2, 2}
             continue;
           }
           mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
@@ -242,13 +266,13 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
+    // ------------------------------ MMA issuer (leader CTA only in a pair) -----
+    if (lane == 0 && rank == 0) {
       int it = 0, ti = 0;
       int cur_n0 = -1;
       uint32_t slab_gen = 0;
       for (int tile = t_begin; tile < t_end; tile += t_step, ++ti) {
-        const TileCoord tc = decode_tile(args, tile);
+        const TileCoord tc = decode_tile(args, rank, tile);
         const int kb_begin = tc.kb_begin, kb_end = tc.kb_end;
         if (RB && tc.n0 != cur_n0) {
           mbar_wait(slab_full_bar, slab_gen & 1u);
@@ -279,7 +303,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               a_hi = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
               a_lo = make_smem_desc_sw128(a_base + BM * 128 + k * 32, 16, 1024);
               b_hi = make_smem_desc_sw128(b_base + k * 32, 16, 1024);
-              b_lo = make_smem_desc_sw128(b_base + BN * 128 + k * 32, 16, 1024);
+              b_lo = make_smem_desc_sw128(b_base + BNL * 128 + k * 32, 16, 1024);
             } else {
               // MN-major SW128: 64-wide MN chunks 16 KB apart (LBO), 8-k groups 1024 B apart (SBO),
               // one k-step (16) = two k groups = +2048 B; lo plane 8 KB after hi inside a chunk.
@@ -288,16 +312,26 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               b_hi = make_smem_desc_sw128(b_base + k * 2048, 16384, 1024);
               b_lo = make_smem_desc_sw128(b_base + 8192 + k * 2048, 16384, 1024);
             }
-            umma_bf16_ss(tmem_d, a_hi, b_lo, args.idesc, acc);
-            acc = 1;
-            umma_bf16_ss(tmem_d, a_lo, b_hi, args.idesc, 1);
-            umma_bf16_ss(tmem_d, a_hi, b_hi, args.idesc, 1);
+            if (PAIR) {
+              umma_bf16_ss_pair(tmem_d, a_hi, b_lo, args.idesc, acc);
+              acc = 1;
+              umma_bf16_ss_pair(tmem_d, a_lo, b_hi, args.idesc, 1);
+              umma_bf16_ss_pair(tmem_d, a_hi, b_hi, args.idesc, 1);
+            } else {
+              umma_bf16_ss(tmem_d, a_hi, b_lo, args.idesc, acc);
+              acc = 1;
+              umma_bf16_ss(tmem_d, a_lo, b_hi, args.idesc, 1);
+              umma_bf16_ss(tmem_d, a_hi, b_hi, args.idesc, 1);
+            }
           }
-          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+          // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+          if (PAIR) umma_commit_pair(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);
         }
-        if (RB && (tile + 1 >= t_end || decode_tile(args, tile + 1).n0 != tc.n0))
+        if (RB && (tile + 1 >= t_end || decode_tile(args, rank, tile + 1).n0 != tc.n0))
           umma_commit(slab_empty_bar);    // last MMA reading this weight slab: the producer may overwrite it
-        umma_commit(&tmem_full_bar[ab]);  // accumulator of this tile complete
+        if (PAIR) umma_commit_pair(&tmem_full_bar[ab]);   // accumulator of this tile complete (both CTAs' halves)
+        else umma_commit(&tmem_full_bar[ab]);
         if (ti == 0) DBG_T(3);
       }
     }
@@ -327,7 +361,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t row128 = (uint32_t)lane * 128u, sw128 = (uint32_t)(lane & 7);
 
     auto chunk_valid = [&](int tile, int ch) -> bool {
-      const TileCoord tc = decode_tile(args, tile);
+      const TileCoord tc = decode_tile(args, rank, tile);
       return tc.m0 + q * 32 < args.M && tc.n0 + half * cols_half + ch * 32 < args.N;
     };
     auto advance = [&](int& tile, int& ch) {   // next chunk of this warp that touches the output at all
@@ -336,7 +370,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       } while (tile < t_end && !chunk_valid(tile, ch));
     };
     auto issue_in = [&](int tile, int ch, int b) {   // lane 0: TMA loads of one chunk's residual / mask
-      const TileCoord tc = decode_tile(args, tile);
+      const TileCoord tc = decode_tile(args, rank, tile);
       const int mr = tc.m0 + q * 32, nc = tc.n0 + half * cols_half + ch * 32;
       uint8_t* buf = wbuf + (uint32_t)b * args.epi_buf_bytes;
       mbar_arrive_expect_tx(&in_bar[b], in_bytes);
@@ -355,7 +389,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     int ti = 0;
     for (int tile = t_begin; tile < t_end; tile += t_step, ++ti) {
-      const TileCoord tc = decode_tile(args, tile);
+      const TileCoord tc = decode_tile(args, rank, tile);
       const int n0 = tc.n0, m0 = tc.m0;
       const int ab = ti & 1;
       mbar_wait(&tmem_full_bar[ab], (uint32_t)(ti >> 1) & 1u);
@@ -503,7 +537,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // all tcgen05.ld of this warp for this accumulator buffer are complete: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[ab]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&tmem_empty_bar[ab]);
+        else mbar_arrive(&tmem_empty_bar[ab]);
+      }
       if (ti == 0 && warp == 2 && lane == 0) DBG_T(5);
     }
     if (lane == 0) bulk_wait_group<0>();   // every store has been performed before the CTA retires
@@ -527,7 +564,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int rr = lane >> 2;       // row sub-index 0..7
     int ti = 0;
     for (int tile = t_begin; tile < t_end; tile += t_step, ++ti) {
-    const TileCoord tc = decode_tile(args, tile);
+    const TileCoord tc = decode_tile(args, rank, tile);
     const int n0 = tc.n0, m0 = tc.m0;
     const int ab = ti & 1;
     mbar_wait(&tmem_full_bar[ab], (uint32_t)(ti >> 1) & 1u);
@@ -679,7 +716,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // all tcgen05.ld of this warp for this accumulator buffer are complete: hand it back to the MMA warp
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tmem_empty_bar[ab]);
+    if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&tmem_empty_bar[ab]);
+        else mbar_arrive(&tmem_empty_bar[ab]);
+      }
     if (ti == 0 && warp == 2 && lane == 0) DBG_T(5);
     }  // tile loop
   }
@@ -687,9 +727,11 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) DBG_T(6);
+  if (PAIR) cluster_sync_all();   // the leader's MMAs have read the peer's shared memory; both may release TMEM
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * args.tmem_cols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 2 * args.tmem_cols);
+    else tmem_dealloc(tmem_base, 2 * args.tmem_cols);
     if (lane == 0) DBG_T(7);
   }
 }
@@ -860,6 +902,19 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
       while (bn > 32 && tiles_m * cdiv(g->N, bn) < num_sms) bn >>= 1;
     if (nt && bn < 64) bn = 64;
   }
+  // CTA pairs (cta_group::2): 256 x 256 output tiles over two SMs, each staging 128 rows of A and 128 rows of B per
+  // k-block: 64 KB per CTA and k-block for twice the MMA work of a 128 x 128 tile (the K <= 1024 shapes are bound by
+  // the L2 -> SM operand stream).  CDETR_GEMM_PAIR: 0 never, 1 whenever eligible, unset = heuristic below.
+  bool pair = false;
+  {
+    const char* e = getenv("CDETR_GEMM_PAIR");
+    const int pair_mode = e != nullptr ? atoi(e) : -1;
+    const bool eligible = !nt && g->N >= 256 && g->M >= 256 && g->split_k <= 1 && (g->block_n <= 0 || g->block_n == 256);
+    if (pair_mode == 1) pair = eligible;
+    else if (pair_mode == -1)   // tools/pair_sweep.py (profiles/r01_pair_sweep_v18.txt): 1.05-1.8x for K >= 512, <= 1.0x below
+      pair = eligible && g->N % 256 == 0 && g->K >= 512 && cdiv(g->M, 256) * (g->N / 256) >= num_sms / 4;
+    if (pair) bn = 256;
+  }
   CDETR_CHECK_ARG(bn >= 16 && bn <= 256 && bn % 16 == 0, "gemm: bad block_n %d", bn);
   CDETR_CHECK_ARG(!nt || bn % 64 == 0, "gemm: mode 1 needs block_n multiple of 64");
 
@@ -907,7 +962,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
       if ((rc = make_conv_map(&tmA, g->a, g->conv_C, g->conv_W, g->conv_H, conv_B, g->conv_W, BM / g->conv_W)) != 0)
         return rc;
     } else if ((rc = make_split_map(&tmA, g->a, g->K, g->M, BK, BM)) != 0) return rc;
-    if ((rc = make_split_map(&tmB, g->b, g->K, g->N, BK, bn)) != 0) return rc;
+    if ((rc = make_split_map(&tmB, g->b, g->K, g->N, BK, pair ? bn / 2 : bn)) != 0) return rc;
   } else {
     if ((rc = make_split_map(&tmA, g->a, g->M, g->K, 64, BK)) != 0) return rc;
     if (conv) {
@@ -924,12 +979,13 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   ka.conv = conv ? 1 : 0;
   ka.cH = conv ? g->conv_H : 1; ka.cW = conv ? g->conv_W : 1; ka.cC = conv ? g->conv_C : 1;
   ka.cdil = g->conv_dil; ka.csign = g->conv_sign;
-  ka.idesc = make_idesc_bf16_f32(BM, bn, nt ? 1 : 0, nt ? 1 : 0);
+  ka.idesc = make_idesc_bf16_f32(pair ? 2 * BM : BM, bn, nt ? 1 : 0, nt ? 1 : 0);
+  ka.tile_m = pair ? 2 * BM : BM;
   uint32_t cols = 32;
   while ((int)cols < bn) cols <<= 1;
   ka.tmem_cols = cols;
   const uint32_t a_bytes = 2u * BM * 128u;
-  const uint32_t b_bytes = nt ? (uint32_t)((bn + 63) / 64) * 16384u : 2u * (uint32_t)bn * 128u;
+  const uint32_t b_bytes = nt ? (uint32_t)((bn + 63) / 64) * 16384u : 2u * (uint32_t)(pair ? bn / 2 : bn) * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t tail_bytes = (2 * MAX_STAGES + 6 + 16) * 8 + 16;
   const uint32_t smem_max = 227u * 1024u - 1024u - tail_bytes;   // dynamic smem minus alignment slack and barriers
@@ -975,7 +1031,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
     if (f >= 1 && f <= MAX_STAGES && (uint32_t)f * stage_bytes <= smem_budget) stages = f;
   }
   CDETR_CHECK_ARG((uint32_t)stages * stage_bytes <= smem_budget, "gemm: tile does not fit shared memory");
-  ka.tiles_m = cdiv(g->M, BM);
+  ka.tiles_m = cdiv(g->M, ka.tile_m);
   ka.tiles_n = cdiv(g->N, bn);
   ka.total_tiles = ka.tiles_m * ka.tiles_n * splits;
   // Resident-B schedule: short-K problems with many m-tiles per n-tile keep the [bn x K] weight slab in shared memory
@@ -986,7 +1042,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   bool resident = false;
   if (const char* e = getenv("CDETR_GEMM_RESIDENT")) {
     const int f = atoi(e);
-    if (f == 1) resident = !nt && !conv && splits == 1 && (uint32_t)num_kb * b_bytes + 2 * a_bytes <= smem_budget;
+    if (f == 1) resident = !pair && !nt && !conv && splits == 1 && (uint32_t)num_kb * b_bytes + 2 * a_bytes <= smem_budget;
   }
   ka.resident_b = 0;
   ka.tiles_per_cta = 0;
@@ -1058,17 +1114,22 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
 
   int nctas = num_sms * ctas_per_sm;
   if (nctas > ka.total_tiles) nctas = ka.total_tiles;
+  if (pair) {   // clusters of two CTAs, one 256-row tile per cluster at a time
+    nctas = 2 * ka.total_tiles;
+    if (nctas > (num_sms & ~1)) nctas = num_sms & ~1;
+  }
   if (ka.resident_b) {   // contiguous runs of tiles_per_cta tiles (n-major order)
     ka.tiles_per_cta = cdiv(ka.total_tiles, nctas);
     nctas = cdiv(ka.total_tiles, ka.tiles_per_cta);
   }
   dim3 grid(nctas);
-  auto kern = nt ? gemm_split_kernel<true> : gemm_split_kernel<false>;
-  static size_t configured[2] = {0, 0};
-  if (configured[nt] < smem_bytes) {
+  auto kern = nt ? gemm_split_kernel<true, false> : (pair ? gemm_split_kernel<false, true> : gemm_split_kernel<false, false>);
+  static size_t configured[3] = {0, 0, 0};
+  const int ki = nt ? 1 : (pair ? 2 : 0);
+  if (configured[ki] < smem_bytes) {
     CDETR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           227 * 1024));
-    configured[nt] = 227 * 1024;
+    configured[ki] = 227 * 1024;
   }
   static int use_pdl = -1;
   if (use_pdl < 0) {
@@ -1081,11 +1142,22 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   CDETR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOutF, tmOutS, tmAdd, tmMask, ka));
   return CDETR_OK;
 }

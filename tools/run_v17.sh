@@ -1,6 +1,6 @@
 #!/bin/bash
 set -x
-TAG=${1:-v17}
+TAG=${1:-v19}
 mkdir -p gpurun_out
 timeout 300 python tests/gpu_gemm_probe.py > gpurun_out/gemm_probe_$TAG.log 2>&1; grep -c OK gpurun_out/gemm_probe_$TAG.log; grep -a "FAIL\|rror" gpurun_out/gemm_probe_$TAG.log | head -20
 timeout 300 python bench.py --steps 10 --warmup 3 --skip-cpu > gpurun_out/bench_c3_$TAG.json 2> gpurun_out/bench_c3_$TAG.err
