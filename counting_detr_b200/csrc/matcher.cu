@@ -97,7 +97,7 @@ __device__ __forceinline__ void bsync() {
 template <bool ONE_WARP>
 __global__ void lsap_kernel(const float* __restrict__ cost_all, const int* __restrict__ tgt_off, int Q,
                             int Tmax, int64_t* __restrict__ out_q, int64_t* __restrict__ out_t,
-                            int* __restrict__ out_n, int* __restrict__ status) {
+                            int* __restrict__ out_n, int* __restrict__ status, int stage_cost, int stage_off) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int b = blockIdx.x;
   const int T = tgt_off[b + 1] - tgt_off[b];
@@ -105,6 +105,9 @@ __global__ void lsap_kernel(const float* __restrict__ cost_all, const int* __res
   const int nr = transposed ? T : Q, nc = transposed ? Q : T;
   const int ncap = max(Q, Tmax);
   const float* cost = cost_all + (int64_t)b * Q * Tmax;  // [nr, nc] row-major
+  // small problems (300 x 50: 60 KB) keep the whole cost slab in shared memory: every augmentation step re-reads one
+  // row, and the L2 round trip of that read was the longest link of the dependent chain (3.4 us per step)
+  float* cost_s = reinterpret_cast<float*>(smraw + stage_off);
   double* u = reinterpret_cast<double*>(smraw);
   double* v = u + ncap;
   double* spc = v + ncap;
@@ -128,6 +131,15 @@ __global__ void lsap_kernel(const float* __restrict__ cost_all, const int* __res
   for (int i = tid; i < nr; i += nt) { u[i] = 0.0; col4row[i] = -1; }
   for (int j = tid; j < nc; j += nt) { v[j] = 0.0; row4col[j] = -1; }
   if (tid == 0) s_fail = 0;
+  if (stage_cost) {
+    const int n4 = (nr * nc) >> 2;
+    if ((reinterpret_cast<uintptr_t>(cost) & 15) == 0) {
+      for (int i = tid; i < n4; i += nt) reinterpret_cast<float4*>(cost_s)[i] = __ldg(reinterpret_cast<const float4*>(cost) + i);
+      for (int i = 4 * n4 + tid; i < nr * nc; i += nt) cost_s[i] = __ldg(cost + i);
+    } else {
+      for (int i = tid; i < nr * nc; i += nt) cost_s[i] = __ldg(cost + i);
+    }
+  }
   bsync<ONE_WARP>();
 
   for (int cur = 0; cur < nr; ++cur) {
@@ -144,12 +156,12 @@ __global__ void lsap_kernel(const float* __restrict__ cost_all, const int* __res
       const int nrem = s_nrem;
       const double minval = s_minval;
       const double ui = u[i];
-      const float* crow = cost + (int64_t)i * nc;
+      const float* crow = stage_cost ? cost_s + (int64_t)i * nc : cost + (int64_t)i * nc;
       Key best;
       best.val = INFINITY; best.pri = 2; best.pos = 0x7fffffff;
       for (int it = tid; it < nrem; it += nt) {
         const int j = remaining[it];
-        const double r = __dsub_rn(__dsub_rn(__dadd_rn(minval, (double)__ldg(crow + j)), ui), v[j]);
+        const double r = __dsub_rn(__dsub_rn(__dadd_rn(minval, (double)crow[j]), ui), v[j]);
         double sj = spc[j];
         if (r < sj) {
           sj = r;
@@ -274,9 +286,13 @@ extern "C" int cdetr_lsap(const float* cost, const int* tgt_off, int B, int Q, i
   cudaStream_t s = reinterpret_cast<cudaStream_t>(s_);
   CDETR_CHECK_ARG(cost && tgt_off && out_q && out_t && out_n && status && B > 0 && Q > 0, "lsap: bad args");
   const int ncap = Q > Tmax ? Q : Tmax;
+  const size_t base = (lsap_smem(ncap, 32) + 15) / 16 * 16;
+  const size_t slab = (size_t)Q * Tmax * sizeof(float);
+  const int stage_cost = base + slab <= 200 * 1024 ? 1 : 0;
   if (ncap <= 384) {
-    const size_t smem = lsap_smem(ncap, 32);
-    lsap_kernel<true><<<B, 32, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status);
+    const size_t smem = stage_cost ? base + slab : lsap_smem(ncap, 32);
+    { static bool once = false; if (!once) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(lsap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); once = true; } }
+    lsap_kernel<true><<<B, 32, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status, stage_cost, (int)base);
   } else {
     int nt = 256;
     if (ncap > 768) nt = 512;
@@ -284,7 +300,7 @@ extern "C" int cdetr_lsap(const float* cost, const int* tgt_off, int B, int Q, i
     const size_t smem = lsap_smem(ncap, nt);
     CDETR_CHECK_ARG(smem <= 200 * 1024, "lsap: problem too large for shared memory (n=%d)", ncap);
     { static bool once_lsap_kernel_false_ = false; if (!once_lsap_kernel_false_) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(lsap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); once_lsap_kernel_false_ = true; } }
-    lsap_kernel<false><<<B, nt, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status);
+    lsap_kernel<false><<<B, nt, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status, 0, 0);
   }
   CDETR_CHECK_LAUNCH();
   return 0;
