@@ -157,6 +157,7 @@ __device__ __forceinline__ void store_rows_split(__nv_bfloat16* hi, __nv_bfloat1
 // ------------------------------------------------------------------------------------------------ forward
 // grid (nh, B, nsplit); strips of 16 queries round-robin over (warp, blockIdx.z)
 __global__ void __launch_bounds__(NTHREADS, 1) mha_fwd_tc_kernel(const MhaArgs a, const int Lp, const int PT) {
+  pdl_trigger();   // light successors (launch_light) may pre-launch; they wait for this grid to finish
   extern __shared__ __align__(16) uint8_t smem[];
   __nv_bfloat16* Kh = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* Kl = Kh + Lp * KP;
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mha_fwd_tc_kernel(const MhaArgs a
 // ------------------------------------------------------------------------------------------------ backward, queries
 // D_i = dO_i . O_i (written to dsum for the key-side kernel), dq_i = scale * sum_j dS_ij k_j
 __global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_q_tc_kernel(const MhaArgs a, const int Lp, const int PT) {
+  pdl_trigger();   // light successors (launch_light) may pre-launch; they wait for this grid to finish
   extern __shared__ __align__(16) uint8_t smem[];
   __nv_bfloat16* Kh = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* Kl = Kh + Lp * KP;
@@ -309,6 +311,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_q_tc_kernel(const MhaArgs
 // ------------------------------------------------------------------------------------------------ backward, keys
 // dv_j = sum_i P_ij dO_i ;  dk_j = scale * sum_i dS_ij q_i     (strips of 16 keys, chunks of 64 queries)
 __global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_kv_tc_kernel(const MhaArgs a, const int Lp, const int PT) {
+  pdl_trigger();   // light successors (launch_light) may pre-launch; they wait for this grid to finish
   extern __shared__ __align__(16) uint8_t smem[];
   __nv_bfloat16* Qh = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* Ql = Qh + Lp * KP;

@@ -28,6 +28,8 @@ __global__ void groupnorm_fwd_kernel(const float* __restrict__ x, int N, int C, 
                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                      float eps, float* __restrict__ y, __nv_bfloat16* y_hi,
                                      __nv_bfloat16* y_lo, int64_t ld_split, float* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[33];
   const int b = blockIdx.x / G, g = blockIdx.x % G;
   const int cg = C / G;
@@ -64,6 +66,8 @@ __global__ void groupnorm_bwd_kernel(const float* __restrict__ dy, const float* 
                                      const float* __restrict__ stats, float* __restrict__ dx,
                                      __nv_bfloat16* dx_hi, __nv_bfloat16* dx_lo, int64_t ld_split,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[33];
   __shared__ float cs[2][64];  // per-channel partial sums (cg <= 64)
   const int b = blockIdx.x / G, g = blockIdx.x % G;
@@ -116,6 +120,8 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
                                      const float* __restrict__ beta, float eps, float* __restrict__ z_out,
                                      float* __restrict__ y, __nv_bfloat16* y_hi, __nv_bfloat16* y_lo,
                                      int64_t ld_split, float* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -179,6 +185,8 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
                                      __nv_bfloat16* dz_hi, __nv_bfloat16* dz_lo, int64_t ld_split,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                      int rows_per_cta) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sg[LN_C], sb[LN_C];
   for (int i = threadIdx.x; i < LN_C; i += blockDim.x) { sg[i] = 0.0f; sb[i] = 0.0f; }
   __syncthreads();
@@ -261,7 +269,7 @@ extern "C" int cdetr_groupnorm_fwd(const float* x, int B, int N, int C, int G, c
                                    float* stats, cdetr_stream_t s) {
   CDETR_CHECK_ARG(x && gamma && beta && stats && C % G == 0 && C / G <= 64, "groupnorm_fwd: bad args");
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(y_split.base);
-  groupnorm_fwd_kernel<<<B * G, 512, 0, STREAM(s)>>>(x, N, C, G, gamma, beta, eps, y, hi,
+  launch_light(groupnorm_fwd_kernel, dim3(B * G), dim3(512), 0, STREAM(s), x, N, C, G, gamma, beta, eps, y, hi,
                                                      hi ? hi + y_split.plane : nullptr, y_split.ld, stats);
   CDETR_CHECK_LAUNCH();
   return 0;
@@ -275,7 +283,7 @@ extern "C" int cdetr_groupnorm_bwd(const float* dy, const float* x, int B, int N
                       512 % (C / G) == 0,
                   "groupnorm_bwd: bad args");
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(dx_split.base);
-  groupnorm_bwd_kernel<<<B * G, 512, 0, STREAM(s)>>>(dy, x, N, C, G, gamma, stats, dx, hi,
+  launch_light(groupnorm_bwd_kernel, dim3(B * G), dim3(512), 0, STREAM(s), dy, x, N, C, G, gamma, stats, dx, hi,
                                                      hi ? hi + dx_split.plane : nullptr, dx_split.ld,
                                                      dgamma, dbeta);
   CDETR_CHECK_LAUNCH();
@@ -288,7 +296,7 @@ extern "C" int cdetr_layernorm_fwd(const float* x, const float* res, int64_t M, 
   CDETR_CHECK_ARG(x && gamma && beta && C == LN_C && M > 0, "layernorm_fwd: needs C == 256");
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(y_split.base);
   const int warps = 8;
-  layernorm_fwd_kernel<<<cdiv(M, warps), warps * 32, 0, STREAM(s)>>>(
+  launch_light(layernorm_fwd_kernel, dim3(cdiv(M, warps)), dim3(warps * 32), 0, STREAM(s), 
       x, res, M, gamma, beta, eps, z_out, y, hi, hi ? hi + y_split.plane : nullptr, y_split.ld, stats);
   CDETR_CHECK_LAUNCH();
   return 0;
@@ -301,7 +309,7 @@ extern "C" int cdetr_layernorm_bwd(const float* dy, const float* dy2, const floa
                   "layernorm_bwd: needs C == 256");
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(dz_split.base);
   const int rows_per_cta = 64;
-  layernorm_bwd_kernel<<<cdiv(M, rows_per_cta), 256, 0, STREAM(s)>>>(
+  launch_light(layernorm_bwd_kernel, dim3(cdiv(M, rows_per_cta)), dim3(256), 0, STREAM(s), 
       dy, dy2, z, stats, M, gamma, dz, hi, hi ? hi + dz_split.plane : nullptr, dz_split.ld, dgamma,
       dbeta, rows_per_cta);
   CDETR_CHECK_LAUNCH();

@@ -337,6 +337,8 @@ __device__ __forceinline__ void mma_bf16_k(float (&c)[4], const uint32_t (&a)[4]
 }
 template <int MT>   // key rows handled = 16 * MT (n <= 16 * MT)
 __global__ void __launch_bounds__(256) rcda_bwd_k_mma_kernel(const RcdaArgs a) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[16 * MT][HD + 1];
   const int head = blockIdx.x, b = blockIdx.y, which = blockIdx.z;
   const int n = which == 0 ? a.W : a.H;
@@ -414,8 +416,8 @@ __global__ void __launch_bounds__(256) rcda_bwd_k_mma_kernel(const RcdaArgs a) {
 }
 int launch_bwd_k(const RcdaArgs& a, cudaStream_t s) {
   const int n = a.H > a.W ? a.H : a.W;
-  if (n <= 32) rcda_bwd_k_mma_kernel<2><<<dim3(a.nh, a.B, 2), 256, 0, s>>>(a);
-  else rcda_bwd_k_mma_kernel<4><<<dim3(a.nh, a.B, 2), 256, 0, s>>>(a);
+  if (n <= 32) launch_light(rcda_bwd_k_mma_kernel<2>, dim3(a.nh, a.B, 2), dim3(256), 0, s, a);
+  else launch_light(rcda_bwd_k_mma_kernel<4>, dim3(a.nh, a.B, 2), dim3(256), 0, s, a);
   return 0;
 }
 

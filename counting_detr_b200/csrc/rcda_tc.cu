@@ -74,6 +74,7 @@ __device__ __forceinline__ void softmax32(const float* __restrict__ qv, const fl
 
 __global__ void __launch_bounds__(320, 1)
 rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
+  pdl_trigger();   // light successors (launch_light) may pre-launch; they wait for this grid to finish
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Vs = smem;                                   // [2][HP][WP][32] bf16, SW64
@@ -283,6 +284,7 @@ struct TcBwdArgs {
 
 __global__ void __launch_bounds__(320, 1)
 rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a) {
+  pdl_trigger();   // light successors (launch_light) may pre-launch; they wait for this grid to finish
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Vs = smem;                     // V hi/lo; after the last MMA its first 8 KB are reused for the K slices
@@ -536,6 +538,7 @@ struct TcBwdVArgs {
 
 __global__ void __launch_bounds__(320, 2)
 rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a) {
+  pdl_trigger();   // light successors (launch_light) may pre-launch; they wait for this grid to finish
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Ps = smem;                                    // [2 bufs][2 planes][128][64] bf16, SW128 K-major

@@ -20,6 +20,8 @@ __device__ __forceinline__ float dim_t_of(int i, int num_feats) {
 // emb[n, off + i] = sin/cos(pos[n*pos_stride] * 2pi / dim_t(i)),  i < num_feats (even: sin, odd: cos)
 __global__ void sine_embed_kernel(const float* __restrict__ pos, int64_t n, int pos_stride, int num_feats,
                                   int off, int ld, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = n * num_feats;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -34,6 +36,8 @@ __global__ void sine_embed_kernel(const float* __restrict__ pos, int64_t n, int 
 __global__ void sine_embed_bwd_kernel(const float* __restrict__ pos, int64_t n, int pos_stride,
                                       int num_feats, int off, int ld, const float* __restrict__ demb,
                                       float* __restrict__ dpos) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -54,6 +58,8 @@ __global__ void sine_embed_bwd_kernel(const float* __restrict__ pos, int64_t n, 
 __global__ void add_bcast_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t M,
                                  int E, int mode, int H, int W, int64_t rows_y, float* __restrict__ out,
                                  __nv_bfloat16* o_hi, __nv_bfloat16* o_lo, int64_t ld_split) {
+  pdl_trigger();
+  pdl_wait();
   const int e8 = E / 8;
   const int64_t total = M * e8;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
@@ -97,6 +103,8 @@ __global__ void reduce_axis_kernel(const float* __restrict__ x, int B, int H, in
                                    float scale, const float* __restrict__ add, int accumulate,
                                    float* __restrict__ out, __nv_bfloat16* o_hi, __nv_bfloat16* o_lo,
                                    int64_t ld_split) {
+  pdl_trigger();
+  pdl_wait();
   const int R = axis == 1 ? W : H;
   const int64_t total = (int64_t)B * R * E;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
@@ -127,6 +135,8 @@ __global__ void combine_bcast_kernel(const float* __restrict__ a, const float* _
                                      const float* __restrict__ c, const float* __restrict__ row, float sr,
                                      const float* __restrict__ col, float sc, int64_t M, int E, int H, int W,
                                      float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = M * E;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
@@ -148,6 +158,8 @@ __global__ void combine_bcast_kernel(const float* __restrict__ a, const float* _
 __global__ void colsum_kernel(const float* __restrict__ x, const __nv_bfloat16* x_hi,
                               const __nv_bfloat16* x_lo, int64_t ld, int64_t M, int N, int rows_per_cta,
                               float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][256 + 8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
@@ -196,6 +208,8 @@ __device__ __forceinline__ float inv_sigmoid(float x) {
 }
 __global__ void box_head_fwd_kernel(const float* __restrict__ t, const float* __restrict__ ref, int64_t M,
                                     float* __restrict__ boxes) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= M * 4) return;
   const int64_t m = i / 4;
@@ -209,6 +223,8 @@ __global__ void box_head_bwd_kernel(const float* __restrict__ dboxes, const floa
                                     const float* __restrict__ ref, int64_t M, float* __restrict__ dt,
                                     __nv_bfloat16* dt_hi, __nv_bfloat16* dt_lo, int64_t ld_split,
                                     float* __restrict__ dref) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= M * 4) return;
   const int64_t m = i / 4;
@@ -231,6 +247,8 @@ __global__ void box_head_bwd_kernel(const float* __restrict__ dboxes, const floa
 
 // y = relu'(mask) * x as split (mask fp32 or via >0 of saved activations) -- used for MLP/FFN hidden grads
 __global__ void scale_kernel(float* __restrict__ x, int64_t n, float s) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x)
     x[i] *= s;
@@ -251,7 +269,7 @@ inline int grid_for(int64_t n, int threads = 256) {
 extern "C" int cdetr_sine_embed(const float* pos, int64_t n, int pos_stride, int num_feats, int off,
                                 int ld, float* out, cdetr_stream_t s) {
   CDETR_CHECK_ARG(pos && out && n > 0 && num_feats > 0 && off + num_feats <= ld, "sine_embed: bad args");
-  sine_embed_kernel<<<grid_for(n * num_feats), 256, 0, STREAM(s)>>>(pos, n, pos_stride, num_feats, off, ld, out);
+  launch_light(sine_embed_kernel, dim3(grid_for(n * num_feats)), dim3(256), 0, STREAM(s), pos, n, pos_stride, num_feats, off, ld, out);
   CDETR_CHECK_LAUNCH();
   return 0;
 }
@@ -259,7 +277,7 @@ extern "C" int cdetr_sine_embed(const float* pos, int64_t n, int pos_stride, int
 extern "C" int cdetr_sine_embed_bwd(const float* pos, int64_t n, int pos_stride, int num_feats, int off,
                                     int ld, const float* demb, float* dpos, cdetr_stream_t s) {
   CDETR_CHECK_ARG(pos && demb && dpos && n > 0, "sine_embed_bwd: bad args");
-  sine_embed_bwd_kernel<<<cdiv(n, 8), 256, 0, STREAM(s)>>>(pos, n, pos_stride, num_feats, off, ld, demb, dpos);
+  launch_light(sine_embed_bwd_kernel, dim3(cdiv(n, 8)), dim3(256), 0, STREAM(s), pos, n, pos_stride, num_feats, off, ld, demb, dpos);
   CDETR_CHECK_LAUNCH();
   return 0;
 }
@@ -267,7 +285,7 @@ extern "C" int cdetr_sine_embed_bwd(const float* pos, int64_t n, int pos_stride,
 extern "C" int cdetr_add_bcast(const float* x, const float* y, int64_t M, int E, int mode, int H, int W,
                                int64_t rows_y, float* out, cdetr_split_t out_split, cdetr_stream_t s) {
   CDETR_CHECK_ARG(x && M > 0 && E % 8 == 0 && mode >= 0 && mode <= 3, "add_bcast: bad args");
-  add_bcast_kernel<<<grid_for(M * (E / 8)), 256, 0, STREAM(s)>>>(x, y, M, E, mode, H, W, rows_y, out,
+  launch_light(add_bcast_kernel, dim3(grid_for(M * (E / 8))), dim3(256), 0, STREAM(s), x, y, M, E, mode, H, W, rows_y, out,
                                                                 SPLIT_HI(out_split), SPLIT_LO(out_split),
                                                                 out_split.ld);
   CDETR_CHECK_LAUNCH();
@@ -279,7 +297,7 @@ extern "C" int cdetr_reduce_axis(const float* x, int B, int H, int W, int E, int
                                  cdetr_stream_t s) {
   CDETR_CHECK_ARG(x && (axis == 1 || axis == 2) && (out || out_split.base), "reduce_axis: bad args");
   const int R = axis == 1 ? W : H;
-  reduce_axis_kernel<<<grid_for((int64_t)B * R * E), 256, 0, STREAM(s)>>>(
+  launch_light(reduce_axis_kernel, dim3(grid_for((int64_t)B * R * E)), dim3(256), 0, STREAM(s), 
       x, B, H, W, E, axis, scale, add, accumulate, out, SPLIT_HI(out_split), SPLIT_LO(out_split), out_split.ld);
   CDETR_CHECK_LAUNCH();
   return 0;
@@ -289,7 +307,7 @@ extern "C" int cdetr_combine_bcast(const float* a, const float* b, const float* 
                                    float sr, const float* col, float sc, int64_t M, int E, int H, int W,
                                    float* out, cdetr_stream_t s) {
   CDETR_CHECK_ARG(out && M > 0, "combine_bcast: bad args");
-  combine_bcast_kernel<<<grid_for(M * E), 256, 0, STREAM(s)>>>(a, b, c, row, sr, col, sc, M, E, H, W, out);
+  launch_light(combine_bcast_kernel, dim3(grid_for(M * E)), dim3(256), 0, STREAM(s), a, b, c, row, sr, col, sc, M, E, H, W, out);
   CDETR_CHECK_LAUNCH();
   return 0;
 }
@@ -300,7 +318,7 @@ extern "C" int cdetr_colsum(const float* x, cdetr_split_t x_split, int64_t ld, i
   int rows_per_cta = 512;
   while (rows_per_cta > 64 && cdiv(M, rows_per_cta) * cdiv(N, 256) < 2 * 148) rows_per_cta >>= 1;
   dim3 grid(cdiv(M, rows_per_cta), cdiv(N, 256));
-  colsum_kernel<<<grid, 256, 0, STREAM(s)>>>(x, SPLIT_HI(x_split), SPLIT_LO(x_split),
+  launch_light(colsum_kernel, dim3(grid), dim3(256), 0, STREAM(s), x, SPLIT_HI(x_split), SPLIT_LO(x_split),
                                              x ? ld : x_split.ld, M, N, rows_per_cta, out);
   CDETR_CHECK_LAUNCH();
   return 0;
@@ -309,7 +327,7 @@ extern "C" int cdetr_colsum(const float* x, cdetr_split_t x_split, int64_t ld, i
 extern "C" int cdetr_box_head_fwd(const float* t, const float* ref, int64_t M, float* boxes,
                                   cdetr_stream_t s) {
   CDETR_CHECK_ARG(t && ref && boxes && M > 0, "box_head_fwd: bad args");
-  box_head_fwd_kernel<<<cdiv(M * 4, 256), 256, 0, STREAM(s)>>>(t, ref, M, boxes);
+  launch_light(box_head_fwd_kernel, dim3(cdiv(M * 4, 256)), dim3(256), 0, STREAM(s), t, ref, M, boxes);
   CDETR_CHECK_LAUNCH();
   return 0;
 }
@@ -317,7 +335,7 @@ extern "C" int cdetr_box_head_fwd(const float* t, const float* ref, int64_t M, f
 extern "C" int cdetr_box_head_bwd(const float* dboxes, const float* boxes, const float* ref, int64_t M,
                                   float* dt, cdetr_split_t dt_split, float* dref, cdetr_stream_t s) {
   CDETR_CHECK_ARG(dboxes && boxes && ref && M > 0, "box_head_bwd: bad args");
-  box_head_bwd_kernel<<<cdiv(M * 4, 256), 256, 0, STREAM(s)>>>(dboxes, boxes, ref, M, dt, SPLIT_HI(dt_split),
+  launch_light(box_head_bwd_kernel, dim3(cdiv(M * 4, 256)), dim3(256), 0, STREAM(s), dboxes, boxes, ref, M, dt, SPLIT_HI(dt_split),
                                                              SPLIT_LO(dt_split), dt_split.ld, dref);
   CDETR_CHECK_LAUNCH();
   return 0;
@@ -325,7 +343,7 @@ extern "C" int cdetr_box_head_bwd(const float* dboxes, const float* boxes, const
 
 extern "C" int cdetr_scale(float* x, int64_t n, float a, cdetr_stream_t s) {
   CDETR_CHECK_ARG(x && n > 0, "scale: bad args");
-  scale_kernel<<<grid_for(n), 256, 0, STREAM(s)>>>(x, n, a);
+  launch_light(scale_kernel, dim3(grid_for(n)), dim3(256), 0, STREAM(s), x, n, a);
   CDETR_CHECK_LAUNCH();
   return 0;
 }
