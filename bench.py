@@ -389,8 +389,19 @@ def run_ours(args):
             pass
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         achieved = flops / (gemm_ms * 1e-3) / 1e12
+        # DRAM traffic of the family from the committed ncu capture of the same workload (None for other workloads)
+        traffic, traffic_note = None, None
+        if args.workload == "c3" and world == 1:
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic_c3.json")))
+                traffic = tj["dram_bytes"] / max(tj["launches"], 1)
+                traffic_note = (f"dram__bytes_read+write summed over the {tj['launches']} GEMM launches of one step "
+                                f"= {tj['dram_bytes'] / 1e9:.2f} GB per step (ncu, cold cache); value = mean bytes per launch")
+            except Exception:
+                pass
         roofline = {"bound": "tensor", "kernel": "gemm_split_kernel (tcgen05 split-bf16 GEMM family: conv/linear fwd, dgrad, wgrad)",
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_note": traffic_note,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                     "algorithmic_gflop_per_step": flops / 1e9, "gemm_ms_per_step": gemm_ms, "gemm_launches_per_step": len(trace),
                     "note": "algorithmic (fp32-equivalent) FLOPs; each is issued as 3 bf16 MMAs (hi*hi+hi*lo+lo*hi), so the "
