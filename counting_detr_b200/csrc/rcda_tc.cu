@@ -39,7 +39,39 @@ struct TcArgs {
   __nv_bfloat16* o_lo;
   int64_t ld_o;
   uint32_t idesc;
+  uint32_t idesc_s;   // logits MMA: [128 x 32] x [32 x 32]
 };
+
+// softmax over the first n entries of a logit row (entries >= n or masked get probability 0)
+__device__ __forceinline__ void softmax_row32(float (&p)[32], int n, const uint8_t* __restrict__ mask) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    if (k >= n || (mask && mask[k])) p[k] = -INFINITY;
+    mx = fmaxf(mx, p[k]);
+  }
+  float sum = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    p[k] = expf(p[k] - mx);
+    sum += p[k];
+  }
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) p[k] *= inv;
+}
+// one 32-value row -> split-bf16 K-major SWIZZLE_64B operand row r (64-byte rows): hi plane at dst, lo at dst + plane
+__device__ __forceinline__ void write_operand_row32(uint8_t* dst, uint32_t plane_bytes, int r, const float (&x)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_bf16_pair(x[8 * j + 2 * i], x[8 * j + 2 * i + 1], hw[i], lw[i]);
+    const uint32_t off = (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4);
+    *reinterpret_cast<uint4*>(dst + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(dst + plane_bytes + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
 
 __device__ __forceinline__ void softmax32(const float* __restrict__ qv, const float* __restrict__ Ks, int n,
                                           const uint8_t* __restrict__ mask, float (&p)[32]) {
@@ -79,14 +111,17 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Vs = smem;                                   // [2][HP][WP][32] bf16, SW64
   uint8_t* As = Vs + 2 * V_PLANE_BYTES;                 // [2 tiles][2 planes][128][32] bf16, SW64 K-major
-  float* Ksr = reinterpret_cast<float*>(As + 4 * A_PLANE_BYTES);  // [32][32]
-  float* Ksc = Ksr + 32 * HD;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Ksc + 32 * HD);
+  // key tiles as split-bf16 K-major SW64 B operands of the logit MMAs: [2 sides][2 planes][32 keys][32 d] = 8 KB
+  uint8_t* Kb = As + 4 * A_PLANE_BYTES;
+  constexpr uint32_t K_PLANE_BYTES = 32 * HD * 2;   // 2048
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Kb + 4 * K_PLANE_BYTES);
   uint64_t* v_full = bars;
   uint64_t* a_ready = bars + 1;  // [2]
   uint64_t* t_full = bars + 3;   // [2]
   uint64_t* t_empty = bars + 5;  // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* q_ready = bars + 7;  // [2]  q_r (phase 0) / q_c (phase 1) operand of the group written
+  uint64_t* s_full = bars + 9;   // [2]  logits of the group in TMEM (phase 0: row side, phase 1: column side)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, b = blockIdx.z;
@@ -100,6 +135,8 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
       mbar_init(&a_ready[g], 4);      // one elected lane per warp of the group
       mbar_init(&t_full[g], 1);
       mbar_init(&t_empty[g], 4);
+      mbar_init(&q_ready[g], 4);
+      mbar_init(&s_full[g], 1);
     }
     fence_barrier_init();
   }
@@ -121,6 +158,27 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
   } else if (warp == 1) {
     if (lane == 0) {
       const int ngroups = (q_cta + TQ < a.L) ? 2 : 1;
+      // logits: S = q K^T per side and group, [128 x 32] x [32 x 32] into the first 32 columns of the group's buffer
+      for (int side = 0; side < 2; ++side) {
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(&q_ready[g], (uint32_t)side);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(As) + (uint32_t)g * 2u * A_PLANE_BYTES;
+          const uint32_t k_base = smem_u32(Kb) + (uint32_t)side * 2u * K_PLANE_BYTES;
+          const uint32_t d = tmem_base + (uint32_t)g * 256u;
+#pragma unroll
+          for (int ks = 0; ks < HD / 16; ++ks) {
+            const uint64_t a_hi = make_smem_desc(a_base + ks * 32, 16, 512, 4);
+            const uint64_t a_lo = make_smem_desc(a_base + A_PLANE_BYTES + ks * 32, 16, 512, 4);
+            const uint64_t b_hi = make_smem_desc(k_base + ks * 32, 16, 512, 4);
+            const uint64_t b_lo = make_smem_desc(k_base + K_PLANE_BYTES + ks * 32, 16, 512, 4);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc_s, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc_s, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc_s, 1);
+          }
+          umma_commit(&s_full[g]);
+        }
+      }
       mbar_wait(v_full, 0);
       const uint32_t v_base = smem_u32(Vs);
       for (int p = 0; p < nblk; ++p) {
@@ -157,10 +215,25 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
     const int q = q_cta + g * TQ + r;
     const bool ok = q < a.L;
     const bool active = q_cta + g * TQ < a.L;   // whole group idle when its tile is past the end
-    for (int i = ct; i < 32 * HD; i += 256) {
-      const int k = i / HD, dch = i % HD;
-      Ksr[i] = k < a.W ? a.kr[((int64_t)b * a.W + k) * a.E + head * HD + dch] : 0.0f;
-      Ksc[i] = k < a.H ? a.kc[((int64_t)b * a.H + k) * a.E + head * HD + dch] : 0.0f;
+    {   // thread -> (side, key, 8-channel chunk): 2 x 32 x 4 = 256 chunks of the two key tiles
+      const int side = ct >> 7, k = (ct >> 2) & 31, j = ct & 3;
+      const int n = side == 0 ? a.W : a.H;
+      const float* kp = (side == 0 ? a.kr : a.kc) + ((int64_t)b * n + k) * a.E + head * HD + j * 8;
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = 0.0f;
+      if (k < n) {
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(kp)), t1 = __ldg(reinterpret_cast<const float4*>(kp) + 1);
+        x[0] = t0.x; x[1] = t0.y; x[2] = t0.z; x[3] = t0.w; x[4] = t1.x; x[5] = t1.y; x[6] = t1.z; x[7] = t1.w;
+      }
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_bf16_pair(x[2 * i], x[2 * i + 1], hw[i], lw[i]);
+      uint8_t* kd = Kb + (size_t)side * 2 * K_PLANE_BYTES;
+      const uint32_t off = (uint32_t)k * 64u + (uint32_t)((j ^ ((k >> 1) & 3)) << 4);
+      *reinterpret_cast<uint4*>(kd + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(kd + K_PLANE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      fence_proxy_async();
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (active) {
@@ -168,8 +241,12 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
       const float scale = rsqrtf((float)HD);
       const int64_t bh = (int64_t)b * a.nh + head;
       float ac[32];
+      const uint32_t taddr_s = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * 256u;
       {
         float ar[32], qv[HD];
+        // ---- row side: q_r (scaled) -> A operand -> tensor core -> logits of this query back from TMEM
+#pragma unroll
+        for (int j = 0; j < HD; ++j) qv[j] = 0.0f;
         if (ok) {
           const float4* qp = reinterpret_cast<const float4*>(a.qr + ((int64_t)b * a.L + q) * a.E + head * HD);
 #pragma unroll
@@ -177,29 +254,14 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
             const float4 t = __ldg(qp + j);
             qv[4 * j] = t.x * scale; qv[4 * j + 1] = t.y * scale; qv[4 * j + 2] = t.z * scale; qv[4 * j + 3] = t.w * scale;
           }
-          softmax32(qv, Ksr, a.W, a.mask_row ? a.mask_row + (int64_t)b * a.W : nullptr, ar);
-#pragma unroll
-          for (int w = 0; w < 32; ++w)
-            if (w < a.W) a.ar[(bh * a.W + w) * a.L + q] = ar[w];
-        } else {
-#pragma unroll
-          for (int w = 0; w < 32; ++w) ar[w] = 0.0f;
         }
-        // A operand: row r, 4 chunks of 8 k-values; SWIZZLE_64B: 16-byte chunk j of row r lives at j ^ ((r >> 1) & 3)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t hw[4], lw[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            split_bf16_pair(ar[8 * j + 2 * i], ar[8 * j + 2 * i + 1], hw[i], lw[i]);
-          }
-          const uint32_t off = (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4);
-          *reinterpret_cast<uint4*>(Ag + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint4*>(Ag + A_PLANE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        }
-        fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core (async proxy)
+        write_operand_row32(Ag, A_PLANE_BYTES, r, qv);
+        fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_ready[g]);
+        if (lane == 0) mbar_arrive(&q_ready[g]);
+        // column-side query while the row logits are computed
+#pragma unroll
+        for (int j = 0; j < HD; ++j) qv[j] = 0.0f;
         if (ok) {
           const float4* qp = reinterpret_cast<const float4*>(a.qc + ((int64_t)b * a.L + q) * a.E + head * HD);
 #pragma unroll
@@ -207,7 +269,48 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
             const float4 t = __ldg(qp + j);
             qv[4 * j] = t.x * scale; qv[4 * j + 1] = t.y * scale; qv[4 * j + 2] = t.z * scale; qv[4 * j + 3] = t.w * scale;
           }
-          softmax32(qv, Ksc, a.H, a.mask_col ? a.mask_col + (int64_t)b * a.H : nullptr, ac);
+        }
+        mbar_wait(&s_full[g], 0);
+        tc_fence_after();
+        {
+          uint32_t t[32];
+          tmem_ld_32x32b_x32(taddr_s, t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int w = 0; w < 32; ++w) ar[w] = __uint_as_float(t[w]);
+        }
+        tc_fence_before();
+        // the row-logit MMAs have consumed q_r: the operand buffer takes q_c
+        write_operand_row32(Ag, A_PLANE_BYTES, r, qv);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&q_ready[g]);
+        if (ok) {
+          softmax_row32(ar, a.W, a.mask_row ? a.mask_row + (int64_t)b * a.W : nullptr);
+#pragma unroll
+          for (int w = 0; w < 32; ++w)
+            if (w < a.W) a.ar[(bh * a.W + w) * a.L + q] = ar[w];
+        } else {
+#pragma unroll
+          for (int w = 0; w < 32; ++w) ar[w] = 0.0f;
+        }
+        mbar_wait(&s_full[g], 1);
+        tc_fence_after();
+        {
+          uint32_t t[32];
+          tmem_ld_32x32b_x32(taddr_s, t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 32; ++h) ac[h] = __uint_as_float(t[h]);
+        }
+        tc_fence_before();
+        // the column-logit MMAs have consumed q_c: the operand buffer takes A_r for the main contraction
+        write_operand_row32(Ag, A_PLANE_BYTES, r, ar);
+        fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[g]);
+        if (ok) {
+          softmax_row32(ac, a.H, a.mask_col ? a.mask_col + (int64_t)b * a.H : nullptr);
 #pragma unroll
           for (int h = 0; h < 32; ++h)
             if (h < a.H) a.ac[(bh * a.H + h) * a.L + q] = ac[h];
@@ -741,6 +844,7 @@ extern "C" int cdetr_rcda_fwd_tc(int B, int L, int H, int W, int E, int nh, cons
   a.qr = qr; a.qc = qc; a.kr = kr; a.kc = kc; a.mask_row = mask_row; a.mask_col = mask_col; a.ar = ar; a.ac = ac;
   a.o_hi = reinterpret_cast<__nv_bfloat16*>(o.base); a.o_lo = a.o_hi + o.plane; a.ld_o = o.ld;
   a.idesc = make_idesc_bf16_f32(TQ, 256, 0, 1);
+  a.idesc_s = make_idesc_bf16_f32(TQ, 32, 0, 0);
   const size_t smem = 2 * V_PLANE_BYTES + 4 * A_PLANE_BYTES + 2 * 32 * HD * sizeof(float) + 128 + 1024;
   static bool once = false;
   if (!once) {

@@ -213,8 +213,9 @@ for (Bz, Lq, Hh, Ww) in [(2, 300, 32, 32), (1, 70, 9, 13), (1, 1024, 32, 32), (1
         ar2 = torch.empty_like(ar); ac2 = torch.empty_like(ac); o2 = zs(Bz * Lq, E)
         L.call("cdetr_rcda_fwd_tc", Bz, Lq, Hh, Ww, E, nh, qr, qc, kr, kc, S(v.detach()), None, None, ar2, ac2, o2)
         report(f"rcda_fwd_tc {tag}", L.from_split(o2).view(Bz, Lq, E), ref.detach(), 3e-5)
-        report(f"rcda_fwd_tc A_r {tag}", ar2.permute(0, 1, 3, 2), a_r.detach(), 1e-5)
-        report(f"rcda_fwd_tc A_c {tag}", ac2.permute(0, 1, 3, 2), a_c.detach(), 1e-5)
+        # logits come from the 3-pass split-bf16 tensor-core product (2^-16 relative per operand pair): 3e-5, like O
+        report(f"rcda_fwd_tc A_r {tag}", ar2.permute(0, 1, 3, 2), a_r.detach(), 3e-5)
+        report(f"rcda_fwd_tc A_c {tag}", ac2.permute(0, 1, 3, 2), a_c.detach(), 3e-5)
     dO = torch.randn(Bz, Lq, E, device=dev)
     ref.backward(dO)
     dsr = torch.empty_like(ar); dsc = torch.empty_like(ac)
