@@ -383,6 +383,7 @@ struct TcBwdArgs {
   __nv_bfloat16 *dqr_hi, *dqr_lo, *dqc_hi, *dqc_lo;
   int64_t ld_g;
   uint32_t idesc;
+  uint32_t idesc_q;   // dq MMA: [128 x 32 keys] x [32 keys x 32 d], B MN-major
 };
 
 __global__ void __launch_bounds__(320, 1)
@@ -399,7 +400,9 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
   uint64_t* a_ready = bars + 1;  // [2]
   uint64_t* t_full = bars + 3;   // [2]
   uint64_t* t_empty = bars + 5;  // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 7);
+  uint64_t* q_ready = bars + 7;  // [2]  dS_r (phase 0) / dS_c (phase 1) operand of the group written
+  uint64_t* s_full = bars + 9;   // [2]  dq of the group in TMEM
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 11);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, b = blockIdx.z;
   const int q_cta = blockIdx.x * 2 * TQ;
@@ -411,6 +414,8 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
       mbar_init(&a_ready[g], 4);      // one elected lane per warp of the group
       mbar_init(&t_full[g], 1);
       mbar_init(&t_empty[g], 4);
+      mbar_init(&q_ready[g], 4);
+      mbar_init(&s_full[g], 1);
     }
     fence_barrier_init();
   }
@@ -454,6 +459,28 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
             umma_bf16_ss(d, a_hi, b_hi, a.idesc, 1);
           }
           umma_commit(&t_full[g]);
+        }
+      }
+      // dq = dS K per side and group: A = dS rows [128 x 32 keys] (K-major), B = key tile [32 keys x 32 d] read as
+      // an MN-major operand (row = key = k index, 64-byte rows of 32 channels), D = first 32 columns of the buffer
+      for (int side = 0; side < 2; ++side) {
+        for (int g = 0; g < ngroups; ++g) {
+          mbar_wait(&q_ready[g], (uint32_t)side);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(As) + (uint32_t)g * 2u * A_PLANE_BYTES;
+          const uint32_t k_base = smem_u32(Vs) + (uint32_t)side * 4096u;
+          const uint32_t d = tmem_base + (uint32_t)g * 256u;
+#pragma unroll
+          for (int ks = 0; ks < WP / 16; ++ks) {
+            const uint64_t a_hi = make_smem_desc(a_base + ks * 32, 16, 512, 4);
+            const uint64_t a_lo = make_smem_desc(a_base + A_PLANE_BYTES + ks * 32, 16, 512, 4);
+            const uint64_t b_hi = make_smem_desc(k_base + ks * 1024, 2048, 512, 4);
+            const uint64_t b_lo = make_smem_desc(k_base + 2048 + ks * 1024, 2048, 512, 4);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc_q, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc_q, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc_q, 1);
+          }
+          umma_commit(&s_full[g]);
         }
       }
     }
@@ -535,76 +562,101 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
         }
       }
     }
-    // every MMA has completed once both groups are past their last t_full wait: reuse the V region for K
+    // every G MMA has completed once both groups are past their last t_full wait: the V region takes the two key
+    // tiles as split-bf16 operands ([2 sides][2 planes][32 keys][32 d], SW64 rows of 64 bytes) and the dO operand
+    // buffers take the dS rows; dq = scale * dS K then runs on the tensor core and comes back one query per thread
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    float* Ksr = reinterpret_cast<float*>(Vs);
-    float* Ksc = Ksr + 32 * HD;
-    for (int i = ct; i < 32 * HD; i += 256) {
-      const int k = i / HD, dch = i % HD;
-      Ksr[i] = k < a.W ? a.kr[((int64_t)b * a.W + k) * a.E + head * HD + dch] : 0.0f;
-      Ksc[i] = k < a.H ? a.kc[((int64_t)b * a.H + k) * a.E + head * HD + dch] : 0.0f;
+    {
+      const int side = ct >> 7, k = (ct >> 2) & 31, j = ct & 3;
+      const int n = side == 0 ? a.W : a.H;
+      const float* kp = (side == 0 ? a.kr : a.kc) + ((int64_t)b * n + k) * a.E + head * HD + j * 8;
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = 0.0f;
+      if (k < n) {
+        const float4 t0 = __ldg(reinterpret_cast<const float4*>(kp)), t1 = __ldg(reinterpret_cast<const float4*>(kp) + 1);
+        x[0] = t0.x; x[1] = t0.y; x[2] = t0.z; x[3] = t0.w; x[4] = t1.x; x[5] = t1.y; x[6] = t1.z; x[7] = t1.w;
+      }
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_bf16_pair(x[2 * i], x[2 * i + 1], hw[i], lw[i]);
+      uint8_t* kd = Vs + (size_t)side * 4096;
+      const uint32_t off = (uint32_t)k * 64u + (uint32_t)((j ^ ((k >> 1) & 3)) << 4);
+      *reinterpret_cast<uint4*>(kd + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(kd + 2048 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      fence_proxy_async();
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (ok) {
+    if (active) {
+      uint8_t* Ag = As + (size_t)g * 2 * A_PLANE_BYTES;
       const float scale = rsqrtf((float)HD);
-      {
+      const uint32_t taddr_s = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * 256u;
+      const int64_t off = ((int64_t)b * a.L + q) * a.ld_g + head * HD;
+      float ds[32];
+      {   // row side: dS_r = A_r o (dA_r - <A_r, dA_r>)
         float dot = 0.0f;
 #pragma unroll
         for (int w = 0; w < 32; ++w) dot += ar[w] * dar[w];
-        float dq[HD];
-#pragma unroll
-        for (int j = 0; j < HD; ++j) dq[j] = 0.0f;
 #pragma unroll
         for (int w = 0; w < 32; ++w) {
-          const float ds = ar[w] * (dar[w] - dot);
-          if (w < a.W) a.dsr[(bh * a.W + w) * a.L + q] = ds;
-          const float4* kp = reinterpret_cast<const float4*>(Ksr + w * HD);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 t = kp[j];
-            dq[4 * j] += ds * t.x; dq[4 * j + 1] += ds * t.y; dq[4 * j + 2] += ds * t.z; dq[4 * j + 3] += ds * t.w;
-          }
-        }
-        const int64_t off = ((int64_t)b * a.L + q) * a.ld_g + head * HD;
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-          uint32_t hw[4], lw[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            split_bf16_pair(dq[gg * 8 + 2 * j] * scale, dq[gg * 8 + 2 * j + 1] * scale, hw[j], lw[j]);
-          }
-          reinterpret_cast<uint4*>(a.dqr_hi + off)[gg] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          reinterpret_cast<uint4*>(a.dqr_lo + off)[gg] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          ds[w] = ar[w] * (dar[w] - dot);
+          if (ok && w < a.W) a.dsr[(bh * a.W + w) * a.L + q] = ds[w];
         }
       }
-      {
+      write_operand_row32(Ag, A_PLANE_BYTES, r, ds);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_ready[g]);
+      {   // column side while the tensor core works on the row side
         float dot = 0.0f;
 #pragma unroll
         for (int h = 0; h < 32; ++h) dot += acg[h * TQ + r] * dacg[h * TQ + r];
-        float dq[HD];
-#pragma unroll
-        for (int j = 0; j < HD; ++j) dq[j] = 0.0f;
 #pragma unroll
         for (int h = 0; h < 32; ++h) {
-          const float ds = acg[h * TQ + r] * (dacg[h * TQ + r] - dot);
-          if (h < a.H) a.dsc[(bh * a.H + h) * a.L + q] = ds;
-          const float4* kp = reinterpret_cast<const float4*>(Ksc + h * HD);
+          ds[h] = acg[h * TQ + r] * (dacg[h * TQ + r] - dot);
+          if (ok && h < a.H) a.dsc[(bh * a.H + h) * a.L + q] = ds[h];
+        }
+      }
+      mbar_wait(&s_full[g], 0);
+      tc_fence_after();
+      {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(taddr_s, t);
+        tmem_ld_wait();
+        tc_fence_before();
+        // the row-side MMAs have consumed dS_r: the operand buffer takes dS_c
+        write_operand_row32(Ag, A_PLANE_BYTES, r, ds);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&q_ready[g]);
+        if (ok) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 t = kp[j];
-            dq[4 * j] += ds * t.x; dq[4 * j + 1] += ds * t.y; dq[4 * j + 2] += ds * t.z; dq[4 * j + 3] += ds * t.w;
+          for (int gg = 0; gg < 4; ++gg) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              split_bf16_pair(__uint_as_float(t[gg * 8 + 2 * j]) * scale, __uint_as_float(t[gg * 8 + 2 * j + 1]) * scale, hw[j], lw[j]);
+            reinterpret_cast<uint4*>(a.dqr_hi + off)[gg] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            reinterpret_cast<uint4*>(a.dqr_lo + off)[gg] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
         }
-        const int64_t off = ((int64_t)b * a.L + q) * a.ld_g + head * HD;
+      }
+      mbar_wait(&s_full[g], 1);
+      tc_fence_after();
+      {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(taddr_s, t);
+        tmem_ld_wait();
+        if (ok) {
 #pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-          uint32_t hw[4], lw[4];
+          for (int gg = 0; gg < 4; ++gg) {
+            uint32_t hw[4], lw[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            split_bf16_pair(dq[gg * 8 + 2 * j] * scale, dq[gg * 8 + 2 * j + 1] * scale, hw[j], lw[j]);
+            for (int j = 0; j < 4; ++j)
+              split_bf16_pair(__uint_as_float(t[gg * 8 + 2 * j]) * scale, __uint_as_float(t[gg * 8 + 2 * j + 1]) * scale, hw[j], lw[j]);
+            reinterpret_cast<uint4*>(a.dqc_hi + off)[gg] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            reinterpret_cast<uint4*>(a.dqc_lo + off)[gg] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
           }
-          reinterpret_cast<uint4*>(a.dqc_hi + off)[gg] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          reinterpret_cast<uint4*>(a.dqc_lo + off)[gg] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
       }
     }
@@ -891,6 +943,7 @@ extern "C" int cdetr_rcda_bwd_q_tc(int B, int L, int H, int W, int E, int nh, co
   a.dqc_hi = reinterpret_cast<__nv_bfloat16*>(dqc.base); a.dqc_lo = a.dqc_hi + dqc.plane;
   a.ld_g = dqr.ld;
   a.idesc = make_idesc_bf16_f32(TQ, 256, 0, 0);
+  a.idesc_q = make_idesc_bf16_f32(TQ, 32, 0, 1);
   const size_t smem = 2 * V_PLANE_BYTES + 4 * A_PLANE_BYTES + 4 * 32 * TQ * sizeof(float) + 128 + 1024;
   static bool once = false;
   if (!once) {
