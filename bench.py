@@ -322,9 +322,24 @@ def run_ours(args):
 
     # ---- e2e: public API from pinned host buffers, H2D + loss D2H inside the timed region.  With a captured
     # step the host copies land in the static input tensors the graph reads, then the graph is replayed.
+    # Input pipeline of the captured path (what a training loop with a prefetching loader does): the pinned host batch of
+    # step i+1 is copied to a device staging buffer on a copy stream while step i computes; step i+1 starts with a
+    # device-to-device move into the tensors the graph reads.  Every step's H2D copy and loss read are inside the
+    # timed region.
+    copy_stream = torch.cuda.Stream()
+    img_stage = torch.empty_like(img_d)
+    h2d_done = torch.cuda.Event()
+
+    def prefetch_inputs():
+        copy_stream.wait_stream(torch.cuda.current_stream())   # the previous d2d move has consumed the staging buffer
+        with torch.cuda.stream(copy_stream):
+            img_stage.copy_(img_h, non_blocking=True)
+            h2d_done.record(copy_stream)
+
     def e2e_step():
         if graph is not None:
-            img_d.copy_(img_h, non_blocking=True)
+            torch.cuda.current_stream().wait_event(h2d_done)
+            img_d.copy_(img_stage, non_blocking=True)
             if st == 2:
                 for t, b in zip(targets, tb_h):
                     t["boxes"].copy_(b, non_blocking=True)
@@ -334,6 +349,7 @@ def run_ours(args):
             graph.replay()
             if world > 1:
                 model.allreduce_grads(dist.group.WORLD)
+            prefetch_inputs()          # next step's image batch travels while this step computes
             return g_loss.item()
         img = img_h.to(dev, non_blocking=True)
         model.zero_grad(set_to_none=True)
@@ -351,12 +367,15 @@ def run_ours(args):
             model.allreduce_grads(dist.group.WORLD)
         return loss.item()
 
+    if graph is not None:
+        prefetch_inputs()
     for _ in range(2):
         e2e_step()
     barrier()
     e0.record()
     for _ in range(args.steps):
         e2e_step()
+    torch.cuda.current_stream().wait_stream(copy_stream)   # the K-th prefetch copy also ends inside the timed region
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
