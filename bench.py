@@ -330,8 +330,22 @@ def run_ours(args):
     img_stage = torch.empty_like(img_d)
     h2d_done = torch.cuda.Event()
 
+    loss_pin = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {"n": 0}
+
+    def flush_loss():   # read the last step's loss (end of a run of e2e steps)
+        if graph is not None and e2e_state["n"] >= 1:
+            slot = (e2e_state["n"] - 1) & 1
+            loss_ev[slot].synchronize()
+            e2e_state["n"] = 0
+            return float(loss_pin[slot])
+        return None
+
+    stage_free = torch.cuda.Event()
+
     def prefetch_inputs():
-        copy_stream.wait_stream(torch.cuda.current_stream())   # the previous d2d move has consumed the staging buffer
+        copy_stream.wait_event(stage_free)   # the d2d move of the running step has consumed the staging buffer
         with torch.cuda.stream(copy_stream):
             img_stage.copy_(img_h, non_blocking=True)
             h2d_done.record(copy_stream)
@@ -340,6 +354,7 @@ def run_ours(args):
         if graph is not None:
             torch.cuda.current_stream().wait_event(h2d_done)
             img_d.copy_(img_stage, non_blocking=True)
+            stage_free.record()
             if st == 2:
                 for t, b in zip(targets, tb_h):
                     t["boxes"].copy_(b, non_blocking=True)
@@ -350,7 +365,16 @@ def run_ours(args):
             if world > 1:
                 model.allreduce_grads(dist.group.WORLD)
             prefetch_inputs()          # next step's image batch travels while this step computes
-            return g_loss.item()
+            # the loss leaves through an asynchronous copy into pinned memory; the host reads the PREVIOUS step's
+            # value while this step runs (one device->host read per step, none of them skipped: see flush_loss)
+            slot = e2e_state["n"] & 1
+            loss_pin[slot].copy_(g_loss, non_blocking=True)
+            loss_ev[slot].record()
+            e2e_state["n"] += 1
+            if e2e_state["n"] >= 2:
+                loss_ev[slot ^ 1].synchronize()
+                return float(loss_pin[slot ^ 1])
+            return None
         img = img_h.to(dev, non_blocking=True)
         model.zero_grad(set_to_none=True)
         if st == 2:
@@ -368,13 +392,16 @@ def run_ours(args):
         return loss.item()
 
     if graph is not None:
+        stage_free.record()
         prefetch_inputs()
     for _ in range(2):
         e2e_step()
+    flush_loss()
     barrier()
     e0.record()
     for _ in range(args.steps):
         e2e_step()
+    flush_loss()                                           # the K-th loss is read inside the timed region too
     torch.cuda.current_stream().wait_stream(copy_stream)   # the K-th prefetch copy also ends inside the timed region
     e1.record()
     barrier()
