@@ -73,37 +73,6 @@ __device__ __forceinline__ void write_operand_row32(uint8_t* dst, uint32_t plane
   }
 }
 
-__device__ __forceinline__ void softmax32(const float* __restrict__ qv, const float* __restrict__ Ks, int n,
-                                          const uint8_t* __restrict__ mask, float (&p)[32]) {
-  float mx = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    float s = -INFINITY;
-    if (k < n && !(mask && mask[k])) {
-      const float4* kp = reinterpret_cast<const float4*>(Ks + k * HD);
-      float s0 = 0.0f, s1 = 0.0f;
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        const float4 t = kp[j], u = kp[j + 1];
-        s0 += qv[4 * j] * t.x + qv[4 * j + 1] * t.y + qv[4 * j + 2] * t.z + qv[4 * j + 3] * t.w;
-        s1 += qv[4 * j + 4] * u.x + qv[4 * j + 5] * u.y + qv[4 * j + 6] * u.z + qv[4 * j + 7] * u.w;
-      }
-      s = s0 + s1;
-    }
-    p[k] = s;
-    mx = fmaxf(mx, s);
-  }
-  float sum = 0.0f;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    p[k] = expf(p[k] - mx);
-    sum += p[k];
-  }
-  const float inv = 1.0f / sum;
-#pragma unroll
-  for (int k = 0; k < 32; ++k) p[k] *= inv;
-}
-
 __global__ void __launch_bounds__(320, 1)
 rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
   pdl_trigger();   // light successors (launch_light) may pre-launch; they wait for this grid to finish
