@@ -8,8 +8,12 @@
 //               bf16 passes (hi*lo, lo*hi, hi*hi), fp32 accumulation in one of two 256-column TMEM buffers
 //   warps 2-9   two groups of four warps, each group owns one 128-query tile and one 256-column TMEM buffer (the
 //               tensor core works on one tile while the other tile's epilogue runs; V is staged once for both);
-//               one query per thread: both softmaxes (fp32, CUDA cores; logits are 128x32 per side), A_r written
-//               to shared memory as the split-bf16 A operand (manual SWIZZLE_64B), then the epilogue:
+//               one query per thread.  The logits q K^T of both sides are tensor-core products too: the thread
+//               writes its scaled q row as a split-bf16 A operand row, the MMA warp multiplies the group's
+//               [128 x 32] operand with the [32 keys x 32] key tile (staged once as a split-bf16 B operand) into the
+//               first 32 TMEM columns of the group's buffer and the thread reads its logit row back
+//               (tcgen05.ld.x32); the two softmaxes stay fp32 on the CUDA cores, A_r goes to shared memory as the
+//               split-bf16 A operand of the main contraction (manual SWIZZLE_64B), then the epilogue:
 //               tcgen05.ld of T[q, h, 0:32] and acc += A_c[q,h] * T   (the only CUDA-core FMAs: 1/32 of the MACs)
 // The reference materialises [B*heads, L, W, 32] in HBM (A2/models/row_column_decoupled_attention.py:262-291);
 // here it lives in TMEM only.  Limits of this kernel: H, W <= 32 (512x512 inputs); larger maps use rcda.cu.
