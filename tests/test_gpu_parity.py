@@ -13,8 +13,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _run(script, *args, timeout=900):
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", script), *args], capture_output=True, text=True, timeout=timeout)
+def _run(script, *args, timeout=900, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", script), *args], capture_output=True, text=True, timeout=timeout, env=e)
     tail = (p.stdout + p.stderr)[-4000:]
     assert p.returncode == 0, tail
     return p.stdout, tail
@@ -23,6 +25,22 @@ def _run(script, *args, timeout=900):
 def test_tcgen05_gemm_all_shapes_and_epilogues():
     out, tail = _run("gpu_gemm_probe.py")
     assert "FAILS 0" in out, tail
+
+
+@pytest.mark.parametrize("env", [{"CDETR_GEMM_PAIR": "1"}, {"CDETR_GEMM_PAIR": "0", "CDETR_GEMM_TMA_EPI": "0"}],
+                         ids=["cta_pairs_forced", "single_cta_generic_epilogue"])
+def test_tcgen05_gemm_alternate_paths(env):
+    """The same shape / epilogue matrix with the tile heuristics overridden: CTA pairs (cta_group::2) on every eligible
+    shape incl. the ragged ones, and the single-CTA kernel with the generic per-thread epilogue (the fallback for
+    outputs the TMA unit cannot address)."""
+    out, tail = _run("gpu_gemm_probe.py", env=env)
+    assert "FAILS 0" in out, tail
+
+
+def test_cuda_core_attention_fallbacks():
+    """CDETR_MHA_LEGACY=1: the CUDA-core decoder self-attention (used when a head does not fit shared memory, C4)."""
+    out, tail = _run("gpu_ops_probe.py", env={"CDETR_MHA_LEGACY": "1"})
+    assert "FAILS 0 " in out, tail
 
 
 def test_every_kernel_against_torch_and_oracle():
