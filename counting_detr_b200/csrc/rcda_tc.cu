@@ -307,8 +307,13 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
             tmem_ld_32x32b_x32(taddr_row + (uint32_t)hi * 32u, t);
             tmem_ld_wait();
             const float coef = ac[p * 8 + hi];
+            const float2 coef2 = make_float2(coef, coef);
 #pragma unroll
-            for (int c = 0; c < HD; ++c) acc[c] += coef * __uint_as_float(t[c]);
+            for (int c = 0; c < HD; c += 2) {   // packed FFMA2 (sm_100): two fp32 FMAs per issue slot, same rounding
+              const float2 r2 = __ffma2_rn(coef2, make_float2(__uint_as_float(t[c]), __uint_as_float(t[c + 1])),
+                                           make_float2(acc[c], acc[c + 1]));
+              acc[c] = r2.x; acc[c + 1] = r2.y;
+            }
           }
           tc_fence_before();
           __syncwarp();
@@ -518,16 +523,16 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
             tmem_ld_32x32b_x32(taddr_row + (uint32_t)hi * 32u, t);
             tmem_ld_wait();
             const float cc = acg[(p * 8 + hi) * TQ + r];
-            float s0 = 0.0f, s1 = 0.0f;
+            float2 s2 = make_float2(0.0f, 0.0f);
+            const float2 cc2 = make_float2(cc, cc);
 #pragma unroll
-            for (int w = 0; w < 32; w += 2) {
-              const float g0 = __uint_as_float(t[w]), g1 = __uint_as_float(t[w + 1]);
-              s0 += ar[w] * g0;
-              s1 += ar[w + 1] * g1;
-              dar[w] += cc * g0;
-              dar[w + 1] += cc * g1;
+            for (int w = 0; w < 32; w += 2) {   // packed FFMA2: (s0, s1) += A_r pair * G pair; dA_r pair += A_c * G pair
+              const float2 g2 = make_float2(__uint_as_float(t[w]), __uint_as_float(t[w + 1]));
+              s2 = __ffma2_rn(make_float2(ar[w], ar[w + 1]), g2, s2);
+              const float2 d2 = __ffma2_rn(cc2, g2, make_float2(dar[w], dar[w + 1]));
+              dar[w] = d2.x; dar[w + 1] = d2.y;
             }
-            dacg[(p * 8 + hi) * TQ + r] = s0 + s1;
+            dacg[(p * 8 + hi) * TQ + r] = s2.x + s2.y;
           }
           tc_fence_before();
           __syncwarp();
@@ -776,8 +781,14 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
         for (int j = 0; j < 4; ++j) {        // 4 chunks of 8 queries
           float pv[8];
           const float4 c0 = cr[2 * j], c1 = cr[2 * j + 1], r0 = rr[2 * j], r1 = rr[2 * j + 1];
-          pv[0] = c0.x * r0.x; pv[1] = c0.y * r0.y; pv[2] = c0.z * r0.z; pv[3] = c0.w * r0.w;
-          pv[4] = c1.x * r1.x; pv[5] = c1.y * r1.y; pv[6] = c1.z * r1.z; pv[7] = c1.w * r1.w;
+          {
+            const float2 p01 = __fmul2_rn(make_float2(c0.x, c0.y), make_float2(r0.x, r0.y));
+            const float2 p23 = __fmul2_rn(make_float2(c0.z, c0.w), make_float2(r0.z, r0.w));
+            const float2 p45 = __fmul2_rn(make_float2(c1.x, c1.y), make_float2(r1.x, r1.y));
+            const float2 p67 = __fmul2_rn(make_float2(c1.z, c1.w), make_float2(r1.z, r1.w));
+            pv[0] = p01.x; pv[1] = p01.y; pv[2] = p23.x; pv[3] = p23.y;
+            pv[4] = p45.x; pv[5] = p45.y; pv[6] = p67.x; pv[7] = p67.y;
+          }
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
