@@ -119,3 +119,18 @@ def test_data_parallel_gradient_average_gloo_world2():
     assert [r[1] for r in res] == [1.5, 1.5] and [r[2] for r in res] == [1.5, 1.5]
     assert [r[3] for r in res] == [75.0, 75.0]
     assert res[0][4] != res[1][4]
+
+
+def test_bench_attention_flop_accounting_matches_survey():
+    """bench.py's roofline_attention uses SURVEY.md §8d's algorithmic count: at S=512, Q=300 the attention cores of one
+    image forward are 5.108 GFLOP (6 x [RCDA(1024,32,32) + RCDA(300,32,32) + MHA(300)]), and backward is 2x forward."""
+    import bench
+    E, nh = 256, 8
+    fwd = 6 * (bench.attention_macs("cdetr_rcda_fwd_tc", (1, 1024, 32, 32, E, nh))
+               + bench.attention_macs("cdetr_rcda_fwd_tc", (1, 300, 32, 32, E, nh))
+               + bench.attention_macs("cdetr_mha_fwd", (1, 300, E, nh)))
+    assert abs(2 * fwd / 1e9 - 5.108) < 2e-3
+    bwd = 6 * (sum(bench.attention_macs(n, (1, L_, 32, 32, E, nh)) for L_ in (1024, 300)
+                   for n in ("cdetr_rcda_bwd_q_tc", "cdetr_rcda_bwd_v_tc", "cdetr_rcda_bwd_k"))
+               + bench.attention_macs("cdetr_mha_bwd", (1, 300, E, nh)))
+    assert bwd == 2 * fwd
