@@ -1052,14 +1052,20 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   bool resident = false;
   if (const char* e = getenv("CDETR_GEMM_RESIDENT")) {
     const int f = atoi(e);
-    if (f == 1) resident = !pair && !nt && !conv && splits == 1 && (uint32_t)num_kb * b_bytes + 2 * a_bytes <= smem_budget;
+    if (f == 1) resident = !pair && !nt && !conv && splits == 1 && (uint32_t)num_kb * b_bytes + 2 * a_bytes + 8u * epi_buf <= smem_max;
   }
   ka.resident_b = 0;
   ka.tiles_per_cta = 0;
   size_t operand_bytes = (size_t)stages * stage_bytes;
   if (resident) {
     const uint32_t slab = (uint32_t)num_kb * b_bytes;
-    int st = (int)((smem_budget - slab) / a_bytes);
+    uint32_t budget = smem_budget;
+    if (tma_epi && epi_nb == 2 && budget < slab + 2 * a_bytes) {   // trade the second staging buffer for A stages
+      epi_nb = 1;
+      staging_bytes = 8u * epi_buf;
+      budget = smem_max - staging_bytes;
+    }
+    int st = budget > slab ? (int)((budget - slab) / a_bytes) : 0;
     if (st > MAX_STAGES) st = MAX_STAGES;
     if (const char* e = getenv("CDETR_GEMM_STAGES")) {
       const int f = atoi(e);

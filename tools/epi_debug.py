@@ -25,12 +25,13 @@ def timed(fn):
     return sorted(ts)[1]
 
 
-for (M, N, K, bn) in [(16384, 1024, 256, 0), (16384, 1024, 256, 128), (16384, 256, 256, 0), (65536, 512, 128, 0), (16384, 2048, 512, 0)]:
-    A = L.to_split(torch.randn(M, K, device=dev)); B = L.to_split(torch.randn(N, K, device=dev))
-    outs = torch.empty(2, M, N, device=dev, dtype=torch.bfloat16); bias = torch.randn(N, device=dev)
-    res = []
-    for mode in ("0", "1", "2", "3"):
-        os.environ["CDETR_GEMM_EPI_DEBUG"] = mode
-        res.append(timed(lambda: L.gemm(A, B, M, N, K, out_split=outs, bias=bias, relu=True, block_n=bn)))
-    os.environ.pop("CDETR_GEMM_EPI_DEBUG")
-    print(f"M={M} N={N} K={K} bn={bn or 'auto'}: full {res[0]:.1f} us | no stores {res[1]:.1f} | no staging {res[2]:.1f} | TMEM read only {res[3]:.1f}", flush=True)
+if __name__ == "__main__":
+  for (M, N, K, bn) in [(16384, 1024, 256, 0), (16384, 1024, 256, 128), (16384, 256, 256, 0), (65536, 512, 128, 0), (16384, 2048, 512, 0)]:
+      A = L.to_split(torch.randn(M, K, device=dev)); B = L.to_split(torch.randn(N, K, device=dev))
+      outs = torch.empty(2, M, N, device=dev, dtype=torch.bfloat16); bias = torch.randn(N, device=dev)
+      res = []
+      for mode in ("0", "1", "2", "3"):
+          os.environ["CDETR_GEMM_EPI_DEBUG"] = mode
+          res.append(timed(lambda: L.gemm(A, B, M, N, K, out_split=outs, bias=bias, relu=True, block_n=bn)))
+      os.environ.pop("CDETR_GEMM_EPI_DEBUG")
+      print(f"M={M} N={N} K={K} bn={bn or 'auto'}: full {res[0]:.1f} us | no stores {res[1]:.1f} | no staging {res[2]:.1f} | TMEM read only {res[3]:.1f}", flush=True)
