@@ -41,6 +41,10 @@ def test_sass_uses_tcgen05_and_tma(built_lib):
     out = subprocess.run(["cuobjdump", "-sass", built_lib.LIB_PATH], capture_output=True, text=True).stdout
     assert re.search(r"UTC\w*MMA", out), "no tcgen05.mma in SASS"
     assert "LDTM" in out and "UTMALDG" in out
+    # CTA pairs (cta_group::2 MMA + TMA loads credited to the leader), TMA-store / reduce-add epilogue,
+    # warp-level tensor-core attention (mma.sync) and packed fp32x2 FMAs
+    for mnemonic in ("UTCHMMA.2CTA", "UTMALDG.3D.2CTA", "UTMASTG", "UTMAREDG", "HMMA.16816.F32.BF16", "FFMA2"):
+        assert mnemonic in out, f"{mnemonic} missing from SASS"
 
 
 def test_state_dict_layout_and_trainable_flags():
