@@ -6,8 +6,8 @@
 //
 // One CTA per (sample, head); K / V (forward, query-side backward) or Q / dO (key-side backward) of the head are
 // converted once to split-bf16 in shared memory in the two layouts the MMA B operand needs:
-//   row-major   X[row][KP]   : B[k = channel][n = row]  (S = Q K^T, dP = dO V^T, S^T = K Q^T, dP^T = V dO^T)
-//   transposed  Xt[chan][PT] : B[k = row][n = channel]  (O = P V, dQ = dS K, dV = P^T dO, dK = dS^T Q)
+//   X[row][KP] read directly        : B[k = channel][n = row]  (S = Q K^T, dP = dO V^T, S^T = K Q^T, dP^T = V dO^T)
+//   X[row][KP] through ldmatrix.trans: B[k = row][n = channel]  (O = P V, dQ = dS K, dV = P^T dO, dK = dS^T Q)
 // Each warp owns strips of 16 queries (or keys) and walks the other dimension in chunks of 64 with the accumulator
 // fragments of S / P re-used directly as the A fragments of the second product (no shared-memory round trip).
 // Reference: A2/models/transformer.py:366-372 (nn.MultiheadAttention in the decoder layer) and its autograd.
@@ -49,24 +49,6 @@ __device__ __forceinline__ void stage_rowmajor(const float* __restrict__ src, in
     *reinterpret_cast<uint2*>(lo + r * KP + c4 * 4) = make_uint2(l0, l1);
   }
 }
-// same rows -> transposed split-bf16 smem [32][PT] (element (c, r)); rows >= L are zero
-__device__ __forceinline__ void stage_transposed(const float* __restrict__ src, int64_t ld, int64_t row0, int L, int Lp,
-                                                 int col0, __nv_bfloat16* hi, __nv_bfloat16* lo, int PT) {
-  for (int i = threadIdx.x; i < Lp * 8; i += NTHREADS) {
-    const int r = i >> 3, c4 = i & 7;
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < L) t = __ldg(reinterpret_cast<const float4*>(src + (row0 + r) * ld + col0 + c4 * 4));
-    const float v[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      __nv_bfloat16 h, l;
-      split_bf16(v[e], h, l);
-      hi[(c4 * 4 + e) * PT + r] = h;
-      lo[(c4 * 4 + e) * PT + r] = l;
-    }
-  }
-}
-
 // A fragments (both k-steps of the 32 channels) of two rows of a global fp32 matrix, scaled, as split-bf16
 __device__ __forceinline__ void load_a_frags(const float* __restrict__ p0, const float* __restrict__ p1, bool ok0,
                                              bool ok1, float scale, int t, uint32_t (&ah)[2][4], uint32_t (&al)[2][4]) {
@@ -104,9 +86,19 @@ __device__ __forceinline__ void gemm_rows_x_rowmajor(float (&c)[8][4], const uin
     }
   }
 }
-// o[4][4] (16 rows x 32 channels) += P[16 x 64] Xt[:, k0..k0+63]^T, P given as accumulator fragments p[8][4]
-__device__ __forceinline__ void gemm_p_x_transposed(float (&o)[4][4], const float (&p)[8][4], const __nv_bfloat16* Xth,
-                                                    const __nv_bfloat16* Xtl, int PT, int k0, int ntn, int g, int t) {
+// B fragments of a [16 k x 8 n] block of a ROW-MAJOR staged matrix X[k][n] (k = row, pitch KP): ldmatrix with .trans
+// hands thread (g, t) the pairs X[k0 + 2t .. 2t+1][n0 + g] (b0) and X[k0 + 8 + 2t ..][n0 + g] (b1), i.e. the "col"
+// operand layout of mma.m16n8k16 without a transposed copy in shared memory.
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& b0, uint32_t& b1, const __nv_bfloat16* X, int k0, int n0,
+                                                  int lane) {
+  const __nv_bfloat16* p = X + (k0 + (lane & 15)) * KP + n0;   // lanes 0-7: rows k0..k0+7, lanes 8-15: rows k0+8..k0+15
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+               : "=r"(b0), "=r"(b1)
+               : "r"(smem_u32(p)));
+}
+// o[4][4] (16 rows x 32 channels) += P[16 x 64] X[k0..k0+63, :], P given as accumulator fragments p[8][4], X row-major
+__device__ __forceinline__ void gemm_p_x_rows(float (&o)[4][4], const float (&p)[8][4], const __nv_bfloat16* Xh,
+                                              const __nv_bfloat16* Xl, int k0, int ntn, int lane) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
     if (2 * kk < ntn) {
@@ -117,11 +109,9 @@ __device__ __forceinline__ void gemm_p_x_transposed(float (&o)[4][4], const floa
       split_bf16_pair(p[2 * kk + 1][2], p[2 * kk + 1][3], ah[3], al[3]);
 #pragma unroll
       for (int dt = 0; dt < 4; ++dt) {
-        const int off = (dt * 8 + g) * PT + k0 + 16 * kk + 2 * t;
-        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(Xth + off);
-        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(Xth + off + 8);
-        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(Xtl + off);
-        const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(Xtl + off + 8);
+        uint32_t bh0, bh1, bl0, bl1;
+        ldmatrix_x2_trans(bh0, bh1, Xh, k0 + 16 * kk, dt * 8, lane);
+        ldmatrix_x2_trans(bl0, bl1, Xl, k0 + 16 * kk, dt * 8, lane);
         mma3(o[dt], ah, al, bh0, bh1, bl0, bl1);
       }
     }
@@ -161,13 +151,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mha_fwd_tc_kernel(const MhaArgs a
   extern __shared__ __align__(16) uint8_t smem[];
   __nv_bfloat16* Kh = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* Kl = Kh + Lp * KP;
-  __nv_bfloat16* Vth = Kl + Lp * KP;
-  __nv_bfloat16* Vtl = Vth + HD * PT;
+  __nv_bfloat16* Vh = Kl + Lp * KP;
+  __nv_bfloat16* Vl = Vh + Lp * KP;
   const int head = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int64_t row0 = (int64_t)b * a.L;
   stage_rowmajor(a.k, a.ldq, row0, a.L, Lp, head * HD, Kh, Kl);
-  stage_transposed(a.v, a.ldq, row0, a.L, Lp, head * HD, Vth, Vtl, PT);
+  stage_rowmajor(a.v, a.ldq, row0, a.L, Lp, head * HD, Vh, Vl);
   __syncthreads();
   const float scale = rsqrtf((float)HD);
   for (int strip = warp + NWARPS * blockIdx.z; strip * 16 < a.L; strip += NWARPS * gridDim.z) {
@@ -212,7 +202,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mha_fwd_tc_kernel(const MhaArgs a
       m0 = mn0; m1 = mn1;
 #pragma unroll
       for (int dt = 0; dt < 4; ++dt) { o[dt][0] *= c0; o[dt][1] *= c0; o[dt][2] *= c1; o[dt][3] *= c1; }
-      gemm_p_x_transposed(o, s, Vth, Vtl, PT, j0, ntn, g, t);
+      gemm_p_x_rows(o, s, Vh, Vl, j0, ntn, lane);
     }
     l0 = quad_sum(l0); l1 = quad_sum(l1);
     store_rows_split(a.o_hi, a.o_lo, (row0 + i0) * a.ld_o + head * HD, (row0 + i1) * a.ld_o + head * HD, ok0, ok1, o,
@@ -234,14 +224,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_q_tc_kernel(const MhaArgs
   __nv_bfloat16* Kl = Kh + Lp * KP;
   __nv_bfloat16* Vh = Kl + Lp * KP;
   __nv_bfloat16* Vl = Vh + Lp * KP;
-  __nv_bfloat16* Kth = Vl + Lp * KP;
-  __nv_bfloat16* Ktl = Kth + HD * PT;
   const int head = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int64_t row0 = (int64_t)b * a.L;
   stage_rowmajor(a.k, a.ldq, row0, a.L, Lp, head * HD, Kh, Kl);
   stage_rowmajor(a.v, a.ldq, row0, a.L, Lp, head * HD, Vh, Vl);
-  stage_transposed(a.k, a.ldq, row0, a.L, Lp, head * HD, Kth, Ktl, PT);
   __syncthreads();
   const float scale = rsqrtf((float)HD);
   const int64_t bh = ((int64_t)b * a.nh + head) * a.L;
@@ -301,7 +288,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_q_tc_kernel(const MhaArgs
         s[nt][0] = p0 * (dp[nt][0] - D0); s[nt][1] = p1 * (dp[nt][1] - D0);
         s[nt][2] = p2 * (dp[nt][2] - D1); s[nt][3] = p3 * (dp[nt][3] - D1);
       }
-      gemm_p_x_transposed(dq, s, Kth, Ktl, PT, j0, ntn, g, t);
+      gemm_p_x_rows(dq, s, Kh, Kl, j0, ntn, lane);
     }
     store_rows_split(a.dq_hi, a.dq_lo, (row0 + i0) * a.ld_g + head * HD, (row0 + i1) * a.ld_g + head * HD, ok0, ok1, dq,
                      scale, scale, t);
@@ -317,11 +304,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_kv_tc_kernel(const MhaArg
   __nv_bfloat16* Ql = Qh + Lp * KP;
   __nv_bfloat16* Dh = Ql + Lp * KP;
   __nv_bfloat16* Dl = Dh + Lp * KP;
-  __nv_bfloat16* Qth = Dl + Lp * KP;
-  __nv_bfloat16* Qtl = Qth + HD * PT;
-  __nv_bfloat16* Dth = Qtl + HD * PT;
-  __nv_bfloat16* Dtl = Dth + HD * PT;
-  float* lses = reinterpret_cast<float*>(Dtl + HD * PT);
+  float* lses = reinterpret_cast<float*>(Dl + Lp * KP);
   float* dsums = lses + Lp;
   const int head = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -329,8 +312,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_kv_tc_kernel(const MhaArg
   const int64_t bh = ((int64_t)b * a.nh + head) * a.L;
   stage_rowmajor(a.q, a.ldq, row0, a.L, Lp, head * HD, Qh, Ql);
   stage_rowmajor(a.d_o, a.E, row0, a.L, Lp, head * HD, Dh, Dl);
-  stage_transposed(a.q, a.ldq, row0, a.L, Lp, head * HD, Qth, Qtl, PT);
-  stage_transposed(a.d_o, a.E, row0, a.L, Lp, head * HD, Dth, Dtl, PT);
   for (int i = threadIdx.x; i < Lp; i += NTHREADS) {
     lses[i] = i < a.L ? a.lse[bh + i] : INFINITY;   // padded queries: P = exp(s - inf) = 0
     dsums[i] = i < a.L ? a.dsum[bh + i] : 0.f;
@@ -364,7 +345,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_kv_tc_kernel(const MhaArg
           s[nt][2] = expf(s[nt][2] - ls.x); s[nt][3] = expf(s[nt][3] - ls.y);
         }
       }
-      gemm_p_x_transposed(dv, s, Dth, Dtl, PT, i0, ntn, g, t);     // dV += P^T dO
+      gemm_p_x_rows(dv, s, Dh, Dl, i0, ntn, lane);                 // dV += P^T dO
       gemm_rows_x_rowmajor(dp, vh, vl, Dh, Dl, i0, ntn, g, t);     // dP^T[key, query] = V dO^T
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
@@ -374,7 +355,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_kv_tc_kernel(const MhaArg
           s[nt][2] *= dp[nt][2] - ds.x; s[nt][3] *= dp[nt][3] - ds.y;
         }
       }
-      gemm_p_x_transposed(dk, s, Qth, Qtl, PT, i0, ntn, g, t);     // dK += dS^T Q
+      gemm_p_x_rows(dk, s, Qh, Ql, i0, ntn, lane);                 // dK += dS^T Q
     }
     const int64_t off0 = (row0 + j0r) * a.ld_g + head * HD, off1 = (row0 + j1r) * a.ld_g + head * HD;
     store_rows_split(a.dk_hi, a.dk_lo, off0, off1, ok0, ok1, dk, scale, scale, t);
@@ -387,9 +368,9 @@ int transposed_pitch(int Lp) {   // even, >= Lp + 2, (pitch / 2) % 8 == 4: confl
   while (p % 16 != 8) ++p;
   return p;
 }
-size_t smem_fwd(int Lp, int PT) { return (size_t)(2 * Lp * KP + 2 * HD * PT) * 2; }
-size_t smem_bwd_q(int Lp, int PT) { return (size_t)(4 * Lp * KP + 2 * HD * PT) * 2; }
-size_t smem_bwd_kv(int Lp, int PT) { return (size_t)(4 * Lp * KP + 4 * HD * PT) * 2 + (size_t)2 * Lp * 4; }
+size_t smem_fwd(int Lp, int) { return (size_t)(4 * Lp * KP) * 2; }
+size_t smem_bwd_q(int Lp, int) { return (size_t)(4 * Lp * KP) * 2; }
+size_t smem_bwd_kv(int Lp, int) { return (size_t)(4 * Lp * KP) * 2 + (size_t)2 * Lp * 4; }
 constexpr size_t SMEM_MAX = 227 * 1024;
 
 }  // namespace
