@@ -146,7 +146,7 @@ __device__ __forceinline__ void store_rows_split(__nv_bfloat16* hi, __nv_bfloat1
 
 // ------------------------------------------------------------------------------------------------ forward
 // grid (nh, B, nsplit); strips of 16 queries round-robin over (warp, blockIdx.z)
-__global__ void __launch_bounds__(NTHREADS, 1) mha_fwd_tc_kernel(const MhaArgs a, const int Lp, const int PT) {
+__global__ void __launch_bounds__(NTHREADS, 1) mha_fwd_tc_kernel(const MhaArgs a, const int Lp) {
   pdl_trigger();   // light successors (launch_light) may pre-launch; they wait for this grid to finish
   extern __shared__ __align__(16) uint8_t smem[];
   __nv_bfloat16* Kh = reinterpret_cast<__nv_bfloat16*>(smem);
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mha_fwd_tc_kernel(const MhaArgs a
 
 // ------------------------------------------------------------------------------------------------ backward, queries
 // D_i = dO_i . O_i (written to dsum for the key-side kernel), dq_i = scale * sum_j dS_ij k_j
-__global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_q_tc_kernel(const MhaArgs a, const int Lp, const int PT) {
+__global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_q_tc_kernel(const MhaArgs a, const int Lp) {
   pdl_trigger();   // light successors (launch_light) may pre-launch; they wait for this grid to finish
   extern __shared__ __align__(16) uint8_t smem[];
   __nv_bfloat16* Kh = reinterpret_cast<__nv_bfloat16*>(smem);
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_q_tc_kernel(const MhaArgs
 
 // ------------------------------------------------------------------------------------------------ backward, keys
 // dv_j = sum_i P_ij dO_i ;  dk_j = scale * sum_i dS_ij q_i     (strips of 16 keys, chunks of 64 queries)
-__global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_kv_tc_kernel(const MhaArgs a, const int Lp, const int PT) {
+__global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_kv_tc_kernel(const MhaArgs a, const int Lp) {
   pdl_trigger();   // light successors (launch_light) may pre-launch; they wait for this grid to finish
   extern __shared__ __align__(16) uint8_t smem[];
   __nv_bfloat16* Qh = reinterpret_cast<__nv_bfloat16*>(smem);
@@ -363,50 +363,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) mha_bwd_kv_tc_kernel(const MhaArg
   }
 }
 
-int transposed_pitch(int Lp) {   // even, >= Lp + 2, (pitch / 2) % 8 == 4: conflict-free B-fragment loads
-  int p = Lp + 2;
-  while (p % 16 != 8) ++p;
-  return p;
-}
-size_t smem_fwd(int Lp, int) { return (size_t)(4 * Lp * KP) * 2; }
-size_t smem_bwd_q(int Lp, int) { return (size_t)(4 * Lp * KP) * 2; }
-size_t smem_bwd_kv(int Lp, int) { return (size_t)(4 * Lp * KP) * 2 + (size_t)2 * Lp * 4; }
+size_t smem_fwd(int Lp) { return (size_t)(4 * Lp * KP) * 2; }
+size_t smem_bwd_q(int Lp) { return (size_t)(4 * Lp * KP) * 2; }
+size_t smem_bwd_kv(int Lp) { return (size_t)(4 * Lp * KP) * 2 + (size_t)2 * Lp * 4; }
 constexpr size_t SMEM_MAX = 227 * 1024;
 
 }  // namespace
 
 // Host launchers used by cdetr_mha_fwd / cdetr_mha_bwd (mha.cu).  Return 1 when the head does not fit in shared
-// memory (L > ~380): the caller then falls back to the CUDA-core kernels.
+// memory (L > ~700): the caller then falls back to the CUDA-core kernels.
 int mha_tc_fits(int L) {
-  const int Lp = (L + 15) / 16 * 16, PT = transposed_pitch(Lp);
-  return smem_bwd_kv(Lp, PT) <= SMEM_MAX && smem_bwd_q(Lp, PT) <= SMEM_MAX ? 1 : 0;
+  const int Lp = (L + 15) / 16 * 16;
+  return smem_bwd_kv(Lp) <= SMEM_MAX && smem_bwd_q(Lp) <= SMEM_MAX ? 1 : 0;
 }
 int mha_fwd_tc_launch(const MhaArgs& a, cudaStream_t s) {
-  const int Lp = (a.L + 15) / 16 * 16, PT = transposed_pitch(Lp);
-  const size_t smem = smem_fwd(Lp, PT);
+  const int Lp = (a.L + 15) / 16 * 16;
+  const size_t smem = smem_fwd(Lp);
   static size_t configured = 0;
   if (configured < smem) {
     CDETR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     configured = SMEM_MAX;
   }
-  const int strips = (a.L + 15) / 16;
-  const int nsplit = 1;   // (167 registers x 320 threads: one CTA per SM)
-  (void)strips;
-  mha_fwd_tc_kernel<<<dim3(a.nh, a.B, nsplit), NTHREADS, smem, s>>>(a, Lp, PT);
+  mha_fwd_tc_kernel<<<dim3(a.nh, a.B, 1), NTHREADS, smem, s>>>(a, Lp);   // ~160 registers x 320 threads: one CTA per SM
   CDETR_CHECK_LAUNCH();
   return 0;
 }
 int mha_bwd_tc_launch(const MhaArgs& a, cudaStream_t s) {
-  const int Lp = (a.L + 15) / 16 * 16, PT = transposed_pitch(Lp);
+  const int Lp = (a.L + 15) / 16 * 16;
   static bool configured = false;
   if (!configured) {
     CDETR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_q_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     CDETR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
     configured = true;
   }
-  mha_bwd_q_tc_kernel<<<dim3(a.nh, a.B, 1), NTHREADS, smem_bwd_q(Lp, PT), s>>>(a, Lp, PT);
+  mha_bwd_q_tc_kernel<<<dim3(a.nh, a.B, 1), NTHREADS, smem_bwd_q(Lp), s>>>(a, Lp);
   CDETR_CHECK_LAUNCH();
-  mha_bwd_kv_tc_kernel<<<dim3(a.nh, a.B, 1), NTHREADS, smem_bwd_kv(Lp, PT), s>>>(a, Lp, PT);
+  mha_bwd_kv_tc_kernel<<<dim3(a.nh, a.B, 1), NTHREADS, smem_bwd_kv(Lp), s>>>(a, Lp);
   CDETR_CHECK_LAUNCH();
   return 0;
 }
