@@ -155,6 +155,8 @@ _SIGS = {
     "cdetr_box_head_fwd": "pplp",
     "cdetr_box_head_bwd": "ppplpSp",
     "cdetr_scale": "plf",
+    "cdetr_mask_prepare": "piiiiipppp",
+    "cdetr_exemplar_centres": "piiipp",
     "cdetr_rcda_fwd": "iiiiiipppppppppS",
     "cdetr_rcda_fwd_tc": "iiiiiippppSppppS",
     "cdetr_rcda_bwd_q_tc": "iiiiiippSpppppSS",
@@ -166,7 +168,7 @@ _SIGS = {
     "cdetr_mha_bwd": "iiiippplSpppSSS",
     "cdetr_match_cost": "pipppiiifffp",
     "cdetr_lsap": "ppiiipppp",
-    "cdetr_set_loss_fwd": "ppppppppiiipffppppppp",
+    "cdetr_set_loss_fwd": "ppppppppiiipffpppppppp",
     "cdetr_set_loss_bwd": "pppppplppp",
     "cdetr_bbox_loss_fwd": "ppplppp",
     "cdetr_bbox_loss_bwd": "ppplp",

@@ -79,7 +79,8 @@ __global__ void set_loss_fwd_kernel(const float* __restrict__ logits, const floa
                                     float alpha, float* __restrict__ out,
                                     float* __restrict__ g_ce, float* __restrict__ g_bbox,
                                     float* __restrict__ g_giou, float* __restrict__ g_var_box,
-                                    float* __restrict__ g_var_var, unsigned char* __restrict__ matched) {
+                                    float* __restrict__ g_var_var, unsigned char* __restrict__ matched,
+                                    int* __restrict__ status) {
   __shared__ float red[33];
   const int tid = threadIdx.x, nt = blockDim.x;
   // num_boxes = clamp(sum over ranks / world, min 1)  (A2/models/anchor_detr.py:321-325), read from device memory
@@ -183,6 +184,14 @@ __global__ void set_loss_fwd_kernel(const float* __restrict__ logits, const floa
     out[3] = s_giou * inv_nb;
     out[4] = s_card / (float)B;
     out[5] = (mw * s_iw + mh * s_ih + s_log) * inv_nb;
+    // The matcher could not assign (NaN costs: scipy raises ValueError, the reference's GIoU asserts) or an exemplar
+    // centre fell outside the feature map (the reference raises IndexError): no exception can cross a stream, so the
+    // losses turn NaN, which the reference's training loop treats as fatal (A2/engine.py:47-50).  Flag re-armed.
+    if (status != nullptr && *status != 0) {
+      const float qnan = __int_as_float(0x7fc00000);
+      for (int k = 0; k < 6; ++k) out[k] = qnan;
+      *status = 0;
+    }
   }
 }
 
@@ -245,7 +254,7 @@ extern "C" int cdetr_set_loss_fwd(const float* logits, const float* boxes, const
                                   const float* num_boxes_sum, float inv_world, float focal_alpha, float* out6,
                                   float* g_ce, float* g_bbox,
                                   float* g_giou, float* g_var_box, float* g_var_var, unsigned char* matched,
-                                  cdetr_stream_t s) {
+                                  int* status, cdetr_stream_t s) {
   CDETR_CHECK_ARG(logits && boxes && vars && tgt_boxes && tgt_off && idx_q && idx_t && idx_n && out6 && g_ce &&
                       g_bbox && g_giou && g_var_box && g_var_var && matched && B > 0 && Q > 0 && num_boxes_sum &&
                       inv_world > 0,
@@ -253,7 +262,7 @@ extern "C" int cdetr_set_loss_fwd(const float* logits, const float* boxes, const
   set_loss_fwd_kernel<<<1, 1024, 0, STREAM(s)>>>(logits, boxes, vars, tgt_boxes, tgt_off, idx_q, idx_t, idx_n, B,
                                                  Q, Kmax > 0 ? Kmax : 1, num_boxes_sum, inv_world, focal_alpha, out6, g_ce,
                                                  g_bbox,
-                                                 g_giou, g_var_box, g_var_var, matched);
+                                                 g_giou, g_var_box, g_var_var, matched, status);
   CDETR_CHECK_LAUNCH();
   return 0;
 }

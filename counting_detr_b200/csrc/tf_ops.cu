@@ -347,3 +347,79 @@ extern "C" int cdetr_scale(float* x, int64_t n, float a, cdetr_stream_t s) {
   CDETR_CHECK_LAUNCH();
   return 0;
 }
+
+// ------------------------------------------------------------------ padding mask -> feature-level masks + positions
+// A2/models/backbone.py:112 (F.interpolate(m[None].float(), size=x.shape[-2:]).to(bool)[0]: nearest, source index
+// floor(dst * in/out) in fp32, clamped), A2/models/transformer.py:497-503 (mask2pos: positions from the FIRST column /
+// FIRST row of the feature mask: (cumsum(~m) - 0.5) / count), A2/models/row_column_decoupled_attention.py:238-249
+// (key padding taken from mask[:, 0, :] / mask[:, :, 0]).  One CTA per sample; H, W <= 1024.
+namespace {
+__global__ void mask_prepare_kernel(const uint8_t* __restrict__ mask, int S1, int S2, int H, int W,
+                                    uint8_t* __restrict__ mrow, uint8_t* __restrict__ mcol, float* __restrict__ pos_row,
+                                    float* __restrict__ pos_col) {
+  __shared__ float cnt[2];
+  const int b = blockIdx.x;
+  const uint8_t* m = mask + (int64_t)b * S1 * S2;
+  const float sy = (float)S1 / (float)H, sx = (float)S2 / (float)W;
+  // first feature row -> row mask [W]; first feature column -> column mask [H]  (source row / column 0)
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const int xs = min((int)floorf((float)x * sx), S2 - 1);
+    mrow[b * W + x] = m[xs] != 0;
+  }
+  for (int y = threadIdx.x; y < H; y += blockDim.x) {
+    const int ys = min((int)floorf((float)y * sy), S1 - 1);
+    mcol[b * H + y] = m[(int64_t)ys * S2] != 0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {   // serial fp32 cumsum of <= 1024 ones: exact integers, same values as torch.cumsum
+    const int n = threadIdx.x == 0 ? W : H;
+    const uint8_t* mk = threadIdx.x == 0 ? mrow + b * W : mcol + b * H;
+    float* out = threadIdx.x == 0 ? pos_row + b * W : pos_col + b * H;
+    float c = 0.0f;
+    for (int i = 0; i < n; ++i) {
+      c += mk[i] ? 0.0f : 1.0f;
+      out[i] = c;
+    }
+    cnt[threadIdx.x] = c;
+  }
+  __syncthreads();
+  for (int x = threadIdx.x; x < W; x += blockDim.x) pos_row[b * W + x] = __fdiv_rn(__fsub_rn(pos_row[b * W + x], 0.5f), cnt[0]);
+  for (int y = threadIdx.x; y < H; y += blockDim.x) pos_col[b * H + y] = __fdiv_rn(__fsub_rn(pos_col[b * H + y], 0.5f), cnt[1]);
+}
+
+// A2/models/backbone.py:122-128: centre = int((x1*W + x2*W) / 2) in fp32 (truncation), rects of SAMPLE 0 only.
+// Out-of-range centres (the reference raises IndexError for >= 1 and wraps negatives) are clamped and flagged.
+__global__ void exemplar_centres_kernel(const float* __restrict__ rects0, int n_ex, int H, int W, int* __restrict__ yx,
+                                        int* __restrict__ status) {
+  const int k = threadIdx.x;
+  if (k >= n_ex) return;
+  const float x1 = rects0[4 * k], y1 = rects0[4 * k + 1], x2 = rects0[4 * k + 2], y2 = rects0[4 * k + 3];
+  const float fx = __fdiv_rn(__fadd_rn(__fmul_rn(x1, (float)W), __fmul_rn(x2, (float)W)), 2.0f);
+  const float fy = __fdiv_rn(__fadd_rn(__fmul_rn(y1, (float)H), __fmul_rn(y2, (float)H)), 2.0f);
+  int xc = (int)fx, yc = (int)fy;   // cvt.rzi: truncation toward zero like Python int()
+  if (xc < 0 || xc >= W || yc < 0 || yc >= H || !(fx == fx) || !(fy == fy)) {
+    if (status) atomicOr(status, 2);
+    xc = min(max(xc, 0), W - 1);
+    yc = min(max(yc, 0), H - 1);
+  }
+  yx[2 * k] = yc;
+  yx[2 * k + 1] = xc;
+}
+}  // namespace
+
+extern "C" int cdetr_mask_prepare(const uint8_t* mask, int B, int S1, int S2, int H, int W, uint8_t* mask_row,
+                                  uint8_t* mask_col, float* pos_row, float* pos_col, cdetr_stream_t s) {
+  CDETR_CHECK_ARG(mask && mask_row && mask_col && pos_row && pos_col && B > 0 && H > 0 && W > 0 && S1 >= H && S2 >= W,
+                  "mask_prepare: bad args");
+  mask_prepare_kernel<<<B, 128, 0, STREAM(s)>>>(mask, S1, S2, H, W, mask_row, mask_col, pos_row, pos_col);
+  CDETR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cdetr_exemplar_centres(const float* rects0, int n_ex, int H, int W, int* centres_yx, int* status,
+                                      cdetr_stream_t s) {
+  CDETR_CHECK_ARG(rects0 && centres_yx && n_ex > 0 && n_ex <= 32 && H > 0 && W > 0, "exemplar_centres: bad args");
+  exemplar_centres_kernel<<<1, 32, 0, STREAM(s)>>>(rects0, n_ex, H, W, centres_yx, status);
+  CDETR_CHECK_LAUNCH();
+  return 0;
+}

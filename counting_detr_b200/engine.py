@@ -578,15 +578,17 @@ class Engine:
             g = (torch.arange(n, dtype=torch.float32) + 0.5) / n
             gx, gy = torch.meshgrid(g, g, indexing="ij")
             ref = torch.stack([gx.reshape(-1), gy.reshape(-1)], -1).to(self.dev)
-        elif cfg.spatial_prior == "defined":
-            assert points is not None, "defined, provide points"
-            ref = torch.as_tensor(points, dtype=torch.float32).reshape(-1, 2).to(self.dev)
+        elif cfg.spatial_prior in ("defined", "sampled"):
+            # A1/models/transformer.py:114-121 (points [1,Q,2] tensor), A2 :125-133 (ndarray [Q,2] / tensor [Q,2])
+            assert points is not None, f"{cfg.spatial_prior}, provide points"
+            ref = torch.as_tensor(points, dtype=torch.float32).reshape(-1, 2).to(self.dev, non_blocking=True)
         else:
             raise ValueError(f"unknown {cfg.spatial_prior} spatial prior")
         return ref.contiguous()
 
-    def forward(self, image, centres_yx=None, points=None, mask=None):
-        """image [B,3,S,S] fp32 cuda; centres_yx int32 [n_ex,2] (stage 2); returns dict of fp32 outputs."""
+    def forward(self, image, centres_yx=None, points=None, mask_img=None):
+        """image [B,3,S1,S2] fp32 cuda; centres_yx device int32 [n_ex,2] (stage 2); mask_img device uint8 [B,S1,S2]
+        (1 = padded pixel) or None; returns the per-layer head outputs (fp32)."""
         self._plan_backbone(image.shape[2], image.shape[3])
         if not self.packed:
             self.pack_weights()
@@ -614,17 +616,17 @@ class Engine:
         L.call("cdetr_groupnorm_fwd", pre, B, N, E, 32, self.params[pn + ".weight"], self.params[pn + ".bias"], 1e-5,
                src, src_s, gst)
         sv["proj"] = dict(pre=pre, gst=gst, proj_in=proj_in)
-        # ---- positions: mask2pos (no padding: (i+0.5)/n; with a mask the caller passes per-sample positions)
-        if mask is None:
-            pos_row = ((torch.arange(W, device=self.dev, dtype=torch.float32) + 0.5) / W).repeat(B)
-            pos_col = ((torch.arange(H, device=self.dev, dtype=torch.float32) + 0.5) / H).repeat(B)
+        # ---- positions: mask2pos.  No padding: (i + 0.5) / n (cached constants); with a padding mask one kernel
+        # downsamples it to the feature map and emits the key-padding rows / columns and the positions
+        if mask_img is None:
+            pos_row, pos_col = self._unpadded_positions(B, H, W)
             masks = (None, None)
         else:
-            nm = ~mask
-            yv = nm[:, :, 0].cumsum(1, dtype=torch.float32); xv = nm[:, 0, :].cumsum(1, dtype=torch.float32)
-            pos_col = ((yv - 0.5) / yv[:, -1:]).reshape(-1).contiguous()
-            pos_row = ((xv - 0.5) / xv[:, -1:]).reshape(-1).contiguous()
-            masks = (mask[:, 0, :].to(torch.uint8).contiguous(), mask[:, :, 0].to(torch.uint8).contiguous())
+            S1, S2 = image.shape[2], image.shape[3]
+            mrow = self.buf("mask_row", (B * W,), torch.uint8); mcol = self.buf("mask_col", (B * H,), torch.uint8)
+            pos_row = self.buf("pos_row_m", (B * W,)); pos_col = self.buf("pos_col_m", (B * H,))
+            L.call("cdetr_mask_prepare", mask_img, B, S1, S2, H, W, mrow, mcol, pos_row, pos_col)
+            masks = (mrow, mcol)
         ref = self.reference_points(points)            # [Qp, 2] (same for every sample)
         P = cfg.num_query_pattern
         Qp = ref.shape[0]
@@ -700,6 +702,15 @@ class Engine:
                 outs.append(self._heads_fwd(tgt_s, MQ, Q, i))
         sv["dec_out_s"] = tgt_s
         return outs, dict(B=B, Q=Q, H=H, W=W)
+
+    def _unpadded_positions(self, B, H, W):
+        key = ("pos_const", (B, H, W), None)
+        t = self._bufs.get(key)
+        if t is None:
+            t = (((torch.arange(W, device=self.dev, dtype=torch.float32) + 0.5) / W).repeat(B).contiguous(),
+                 ((torch.arange(H, device=self.dev, dtype=torch.float32) + 0.5) / H).repeat(B).contiguous())
+            self._bufs[key] = t
+        return t
 
     def _pattern_key(self):
         return "transformer.modify_pattern.weight" if self.cfg.stage == 1 else "transformer.pattern.weight"

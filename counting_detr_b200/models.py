@@ -237,32 +237,29 @@ class AnchorDETR(nn.Module):
 
     def forward(self, samples, points=None, rects=None):
         """stage 2: model(samples, points=None, rects=[B,3,4]) -> (dict, reference_points)
-        stage 1: model(samples, scaled_sample_points[B,Q,2]) -> dict          (A1/A2 anchor_detr.py forward)"""
+        stage 1: model(samples, scaled_sample_points[B,Q,2]) -> dict          (A1/A2 anchor_detr.py forward)
+
+        `samples`: [B,3,S1,S2] tensor, a NestedTensor (anything with .decompose() -> (tensors, mask[B,S1,S2], True =
+        padded pixel)) or a list of [3,h,w] images, which is zero-padded to the largest size with the mask the
+        reference's nested_tensor_from_tensor_list builds (A2/util/misc.py:291-308).  Nothing here reads device data
+        on the host: the padding mask is downsampled and the exemplar centres are computed by kernels."""
         mask = None
         if hasattr(samples, "decompose"):
             samples, mask = samples.decompose()
-            if mask is not None and not bool(mask.any()):
-                mask = None
         elif isinstance(samples, (list, tuple)):
-            samples = torch.stack(list(samples))
+            samples, mask = _pad_images(list(samples))
         eng = self.engine()
         ver = self._current_version()
         if ver != self._param_version:       # weights changed (optimizer.step / load_state_dict): re-pack
             eng.packed = False
             self._param_version = ver
+        rects0 = None
         if self.stage == 2:
             if rects is None:
                 raise ValueError("stage-2 forward needs exemplar rects")
-            B, _, S1, S2 = samples.shape
-            centres = exemplar_centres(rects, feat_size(S1), feat_size(S2))
-            pts = points
-        else:
-            centres = None
-            pts = points
-            if self.spatial_prior == "defined":
-                pts = torch.as_tensor(points).reshape(-1, 2) if points is not None else None
+            rects0 = rects[0]                 # the rects of SAMPLE 0 serve the whole batch (A2/models/backbone.py:122)
         params = [p for p in self.parameters()]
-        outs = _ModelFn.apply(self, samples, centres, pts, mask, *params)
+        outs = _ModelFn.apply(self, samples, rects0, points, mask, *params)
         return self._pack_outputs(outs)
 
     def _pack_outputs(self, flat):
@@ -278,6 +275,21 @@ class AnchorDETR(nn.Module):
         return {"pred_logits": last[0], "pred_wh": last[1][..., 2:], "pred_points": last[1][..., :2]}
 
 
+_STATUS = {}
+
+
+def status_flag(dev):
+    """Per-device int32 flag: set by cdetr_exemplar_centres / cdetr_lsap on a failure the reference would raise on
+    (IndexError / scipy ValueError), consumed (losses -> NaN) and re-armed by cdetr_set_loss_fwd; no host read."""
+    dev = torch.device(dev)
+    if dev.index is None and dev.type == "cuda":
+        dev = torch.device("cuda", torch.cuda.current_device())
+    t = _STATUS.get(dev)
+    if t is None:
+        t = _STATUS[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return t
+
+
 def feat_size(s):
     """spatial size of the DC5 layer4 map: 7x7 s2 p3 conv, 3x3 s2 p1 pool, two stride-2 stages."""
     s = (s + 6 - 7) // 2 + 1
@@ -287,14 +299,33 @@ def feat_size(s):
 
 
 def exemplar_centres(rects, H, W):
-    """int() truncation of the exemplar centres of SAMPLE 0 in fp32 (A2/models/backbone.py:122-128)."""
+    """Host restatement of the exemplar-centre rule (int() truncation in fp32, rects of SAMPLE 0,
+    A2/models/backbone.py:122-128) for callers that want the centres on the host; the model itself uses the
+    device kernel cdetr_exemplar_centres.  Raises IndexError like the reference when a centre leaves the map."""
     r0 = rects[0]
     r0 = torch.as_tensor(np.asarray(r0.detach().cpu() if isinstance(r0, torch.Tensor) else r0), dtype=torch.float32)
     out = []
     for r in r0:
         nx1, ny1, nx2, ny2 = r[0] * W, r[1] * H, r[2] * W, r[3] * H
-        out.append([int((ny1 + ny2) / 2), int((nx1 + nx2) / 2)])
+        yc, xc = int((ny1 + ny2) / 2), int((nx1 + nx2) / 2)
+        if not (-H <= yc < H and -W <= xc < W):
+            raise IndexError(f"exemplar centre ({yc}, {xc}) outside the {H}x{W} feature map")
+        out.append([yc % H, xc % W])     # negative indices wrap in the reference's tensor indexing
     return out
+
+
+def _pad_images(imgs):
+    """nested_tensor_from_tensor_list (A2/util/misc.py:291-308): zero-pad to the largest [h, w], mask True on padding."""
+    if all(im.shape == imgs[0].shape for im in imgs):
+        return torch.stack(imgs), None
+    c = imgs[0].shape[0]
+    h, w = max(im.shape[1] for im in imgs), max(im.shape[2] for im in imgs)
+    out = torch.zeros(len(imgs), c, h, w, dtype=imgs[0].dtype, device=imgs[0].device)
+    mask = torch.ones(len(imgs), h, w, dtype=torch.bool, device=imgs[0].device)
+    for im, o, m in zip(imgs, out, mask):
+        o[:, : im.shape[1], : im.shape[2]].copy_(im)
+        m[: im.shape[1], : im.shape[2]] = False
+    return out, mask
 
 
 class _EngineCfg:
@@ -312,17 +343,25 @@ class _ModelFn(torch.autograd.Function):
     """One autograd node for the whole network: forward and backward are the engine's kernel sequences."""
 
     @staticmethod
-    def forward(ctx, module, image, centres, points, mask, *params):
+    def forward(ctx, module, image, rects0, points, mask, *params):
         eng = module.engine()
         dev = eng.dev
         image = image.to(dev, torch.float32)
         yx = None
-        if centres is not None:
-            # static device copy, refreshed only when the centres change (keeps the step graph-capturable)
-            if getattr(module, "_centres_host", None) != centres:
-                module._centres_dev = torch.tensor(centres, dtype=torch.int32, device=dev)
-                module._centres_host = [list(c) for c in centres]
+        if rects0 is not None:
+            # static device buffers updated in place (fixed addresses: a captured step stays valid when the rects
+            # change); the centres are computed on the device, so device-resident rects cost no host read
+            r = torch.as_tensor(rects0, dtype=torch.float32)
+            n_ex = r.shape[0]
+            if getattr(module, "_rects_dev", None) is None or module._rects_dev.shape[0] != n_ex or module._rects_dev.device != dev:
+                module._rects_dev = torch.zeros(n_ex, 4, device=dev)
+                module._centres_dev = torch.zeros(n_ex, 2, dtype=torch.int32, device=dev)
+            module._rects_dev.copy_(r.reshape(n_ex, 4), non_blocking=True)
+            H, W = feat_size(image.shape[2]), feat_size(image.shape[3])
+            L.call("cdetr_exemplar_centres", module._rects_dev, n_ex, H, W, module._centres_dev, status_flag(dev))
             yx = module._centres_dev
+        if mask is not None:
+            mask = mask.to(dev).to(torch.uint8).contiguous()
         eng.zero_grad()
         outs, dims = eng.forward(image, yx, points, mask)
         B, Q = dims["B"], dims["Q"]
@@ -429,7 +468,7 @@ class HungarianMatcher(nn.Module):
         oq = self._buf("oq", (B, K), torch.int64, dev)
         ot = self._buf("ot", (B, K), torch.int64, dev)
         on = self._buf("on", (B,), torch.int32, dev)
-        status = self._buf("status", (1,), torch.int32, dev)
+        status = status_flag(dev)
         lg = logits.detach().contiguous().float()
         bx = boxes.detach().contiguous().float()
         L.call("cdetr_match_cost", lg, C, bx, self._tg.boxes, self._tg.off, B, Q, Tmax, self.cost_class,
@@ -442,6 +481,10 @@ class HungarianMatcher(nn.Module):
         """Reference contract: list of (index_i, index_j) int64 CPU tensors (A2/models/matcher.py:247)."""
         oq, ot, on, lens = self.match_device(outputs["pred_logits"], outputs["pred_boxes"], targets)
         oq, ot, on = oq.cpu(), ot.cpu(), on.cpu()
+        st = status_flag(outputs["pred_logits"].device)
+        if int(st.item()) & 1:               # this call already synchronises (.cpu()): raise where scipy would
+            st.zero_()
+            raise ValueError("cost matrix contains invalid numeric entries (scipy.optimize.linear_sum_assignment)")
         return [(oq[b, : on[b]].clone(), ot[b, : on[b]].clone()) for b in range(len(lens))]
 
 
@@ -466,7 +509,8 @@ class _SetLossFn(torch.autograd.Function):
         g_giou = torch.empty(B, Q, 4, device=dev); g_vb = torch.empty(B, Q, 4, device=dev)
         g_vv = torch.empty(B, Q, 2, device=dev); matched = torch.empty(B * Q, dtype=torch.uint8, device=dev)
         L.call("cdetr_set_loss_fwd", logits.contiguous(), boxes.contiguous(), pvars.contiguous(), tg.boxes, tg.off, oq,
-               ot, on, B, Q, K, num_boxes, inv_world, crit.focal_alpha, out6, g_ce, g_bbox, g_giou, g_vb, g_vv, matched)
+               ot, on, B, Q, K, num_boxes, inv_world, crit.focal_alpha, out6, g_ce, g_bbox, g_giou, g_vb, g_vv, matched,
+               status_flag(dev))
         ctx.save_for_backward(g_ce, g_bbox, g_giou, g_vb, g_vv)
         ctx.rows = B * Q
         crit.last_indices = (oq, ot, on)

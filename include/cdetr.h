@@ -155,6 +155,16 @@ int cdetr_box_head_fwd(const float* t, const float* ref, int64_t M, float* boxes
 int cdetr_box_head_bwd(const float* dboxes, const float* boxes, const float* ref, int64_t M, float* dt,
                        cdetr_split_t dt_split, float* dref, cdetr_stream_t s);
 int cdetr_scale(float* x, int64_t n, float a, cdetr_stream_t s);
+/* Padding mask [B,S1,S2] (1 = padded pixel) -> what the transformer reads of it: the nearest-neighbour downsample to
+ * the H x W feature map (A2/models/backbone.py:112), of which only the first row / first column are ever used:
+ * mask_row [B,W] / mask_col [B,H] (RCDA key padding, A2/models/row_column_decoupled_attention.py:238-249) and the
+ * normalised positions pos_row [B,W] / pos_col [B,H] of mask2pos (A2/models/transformer.py:497-503). */
+int cdetr_mask_prepare(const uint8_t* mask, int B, int S1, int S2, int H, int W, uint8_t* mask_row, uint8_t* mask_col,
+                       float* pos_row, float* pos_col, cdetr_stream_t s);
+/* Exemplar centres on the device (no host read of the rects): rects0 = fp32 [n_ex,4] xyxy in [0,1] of SAMPLE 0,
+ * centres_yx int32 [n_ex,2] = (int((y1*H + y2*H)/2), int((x1*W + x2*W)/2)) in fp32 with truncation
+ * (A2/models/backbone.py:122-128).  Out-of-range centres are clamped and bit 1 of *status is set. */
+int cdetr_exemplar_centres(const float* rects0, int n_ex, int H, int W, int* centres_yx, int* status, cdetr_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------
  * Attention cores.  RCDA: A2/models/row_column_decoupled_attention.py:210-291 (q scaling, row/col logits,
@@ -212,6 +222,8 @@ int cdetr_set_loss_fwd(const float* logits, const float* boxes, const float* var
                        int Q, int Kmax, const float* num_boxes_sum, float inv_world, float focal_alpha,
                        float* out6, float* g_ce,
                        float* g_bbox, float* g_giou, float* g_var_box, float* g_var_var, unsigned char* matched,
+                       int* status /* NULL or the flag cdetr_lsap / cdetr_exemplar_centres set: non-zero turns the six
+                                      losses NaN (the reference raises there) and re-arms the flag */,
                        cdetr_stream_t s);
 int cdetr_set_loss_bwd(const float* upstream4, const float* g_ce, const float* g_bbox, const float* g_giou,
                        const float* g_var_box, const float* g_var_var, int64_t rows, float* d_logits,

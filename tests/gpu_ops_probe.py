@@ -333,7 +333,7 @@ out6 = torch.empty(6, device=dev)
 g_ce = torch.empty(Bm, Q, 2, device=dev); g_bbox = torch.empty(Bm, Q, 4, device=dev); g_giou = torch.empty(Bm, Q, 4, device=dev)
 g_vb = torch.empty(Bm, Q, 4, device=dev); g_vv = torch.empty(Bm, Q, 2, device=dev); matched = torch.empty(Bm * Q, dtype=torch.uint8, device=dev)
 nb = float(sum(len(t) for t in tg))
-L.call("cdetr_set_loss_fwd", lg, bx, vr, tcat, off, oq, ot, on, Bm, Q, Kmax, torch.tensor([nb], device=dev), 1.0, 0.25, out6, g_ce, g_bbox, g_giou, g_vb, g_vv, matched)
+L.call("cdetr_set_loss_fwd", lg, bx, vr, tcat, off, oq, ot, on, Bm, Q, Kmax, torch.tensor([nb], device=dev), 1.0, 0.25, out6, g_ce, g_bbox, g_giou, g_vb, g_vv, matched, None)
 lc, bc, vc = lg.cpu().requires_grad_(), bx.cpu().requires_grad_(), vr.cpu().requires_grad_()
 targets = [{"boxes": t, "labels": torch.zeros(len(t), dtype=torch.int64)} for t in tg]
 idx = [(oq[b, : on[b]].cpu(), ot[b, : on[b]].cpu()) for b in range(Bm)]

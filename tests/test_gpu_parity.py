@@ -144,9 +144,9 @@ def test_matcher_stress_1000x1000_bit_exact_vs_scipy():
 
 
 def test_full_size_properties():
-    """At the benchmark shapes (C3: B=16, 512x512, Q=300, T=50) the oracle is too slow to be the checker, so
-    check properties: finite losses, a valid assignment, sample independence of everything but the sample-0
-    exemplar quirk, determinism, and that a second backward gives identical gradients."""
+    """Size-independent properties at the benchmark shapes (C3: B=16, 512x512, Q=300, T=50), on top of the value
+    parity of tests/test_gpu_cases.py at the same shapes: finite losses, a valid assignment, sample independence of
+    everything but the sample-0 exemplar quirk, determinism, and that a second backward gives identical gradients."""
     from counting_detr_b200 import synthetic as SY
     B, S, Q, T = 16, 512, 300, 50
     model, crit, _ = _build(2, Q)

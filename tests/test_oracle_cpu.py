@@ -121,3 +121,21 @@ def test_oracle_matches_live_reference(stage):
         assert _close(ro[k], oo[k], 1e-5), k
     for k in rl:
         assert _close(rl[k], ol[k], 1e-5), k
+
+
+# ------------------------------------------------------------------ cases at BASELINE sizes / model variants
+from oracle.make_golden import CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_case_golden(name, golden_dir):
+    """The oracle against outputs of the UNMODIFIED reference (oracle/make_golden.py run_case) at BASELINE.json's own
+    sizes (C1a/b, C2, C3, C4) and for the grid / defined priors, 3 query patterns and a padded NestedTensor batch.
+    Tolerances: 2e-5 relative on outputs and losses (two fp32 CPU implementations of the same graph), matching
+    indices bit-exact, gradients 2e-3 norm-relative per tensor."""
+    from oracle.cases import compare, oracle_case
+    path = os.path.join(golden_dir, name + ".pt")
+    gold = torch.load(path)
+    got = oracle_case(name, gold["config"]["seed"])
+    fails, worst = compare(got, gold, tol_out=2e-5, tol_loss=2e-5, tol_grad_norm=2e-3, tol_grad_small=2e-3)
+    assert not fails, (fails[:10], worst)
