@@ -92,18 +92,19 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_arm(name, steps, warmup, batch=1):
+def cpu_arm(name, steps, warmup, batch=None):
     """The oracle port (oracle/model.py + oracle/criterion.py: CPU PyTorch fp32 restatement of the reference,
-    pinned against the live reference import and its goldens) timed on the host cores: fwd + loss + bwd."""
+    pinned against the live reference import and its goldens) timed on the host cores: fwd + loss + bwd, at the
+    workload's own per-GPU batch size unless `batch` says otherwise."""
     import torch
-    from oracle import criterion as OC, model as OM, weights as OW
-    st, _, S, Q, T = WORKLOADS[name]
+    from oracle import cases as OCS, criterion as OC, model as OM, weights as OW
+    st, B, S, Q, T = WORKLOADS[name]
+    batch = batch or B
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     cfg = OM.Config(stage=st, num_query_position=Q)
-    sd = OW.make_state_dict(cfg, 0)
-    frozen = ("backbone.body.conv1", "backbone.body.layer1", "running_", ".bn", "downsample.1")
-    sd = {k: v.clone().requires_grad_(v.is_floating_point() and not any(f in k for f in frozen)) for k, v in sd.items()}
+    from counting_detr_b200 import synthetic as SY
+    sd = OCS.oracle_state_dict(SY.SynthCfg(stage=st, num_query_position=Q), 0)
     inp = OW.make_inputs(batch, S, T=T, stage=st, Q=Q)
 
     def step():
@@ -125,24 +126,25 @@ def cpu_arm(name, steps, warmup, batch=1):
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
-    dt = (time.perf_counter() - t0) / steps
+    dt = (time.perf_counter() - t0) / max(steps, 1)
     return {"value": batch / dt, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} steps of B={batch} (same shapes per image as the GPU workload), {warmup} warm-up, "
-                      f"fwd+criterion+bwd, torch CPU fp32, {dt * 1e3:.0f} ms/step"}, dt
+            "sample": f"{steps} steps of B={batch} (the GPU workload's per-GPU batch, same shapes), {warmup} warm-up, "
+                      f"fwd+criterion+bwd, torch CPU fp32 on {cores} threads, {dt * 1e3:.0f} ms/step"}, dt
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU PyTorch path (= the oracle port: /root/reference itself cannot travel to the
+    GPU box and is not pip-installable) on the same workload, batch size, steps and warm-up as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(args.steps, 3)
-    warm = min(max(args.warmup, 1), 1)
-    cb, dt = cpu_arm(args.workload, steps, warm, batch=1)
+    cb, dt = cpu_arm(args.workload, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_desc(args.workload), "note": "reference CPU path = oracle port; "
-                       "/root/reference is not present on the GPU box; B=1 sample per step"},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_desc(args.workload), "global_batch": WORKLOADS[args.workload][1],
+                       "note": "reference CPU path = oracle port (pinned to the live reference and its goldens); one "
+                               "process on the host cores whatever --gpus says"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -193,12 +195,59 @@ def attention_roofline(atrace, peak, ms_step):
             "note": "algorithmic fp32-equivalent FLOPs; tensor-core kernels issue 3 bf16 MMAs per product (split operands)"}
 
 
+# ------------------------------------------------------------------------------------------ matcher metric
+def matcher_bench(dev):
+    """BASELINE.json's second metric: matcher us/image (cost matrix + assignment, device-resident indices), with scipy
+    on the same host's cores beside it and an indices-equal flag (scipy on the cost matrix the oracle computes)."""
+    import numpy as np
+    import torch
+    from scipy.optimize import linear_sum_assignment as lsa
+    from counting_detr_b200.models import HungarianMatcher
+    from counting_detr_b200 import synthetic as SY
+    from oracle import criterion as OC
+    out = {}
+    for tag, B, Q, T, reps in (("16x300x50", 16, 300, 50, 20), ("1x1000x1000", 1, 1000, 1000, 3), ("148x1000x1000", 148, 1000, 1000, 2)):
+        m = HungarianMatcher(2.0, 5.0, 2.0)
+        logits = SY.uniform("m_logits", (B, Q, 2), -2.0, 2.0, 5)
+        boxes = torch.cat([SY.uniform("m_c", (B, Q, 2), 0.0, 1.0, 5), SY.uniform("m_s", (B, Q, 2), 0.01, 0.21, 5)], -1)
+        tb = [torch.cat([SY.uniform(f"m_tc{b}", (T, 2), 0.0, 1.0, 5), SY.uniform(f"m_ts{b}", (T, 2), 0.01, 0.21, 5)], -1) for b in range(B)]
+        lg, bx = logits.to(dev), boxes.to(dev)
+        tg = [{"boxes": t.to(dev), "labels": torch.zeros(T, dtype=torch.int64, device=dev)} for t in tb]
+        oq, ot, on, _ = m.match_device(lg, bx, tg)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            oq, ot, on, _ = m.match_device(lg, bx, tg)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps / B
+        oq, ot = oq.cpu(), ot.cpu()
+        nchk = min(B, 3)
+        t_sc, equal = 0.0, True
+        for b in range(nchk):
+            c = OC.match_cost(logits[b], boxes[b], tb[b]).numpy()
+            t0 = time.perf_counter()
+            i, j = lsa(c)
+            t_sc += time.perf_counter() - t0
+            equal &= bool(np.array_equal(oq[b].numpy(), i) and np.array_equal(ot[b].numpy(), j))
+        out[tag] = {"us_per_image": round(us, 2), "latency_ms_per_call": round(us * B / 1e3, 3),
+                    "scipy_us_per_image_same_host": round(t_sc / nchk * 1e6, 1), "indices_equal_scipy": equal,
+                    "images_checked": nchk}
+    out["note"] = ("cost matrix + LSAP kernels, device-resident indices, CUDA events over back-to-back calls; scipy = "
+                   "linear_sum_assignment alone (cost already on the host) on this box's CPU, 1 thread")
+    return out
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from counting_detr_b200 import _lib as L
+    from counting_detr_b200.data import DevicePrefetcher
     from counting_detr_b200.models import build_model
+    from counting_detr_b200.optim import FusedAdamW
+    from counting_detr_b200.step import CapturedStep
     from counting_detr_b200 import synthetic as SY
     from counting_detr_b200.parallel import shard_seed
 
@@ -207,212 +256,153 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
     st, B, S, Q, T = WORKLOADS[args.workload]
-    margs = SY.default_args(st, num_query_position=Q, device=str(dev))
-    model, crit, _ = build_model(margs)
-    model.load_state_dict(SY.make_state_dict(SY.SynthCfg(stage=st, num_query_position=Q), 0), strict=True)
-    model.to(dev).train(); crit.train()
-    if world > 1:
-        # keep NCCL out of the captured graph: gradients alias the flat buffer, one all-reduce after the replay;
-        # T is constant in this benchmark so the criterion's 1-float num_boxes all-reduce is frozen
-        model.alias_param_grads(True)
-        if st == 2:
-            crit.fixed_num_boxes = float(B * T)
-    inp = SY.make_inputs(B, S, T=T, seed=shard_seed(0, rank), stage=st, Q=Q)
-    img_h = inp["image"].pin_memory()
-    img_d = img_h.to(dev)
-    rects_h = inp.get("rects")
-    if st == 2:
-        tb_h = [t["boxes"].pin_memory() for t in inp["targets"]]
-        targets = [{"boxes": b.to(dev), "labels": t["labels"].to(dev)} for b, t in zip(tb_h, inp["targets"])]
-    else:
-        pts_h, whs_h = inp["points"].pin_memory(), inp["whs"].pin_memory()
-        pts_d = pts_h.to(dev)
-        targets = {"points": pts_d, "whs": whs_h.to(dev)}
+    steps, warm = args.steps, max(args.warmup, 3)
 
-    def step():
-        model.zero_grad(set_to_none=True)
+    def build():
+        margs = SY.default_args(st, num_query_position=Q, device=str(dev))
+        model, crit, _ = build_model(margs)
+        model.load_state_dict(SY.make_state_dict(SY.SynthCfg(stage=st, num_query_position=Q), 0), strict=True)
+        model.to(dev).train(); crit.train()
+        return model, crit
+
+    model, crit = build()
+    # two pinned host batches (alternating: the static device inputs really change between steps)
+    host = []
+    for i in range(2):
+        inp = SY.make_inputs(B, S, T=T, seed=shard_seed(i, rank), stage=st, Q=Q)
+        hb = {"image": inp["image"].pin_memory()}
         if st == 2:
-            out, _ = model(img_d, None, rects_h)
+            hb["rects"] = inp["rects"].pin_memory()
+            hb["targets"] = [{"boxes": t["boxes"].pin_memory(), "labels": t["labels"]} for t in inp["targets"]]
         else:
-            out = model(img_d, pts_d)
-        ld = crit(out, targets)
-        loss = sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict)
-        loss.backward()
-        return loss.detach()     # keep no reference to the autograd graph (needed for graph capture)
+            hb["points"] = inp["points"].pin_memory()
+            hb["targets"] = {"points": hb["points"], "whs": inp["whs"].pin_memory()}
+        host.append(hb)
+    devb = [{k: (v.to(dev) if isinstance(v, torch.Tensor) else
+                 ([{kk: vv.to(dev) for kk, vv in t.items()} for t in v] if isinstance(v, list) else
+                  {kk: vv.to(dev) for kk, vv in v.items()})) for k, v in hb.items()} for hb in host]
+
+    def call(stepper, b):
+        if st == 2:
+            return stepper(b["image"], b["targets"], rects=b["rects"])
+        return stepper(b["image"], b["targets"], points=b["points"])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (eager): allocates every buffer, packs weights
-    for _ in range(max(args.warmup, 3)):
-        loss = step()
-    torch.cuda.synchronize()
-    L.COUNTER["launches"] = 0
-    step()
-    launches_per_step = L.COUNTER["launches"]
-    loss_val = float(loss)
-    del loss
-    # ---- optional whole-step CUDA graph
-    graph, use_graph, g_loss = None, not args.no_graph, None
-    if use_graph:
-        try:
-            s = torch.cuda.Stream(priority=-1)     # critical path at high priority; wgrad side stream is low
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                for _ in range(2):
-                    step()
-            torch.cuda.current_stream().wait_stream(s)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=s):
-                g_loss = step()
-            graph.replay()
-            torch.cuda.synchronize()
-            if abs(float(g_loss) - loss_val) > 1e-3 * abs(loss_val):
-                raise RuntimeError(f"graph replay loss {float(g_loss)} != eager loss {loss_val}")
-        except Exception as e:  # fall back to eager launches of the same kernels
-            if rank == 0:
-                import traceback
-                print(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {str(e)[:300]}); timing eager launches", file=sys.stderr)
-                if os.environ.get("BENCH_DEBUG"):
-                    traceback.print_exc()
-            graph, use_graph = None, False
-            torch.cuda.synchronize()
-
-    if world > 1:   # all ranks must take the same path (a lone eager rank would issue different collectives)
-        flag = torch.tensor([1 if graph is not None else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag) == 0:
-            graph, use_graph = None, False
-
-    def run_one():
-        if graph is not None:
-            graph.replay()
-        else:
-            step()
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
         if world > 1:
-            model.allreduce_grads(dist.group.WORLD)
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms / n
 
-    for _ in range(3):
-        run_one()
-    # ---- timed region: exactly K steps, device events, max over ranks
+    # ---- (1) the metric: fwd + criterion + bwd (+ gradient all-reduce), CUDA-graph replay, inputs resident in HBM
+    step_fb = CapturedStep(model, crit, optimizer=None, group=group, use_graph=not args.no_graph)
+    for i in range(warm):
+        out = call(step_fb, devb[i & 1])
+    torch.cuda.synchronize()
+    loss_val = float(out[1])
+    use_graph = step_fb._graph is not None
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
         sampler.start()
+    ms_step = timed(lambda i: call(step_fb, devb[i & 1]), steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * world / ms_step * 1e3
+    launches_per_step = step_fb.launches_per_step
+    if launches_per_step is None:
+        L.COUNTER["launches"] = 0
+        call(step_fb, devb[0])
+        launches_per_step = L.COUNTER["launches"]
+
+    # ---- (2) e2e: the same step through the public API from pinned HOST batches: counting_detr_b200.data.DevicePrefetcher
+    # (H2D of batch i+1 on a copy stream under the compute of batch i) -> CapturedStep -> loss.item() EVERY step (the
+    # reference's loop reads the loss each iteration, A2/engine.py:44); all of it inside the timed region
+    def e2e_run(stepper, n):
+        pf = DevicePrefetcher((host[i & 1] for i in range(n)), dev)
+        last = None
+        for b in pf:
+            _, total = call(stepper, b)
+            last = total.item()
+        return last, pf.h2d_bytes
+
+    e2e_run(step_fb, 3)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        run_one()
+    _, h2d_total = e2e_run(step_fb, steps)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t)
-    ms_step = ms_total / args.steps
-    value = B * world / ms_step * 1e3
-
-    # ---- e2e: public API from pinned host buffers, H2D + loss D2H inside the timed region.  With a captured
-    # step the host copies land in the static input tensors the graph reads, then the graph is replayed.
-    # Input pipeline of the captured path (what a training loop with a prefetching loader does): the pinned host batch of
-    # step i+1 is copied to a device staging buffer on a copy stream while step i computes; step i+1 starts with a
-    # device-to-device move into the tensors the graph reads.  Every step's H2D copy and loss read are inside the
-    # timed region.
-    copy_stream = torch.cuda.Stream()
-    img_stage = torch.empty_like(img_d)
-    h2d_done = torch.cuda.Event()
-
-    loss_pin = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_ev = [torch.cuda.Event() for _ in range(2)]
-    e2e_state = {"n": 0}
-
-    def flush_loss():   # read the last step's loss (end of a run of e2e steps)
-        if graph is not None and e2e_state["n"] >= 1:
-            slot = (e2e_state["n"] - 1) & 1
-            loss_ev[slot].synchronize()
-            e2e_state["n"] = 0
-            return float(loss_pin[slot])
-        return None
-
-    stage_free = torch.cuda.Event()
-
-    def prefetch_inputs():
-        copy_stream.wait_event(stage_free)   # the d2d move of the running step has consumed the staging buffer
-        with torch.cuda.stream(copy_stream):
-            img_stage.copy_(img_h, non_blocking=True)
-            h2d_done.record(copy_stream)
-
-    def e2e_step():
-        if graph is not None:
-            torch.cuda.current_stream().wait_event(h2d_done)
-            img_d.copy_(img_stage, non_blocking=True)
-            stage_free.record()
-            if st == 2:
-                for t, b in zip(targets, tb_h):
-                    t["boxes"].copy_(b, non_blocking=True)
-            else:
-                pts_d.copy_(pts_h, non_blocking=True)
-                targets["whs"].copy_(whs_h, non_blocking=True)
-            graph.replay()
-            if world > 1:
-                model.allreduce_grads(dist.group.WORLD)
-            prefetch_inputs()          # next step's image batch travels while this step computes
-            # the loss leaves through an asynchronous copy into pinned memory; the host reads the PREVIOUS step's
-            # value while this step runs (one device->host read per step, none of them skipped: see flush_loss)
-            slot = e2e_state["n"] & 1
-            loss_pin[slot].copy_(g_loss, non_blocking=True)
-            loss_ev[slot].record()
-            e2e_state["n"] += 1
-            if e2e_state["n"] >= 2:
-                loss_ev[slot ^ 1].synchronize()
-                return float(loss_pin[slot ^ 1])
-            return None
-        img = img_h.to(dev, non_blocking=True)
-        model.zero_grad(set_to_none=True)
-        if st == 2:
-            tg = [{"boxes": b.to(dev, non_blocking=True), "labels": t["labels"]} for b, t in zip(tb_h, targets)]
-            out, _ = model(img, None, rects_h)
-            ld = crit(out, tg)
-        else:
-            p = pts_h.to(dev, non_blocking=True)
-            out = model(img, p)
-            ld = crit(out, {"points": p, "whs": whs_h.to(dev, non_blocking=True)})
-        loss = sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict)
-        loss.backward()
-        if world > 1:
-            model.allreduce_grads(dist.group.WORLD)
-        return loss.item()
-
-    if graph is not None:
-        stage_free.record()
-        prefetch_inputs()
-    for _ in range(2):
-        e2e_step()
-    flush_loss()
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        e2e_step()
-    flush_loss()                                           # the K-th loss is read inside the timed region too
-    torch.cuda.current_stream().wait_stream(copy_stream)   # the K-th prefetch copy also ends inside the timed region
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    ms_e2e = e0.elapsed_time(e1) / steps
     if world > 1:
         t = torch.tensor([ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t)
-    h2d = img_h.numel() * 4 + (sum(b.numel() for b in tb_h) * 4 if st == 2 else (pts_h.numel() + whs_h.numel()) * 4)
-    e2e = {"value": B * world / (ms_e2e / args.steps) * 1e3, "unit": "images/s", "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": 4}
+    e2e = {"value": B * world / ms_e2e * 1e3, "unit": "images/s", "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": int(h2d_total // steps), "d2h_bytes_per_step": 4,
+           "path": "DevicePrefetcher(pinned host batches) -> CapturedStep(model, criterion) -> loss.item() every step"}
+
+    # ---- (3) the whole iteration of the reference's loop: + clip_grad_norm_(0.1) + AdamW (fused) + weight re-pack
+    full = None
+    if not args.no_full:
+        model2, crit2 = build()
+        groups = [{"params": [p for n, p in model2.named_parameters() if "backbone" not in n and p.requires_grad], "lr": 1e-4},
+                  {"params": [p for n, p in model2.named_parameters() if "backbone" in n and p.requires_grad], "lr": 1e-5}]
+        opt = FusedAdamW(groups, lr=1e-4, weight_decay=1e-4)
+        step_full = CapturedStep(model2, crit2, optimizer=opt, max_norm=0.1, group=group, use_graph=not args.no_graph)
+        for i in range(warm):
+            call(step_full, devb[i & 1])
+        ms_full = timed(lambda i: call(step_full, devb[i & 1]), steps)
+        eng2 = model2.engine()
+        ms_opt = timed(lambda i: opt.step(max_norm=0.1), 10)
+        ms_pack = timed(lambda i: eng2.pack_weights(), 10)
+        e2e_run(step_full, 2)
+        barrier()
+        e0.record()
+        e2e_run(step_full, steps)
+        e1.record()
+        barrier()
+        ms_full_e2e = e0.elapsed_time(e1) / steps
+        full = {"ms_per_step": ms_full, "value": B * world / ms_full * 1e3, "e2e_value": B * world / ms_full_e2e * 1e3,
+                "optimizer_ms": ms_opt, "repack_ms": ms_pack, "launches_per_step": step_full.launches_per_step,
+                "what": "fwd + criterion + bwd (+ all-reduce) + fused clip_grad_norm_(0.1) + AdamW (2 LR groups) + re-pack "
+                        "of the updated weights into split-bf16 operands, one CUDA graph; optimizer_ms / repack_ms = "
+                        "those two parts launched eagerly on their own"}
+        del step_full, model2, crit2, opt
+
+    # ---- (4) eager launches through model()/criterion() (what the reference's unmodified engine.py drives)
+    eager = None
+    if use_graph and not args.no_full:
+        def eager_step(i):
+            b = devb[i & 1]
+            if st == 2:
+                o, _ = model(b["image"], None, b["rects"])
+            else:
+                o = model(b["image"], b["points"])
+            ld = crit(o, b["targets"])
+            loss = sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict)
+            loss.backward()
+            if world > 1:
+                model.allreduce_grads(group)
+        eager_step(0)
+        eager = {"ms_per_step": timed(eager_step, min(steps, 10)), "what": "same step, ~1000 eager ctypes launches per step"}
+        eager["value"] = B * world / eager["ms_per_step"] * 1e3
 
     line = None
     if rank == 0:
@@ -420,8 +410,19 @@ def run_ours(args):
         eng = model.engine()
         saved_streams = (eng.side_stream, eng.aux_streams)
         eng.side_stream, eng.aux_streams = None, []      # serialise: each GEMM timed alone on one stream
+        b0 = devb[0]
+
+        def plain_step():
+            if st == 2:
+                o, _ = model(b0["image"], None, b0["rects"])
+            else:
+                o = model(b0["image"], b0["points"])
+            ld = crit(o, b0["targets"])
+            sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict).backward()
+
+        plain_step()
         L.GEMM_TRACE, L.CALL_TRACE = [], []
-        step()
+        plain_step()
         torch.cuda.synchronize()
         trace, L.GEMM_TRACE = L.GEMM_TRACE, None
         atrace, L.CALL_TRACE = L.CALL_TRACE, None
@@ -435,7 +436,6 @@ def run_ours(args):
             pass
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         achieved = flops / (gemm_ms * 1e-3) / 1e12
-        # DRAM traffic of the family from the committed ncu capture of the same workload (None for other workloads)
         traffic, traffic_note = None, None
         if args.workload == "c3" and world == 1:
             try:
@@ -456,19 +456,27 @@ def run_ours(args):
                     "timing": "CUDA events around every GEMM launch of one extra step with the side/aux streams disabled "
                               "(in the timed step weight-gradient GEMMs overlap the dgrad chain on a second stream)"}
         roofline_attention = attention_roofline(atrace, peak, ms_step)
-        cb, _ = cpu_arm(args.workload, 2, 1, batch=1) if not args.skip_cpu else ({"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": "skipped"}, 0)
-        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        matcher = matcher_bench(dev) if (st == 2 and not args.skip_matcher) else None
+        if args.skip_cpu:
+            cb = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": "skipped"}
+        else:
+            cb, _ = cpu_arm(args.workload, 2, 1)
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": steps,
+                "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16 (3-pass split-bf16 operands, fp32 accumulate/norms/softmax/loss)",
                 "data": "synthetic",
                 "config": {"workload": workload_desc(args.workload), "global_batch": B * world,
-                           "parallelism": f"dp{world}" + (" (NCCL grad all-reduce)" if world > 1 else ""),
-                           "launch": "CUDA graph replay of the whole step" if use_graph else "eager launches",
-                           "l2": "per-step working set (~20 GB of activations, 50 MB image batch) >> 126 MB L2, no flush needed"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-                "launches_per_step": launches_per_step, "roofline": roofline, "roofline_attention": roofline_attention,
-                "cpu_baseline": cb,
-                "loss": loss_val}
+                           "step": "zero_grad -> forward -> criterion (device Hungarian matching) -> backward"
+                                   + (" -> NCCL all-reduce of the flat gradient buffer" if world > 1 else "")
+                                   + " (SURVEY.md 8d; optimizer reported separately under full_iteration)",
+                           "parallelism": f"dp{world}" + (" (NCCL grad all-reduce + the reference's num_boxes all-reduce)" if world > 1 else ""),
+                           "launch": "counting_detr_b200.CapturedStep: CUDA graph replay of the whole step" if use_graph else "eager launches",
+                           "l2": "per-step working set (~20 GB of activations, 50 MB image batch) >> 126 MB L2, no flush needed; "
+                                 "two alternating input batches"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * steps,
+                "launches_per_step": launches_per_step, "full_iteration": full, "eager_api": eager,
+                "roofline": roofline, "roofline_attention": roofline_attention, "matcher": matcher,
+                "cpu_baseline": cb, "loss": loss_val}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -484,6 +492,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-matcher", action="store_true")
+    ap.add_argument("--no-full", action="store_true", help="skip the full-iteration (optimizer) and eager-API legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,76 @@
+"""Host -> device input staging for the training loop (first slice).
+
+The reference moves every batch with blocking `.to(device)` calls at the top of the iteration
+(A2/engine.py:25-31, A1/engine.py:49-54), so the H2D copy of batch i+1 never overlaps the compute of batch i.
+`DevicePrefetcher` wraps any iterable of batches (dicts / lists / tuples of tensors, arbitrarily nested; non-tensor
+leaves pass through): it pins each host tensor once into reusable pinned staging buffers, issues the copy of the NEXT
+batch on a dedicated copy stream while the caller works on the current one, and hands out device tensors that are
+safe to use on the current stream (event-ordered; double-buffered so that a batch is never overwritten while a step
+still reads it).  The host only ever waits for a copy issued `depth` batches earlier (before re-using its pinned staging buffer).
+"""
+import torch
+
+
+class DevicePrefetcher:
+    def __init__(self, iterable, device, depth=2):
+        self.it = iterable
+        self.dev = torch.device(device)
+        self.depth = max(int(depth), 2)
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self._slots = [dict(pin={}, dev={}, ready=torch.cuda.Event(), free=None) for _ in range(self.depth)]
+        self.h2d_bytes = 0
+
+    def _stage(self, obj, slot, path):
+        if isinstance(obj, torch.Tensor):
+            if obj.device.type == "cuda":
+                return obj
+            key = (path, tuple(obj.shape), obj.dtype)
+            d = slot["dev"].get(key)
+            if d is None:
+                d = slot["dev"][key] = torch.empty(obj.shape, dtype=obj.dtype, device=self.dev)
+            src = obj
+            if not obj.is_pinned():
+                p = slot["pin"].get(key)
+                if p is None:
+                    p = slot["pin"][key] = torch.empty(obj.shape, dtype=obj.dtype).pin_memory()
+                p.copy_(obj)
+                src = p
+            d.copy_(src, non_blocking=True)
+            self.h2d_bytes += obj.numel() * obj.element_size()
+            return d
+        if isinstance(obj, dict):
+            return {k: self._stage(v, slot, path + (k,)) for k, v in obj.items()}
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(self._stage(v, slot, path + (i,)) for i, v in enumerate(obj))
+        return obj
+
+    def _issue(self, batch, i):
+        slot = self._slots[i % self.depth]
+        if i >= self.depth:
+            slot["ready"].synchronize()              # this slot's previous H2D has left its pinned staging buffers
+        if slot["free"] is not None:
+            self.stream.wait_event(slot["free"])     # the step that used this slot's tensors has been enqueued & done
+        with torch.cuda.stream(self.stream):
+            out = self._stage(batch, slot, ())
+            slot["ready"].record(self.stream)
+        return out, slot
+
+    def __iter__(self):
+        it = iter(self.it)
+        i = 0
+        try:
+            nxt = self._issue(next(it), i)
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, slot = nxt
+            i += 1
+            try:
+                nxt = self._issue(next(it), i)       # next batch travels while the caller computes on this one
+            except StopIteration:
+                nxt = None
+            torch.cuda.current_stream(self.dev).wait_event(slot["ready"])
+            yield cur
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.dev))   # everything the caller enqueued on this batch
+            slot["free"] = ev

@@ -545,6 +545,29 @@ class SetCriterion(nn.Module):
         self.last_indices = None
         self.fixed_num_boxes = None      # per-rank target count when it is constant (benchmarks)
         self._nb_dev = self._nb_host = self._nb_last = None
+        self._nb_prepared_for = None
+
+    def prepare_num_boxes(self, targets, dev, group=None):
+        """num_boxes = clamp(all_reduce(sum T) / world, 1) (A2/models/anchor_detr.py:321-325) without the reference's
+        .item() sync: the per-rank count comes from tensor SHAPES, travels through a pinned float and is summed over
+        ranks by the reference's own 1-float all-reduce; the clamp and the division happen inside cdetr_set_loss_fwd.
+        Callers that replay a captured step call this BEFORE the replay (the collective stays outside the graph)."""
+        ws = _world_size()
+        if self._nb_dev is None or self._nb_dev.device != dev:
+            self._nb_host = torch.zeros(1, pin_memory=True)
+            self._nb_dev = torch.zeros(1, device=dev)
+            self._nb_last = None
+        if self.fixed_num_boxes is not None:       # constant, known global count: no collective needed
+            val, reduce = float(self.fixed_num_boxes) * ws, False
+        else:
+            val, reduce = float(sum(int(t["labels"].shape[0]) for t in targets)), ws > 1
+        if reduce or val != self._nb_last:
+            self._nb_host[0] = val
+            self._nb_dev.copy_(self._nb_host, non_blocking=True)
+            self._nb_last = None if reduce else val
+            if reduce:
+                torch.distributed.all_reduce(self._nb_dev, group=group)
+        self._nb_prepared_for = targets
 
     def forward(self, outputs, targets):
         if "aux_outputs" in outputs:
@@ -556,20 +579,9 @@ class SetCriterion(nn.Module):
         # collective so the step can be captured in a CUDA graph without NCCL inside
         dev = outputs["pred_logits"].device
         ws = _world_size()
-        if self._nb_dev is None or self._nb_dev.device != dev:
-            self._nb_host = torch.zeros(1, pin_memory=True)
-            self._nb_dev = torch.zeros(1, device=dev)
-            self._nb_last = None
-        if self.fixed_num_boxes is not None:
-            val, reduce = float(self.fixed_num_boxes) * ws, False
-        else:
-            val, reduce = float(sum(len(t["labels"]) for t in targets)), ws > 1
-        if reduce or val != self._nb_last:
-            self._nb_host[0] = val
-            self._nb_dev.copy_(self._nb_host, non_blocking=True)
-            self._nb_last = None if reduce else val
-            if reduce:
-                torch.distributed.all_reduce(self._nb_dev)
+        if self._nb_prepared_for is not targets:       # not hoisted by the caller (CapturedStep.prepare_num_boxes)
+            self.prepare_num_boxes(targets, dev)
+        self._nb_prepared_for = None
         ce, err, bbox, giou, card, var = _SetLossFn.apply(self, outputs["pred_logits"], outputs["pred_boxes"],
                                                          outputs["pred_vars"], targets, self._nb_dev, 1.0 / ws)
         res = {}

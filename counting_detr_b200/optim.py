@@ -98,6 +98,8 @@ class FusedAdamW(torch.optim.Optimizer):
         self._hyper_last = None
         self._step_dev = None
         self._norm_out = None
+        self._ps = None
+        self._pending_steps = 0
 
     def _ensure(self):
         entries, ps = [], []
@@ -128,6 +130,15 @@ class FusedAdamW(torch.optim.Optimizer):
                 self._norm_out = torch.zeros(3, device=dev)
                 self._hyper_host = torch.zeros(len(self.param_groups), 4).pin_memory()
                 self._hyper_dev = torch.zeros(len(self.param_groups), 4, device=dev)
+        self._ps = ps
+        self.sync_hyper()
+        return self._tb, ps
+
+    def sync_hyper(self):
+        """Mirror param_groups[i]["lr"/"weight_decay"] into the device hyper-parameter array when they changed (an LR
+        scheduler step); a captured optimizer step reads them from there."""
+        if self._hyper_host is None:
+            return
         hyper = [(float(g["lr"]), float(g["weight_decay"])) for g in self.param_groups]
         if hyper != self._hyper_last:
             for i, (lr, wd) in enumerate(hyper):
@@ -135,7 +146,46 @@ class FusedAdamW(torch.optim.Optimizer):
                 self._hyper_host[i, 1] = wd
             self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
             self._hyper_last = hyper
-        return self._tb, ps
+
+    def note_replayed_step(self, n=1):
+        """A CUDA-graph replay ran the captured step() kernels n more times: the device step counter advanced by
+        itself, the host mirrors (state[p]["step"], torch.optim layout) are brought up to date lazily."""
+        self._pending_steps += n
+
+    def _flush_pending(self):
+        if self._pending_steps:
+            for p in self._ps or []:
+                self.state[p]["step"] += self._pending_steps
+            self._pending_steps = 0
+
+    def snapshot(self):
+        """Copy of the optimizer state (device step counter, moments, host step mirrors); see restore()."""
+        self._flush_pending()
+        return {"step_dev": None if self._step_dev is None else self._step_dev.clone(),
+                "state": {p: (st["step"].clone(), st["exp_avg"].clone(), st["exp_avg_sq"].clone())
+                          for p, st in self.state.items() if len(st)}}
+
+    def restore(self, snap):
+        """Undo every step() since snapshot() (CapturedStep rolls its warm-up iterations back with this).  Tensors are
+        restored in place: the pointer table of a captured step stays valid."""
+        self._flush_pending()
+        for p, st in self.state.items():
+            if not len(st):
+                continue
+            old = snap["state"].get(p)
+            if old is None:
+                st["step"].zero_(); st["exp_avg"].zero_(); st["exp_avg_sq"].zero_()
+            else:
+                st["step"].copy_(old[0]); st["exp_avg"].copy_(old[1]); st["exp_avg_sq"].copy_(old[2])
+        if self._step_dev is not None:
+            if snap["step_dev"] is None:
+                self._step_dev.zero_()
+            else:
+                self._step_dev.copy_(snap["step_dev"])
+
+    def state_dict(self):
+        self._flush_pending()
+        return super().state_dict()
 
     @torch.no_grad()
     def step(self, closure=None, max_norm=None):
@@ -145,6 +195,7 @@ class FusedAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        self._flush_pending()
         tb, ps = self._ensure()
         if tb is None:
             return loss

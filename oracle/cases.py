@@ -58,8 +58,10 @@ def oracle_case(name, seed=0):
         total.backward()
         res["losses"] = {k: v.detach() for k, v in losses.items()}
         res["total_loss"] = total.detach()
-        res["grad_fp"], res["grads_small"] = grad_fingerprints({k: v.grad for k, v in sd.items() if v.grad is not None
-                                                                and (".0." in k or not any(f"transformer.{h}." in k for h in HEADS))})
+        # shared heads: one gradient under index 0 (named_parameters() of the reference dedups the aliases)
+        alias = lambda k: any(f"transformer.{h}." in k and f"transformer.{h}.0." not in k for h in HEADS)
+        res["grad_fp"], res["grads_small"] = grad_fingerprints({k: v.grad for k, v in sd.items()
+                                                                if v.grad is not None and not alias(k)})
     return res
 
 

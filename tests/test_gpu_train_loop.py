@@ -1,0 +1,177 @@
+"""The reference's training loop, call for call, on the CUDA path (-m gpu).
+
+Replicates A2/engine.py:24-63 (forward -> criterion -> weighted sum -> .item() -> optimizer.zero_grad() AFTER the
+forward -> backward -> clip_grad_norm_ -> optimizer.step()) with the three parameter groups of A2/main.py:157-189 and
+torch.optim.AdamW, through the `models` shim package (shim/models), and checks the loss trajectory against the CPU
+oracle driven by the very same loop; then the packaged CapturedStep (CUDA-graph replay of the same iteration with the
+fused clip + AdamW) against the eager loop, and the checkpoint-resume filter of A2/main.py:195-209.
+"""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LR, LR_BACKBONE, WD, MAX_NORM = 1e-4, 1e-5, 1e-4, 0.1        # A2/main.py:30-40 defaults
+
+
+def _shim_build(Q):
+    from counting_detr_b200 import synthetic as SY
+    sys.path.insert(0, os.path.join(ROOT, "shim"))
+    try:
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        from models import build_model                      # the reference's import line (A2/main.py:13)
+    finally:
+        sys.path.remove(os.path.join(ROOT, "shim"))
+    model, crit, pp = build_model(SY.default_args(2, num_query_position=Q, device="cuda"))
+    model.load_state_dict(SY.make_state_dict(SY.SynthCfg(stage=2, num_query_position=Q), 0), strict=True)
+    model.to("cuda")
+    return model, crit
+
+
+def _param_groups(named_parameters):
+    """A2/main.py:150-184 with the default --lr_backbone_names ["backbone"], --lr_linear_proj_names []."""
+    named = list(named_parameters)
+    match = lambda n, kws: any(k in n for k in kws)
+    return [{"params": [p for n, p in named if not match(n, ["backbone"]) and not match(n, []) and p.requires_grad], "lr": LR},
+            {"params": [p for n, p in named if match(n, ["backbone"]) and p.requires_grad], "lr": LR_BACKBONE},
+            {"params": [p for n, p in named if match(n, []) and p.requires_grad], "lr": LR * 0.1}]
+
+
+def _batches(n, B, S, T):
+    from counting_detr_b200 import synthetic as SY
+    return [SY.make_inputs(B, S, T=T, seed=10 + i, stage=2) for i in range(n)]
+
+
+def _reference_loop(model, criterion, optimizer, batches, device, clip=torch.nn.utils.clip_grad_norm_):
+    """train_one_epoch, A2/engine.py:14-63, minus logging."""
+    model.train(); criterion.train()
+    hist = []
+    for ret in batches:
+        image = ret["image"].to(device)
+        rects = ret["rects"].to(device)
+        targets = [{"boxes": t["boxes"].to(device), "labels": t["labels"].to(device)} for t in ret["targets"]]
+        outputs, ref_points = model(image, points=None, rects=rects)
+        loss_dict = criterion(outputs, targets)
+        weight_dict = criterion.weight_dict
+        losses = sum(loss_dict[k] * weight_dict[k] for k in loss_dict.keys() if k in weight_dict)
+        loss_value = losses.item()
+        assert loss_value == loss_value
+        optimizer.zero_grad()
+        losses.backward()
+        clip(model.parameters(), MAX_NORM)
+        optimizer.step()
+        hist.append(loss_value)
+    return hist
+
+
+class _OracleModel(torch.nn.Module):
+    """The CPU oracle behind the same (model, criterion) call protocol, so that the SAME loop drives it."""
+
+    def __init__(self, Q):
+        super().__init__()
+        from counting_detr_b200 import synthetic as SY
+        from oracle import cases as OCS, model as OM
+        self.cfg = OM.Config(stage=2, num_query_position=Q)
+        sd = OCS.oracle_state_dict(SY.SynthCfg(stage=2, num_query_position=Q), 0)
+        self.sd = sd
+        self._named = [(k, v) for k, v in sd.items() if v.requires_grad and not any(
+            f"transformer.{h}." in k and f"transformer.{h}.0." not in k for h in OCS.HEADS)]
+
+    def named_parameters(self, *a, **k):
+        return iter(self._named)
+
+    def parameters(self, *a, **k):
+        return iter(v for _, v in self._named)
+
+    def forward(self, image, points=None, rects=None):
+        from oracle import model as OM
+        return OM.forward(self.sd, self.cfg, image, rects=rects)
+
+
+class _OracleCriterion(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        from oracle import criterion as OC
+        self.weight_dict = dict(OC.STAGE2_WEIGHT_DICT)
+
+    def forward(self, outputs, targets):
+        from oracle import criterion as OC
+        return OC.set_criterion(outputs, targets)[0]
+
+
+def test_reference_loop_call_order_tracks_the_oracle():
+    Q, B, S, T, steps = 50, 2, 128, 7, 3
+    batches = _batches(steps, B, S, T)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    om, oc = _OracleModel(Q), _OracleCriterion()
+    ref = _reference_loop(om, oc, torch.optim.AdamW(_param_groups(om.named_parameters()), lr=LR, weight_decay=WD),
+                          batches, "cpu")
+    model, crit = _shim_build(Q)
+    groups = _param_groups(model.named_parameters())
+    assert [len(g["params"]) for g in groups] == [len(g["params"]) for g in _param_groups(om.named_parameters())]
+    got = _reference_loop(model, crit, torch.optim.AdamW(groups, lr=LR, weight_decay=WD), batches, "cuda")
+    assert got[1] != got[0]
+    for a, b in zip(got, ref):
+        assert abs(a - b) <= 1e-3 * abs(b), (got, ref)          # 1e-3 relative on the loss, every step
+
+
+def test_captured_step_matches_the_eager_loop():
+    """CapturedStep = the same iteration (fused clip + AdamW, weight re-pack) replayed as a CUDA graph: identical loss
+    trajectory on changing batches (images, targets AND exemplar rects change every step), parameters equal at the end,
+    optimizer step counter and LR-scheduler changes honoured."""
+    from counting_detr_b200.optim import FusedAdamW, clip_grad_norm_
+    from counting_detr_b200.step import CapturedStep
+    Q, B, S, T, steps = 50, 2, 128, 7, 5
+    batches = _batches(steps, B, S, T)
+    model_a, crit_a = _shim_build(Q)
+    opt_a = FusedAdamW(_param_groups(model_a.named_parameters()), lr=LR, weight_decay=WD)
+    sched_a = torch.optim.lr_scheduler.StepLR(opt_a, 2)
+    eager = []
+    model_a.train()
+    for ret in batches:
+        out, _ = model_a(ret["image"].cuda(), points=None, rects=ret["rects"].cuda())
+        ld = crit_a(out, [{k: v.cuda() for k, v in t.items()} for t in ret["targets"]])
+        loss = sum(ld[k] * crit_a.weight_dict[k] for k in ld if k in crit_a.weight_dict)
+        opt_a.zero_grad()
+        loss.backward()
+        opt_a.step(max_norm=MAX_NORM)
+        sched_a.step()
+        eager.append(loss.item())
+    model_b, crit_b = _shim_build(Q)
+    model_b.train()
+    opt_b = FusedAdamW(_param_groups(model_b.named_parameters()), lr=LR, weight_decay=WD)
+    sched_b = torch.optim.lr_scheduler.StepLR(opt_b, 2)
+    step = CapturedStep(model_b, crit_b, optimizer=opt_b, max_norm=MAX_NORM)
+    replayed = []
+    for ret in batches:
+        ld, total = step(ret["image"].pin_memory(), [{"boxes": t["boxes"].pin_memory(), "labels": t["labels"]} for t in ret["targets"]],
+                         rects=ret["rects"].pin_memory())
+        sched_b.step()
+        replayed.append(total.item())
+    assert step._graph is not None and step.launches_per_step > 500
+    for a, b in zip(replayed, eager):
+        assert abs(a - b) <= 2e-5 * abs(b), (replayed, eager)   # same kernels; split-K atomics reorder fp32 sums
+    for (n, p), q in zip(model_a.named_parameters(), model_b.parameters()):
+        if p.requires_grad:
+            assert (p - q).abs().max().item() <= 1e-6 + 1e-4 * p.abs().max().item(), n
+    sd = opt_b.state_dict()
+    assert float(sd["state"][0]["step"]) == steps
+
+
+def test_resume_filter_of_main_py():
+    """A2/main.py:195-209: checkpoint['model'] filtered by key and 'transformer.pattern.', load_state_dict(strict=False)."""
+    from counting_detr_b200 import synthetic as SY
+    model, _ = _shim_build(50)
+    ckpt = {"model": SY.make_state_dict(SY.SynthCfg(stage=2, num_query_position=50), 7)}
+    ckpt["model"]["transformer.total_params"] = torch.zeros(1)
+    own = model.state_dict()
+    assert len(own) == 547
+    pretrained = {k: v for k, v in ckpt["model"].items() if k in own and "transformer.pattern." not in k}
+    missing, unexpected = model.load_state_dict(pretrained, strict=False)
+    assert missing == ["transformer.pattern.weight"] and unexpected == []
+    assert torch.equal(model.state_dict()["backbone.body.layer3.0.conv2.weight"].cpu(),
+                       ckpt["model"]["backbone.body.layer3.0.conv2.weight"])

@@ -138,3 +138,21 @@ def test_bench_attention_flop_accounting_matches_survey():
                    for n in ("cdetr_rcda_bwd_q_tc", "cdetr_rcda_bwd_v_tc", "cdetr_rcda_bwd_k"))
                + bench.attention_macs("cdetr_mha_bwd", (1, 300, E, nh)))
     assert bwd == 2 * fwd
+
+
+def test_models_shim_is_the_reference_import_line():
+    """shim/models lets the reference's `from models import build_model` (A2/main.py:13) resolve to the B200 path."""
+    import importlib
+    import sys as _sys
+    shim = os.path.join(ROOT, "shim")
+    saved = {k: _sys.modules.pop(k) for k in list(_sys.modules) if k == "models" or k.startswith("models.")}
+    _sys.path.insert(0, shim)
+    try:
+        m = importlib.import_module("models")
+        from counting_detr_b200 import models as ours
+        assert m.build_model is ours.build_model and m.build is ours.build
+    finally:
+        _sys.path.remove(shim)
+        for k in [k for k in _sys.modules if k == "models" or k.startswith("models.")]:
+            del _sys.modules[k]
+        _sys.modules.update(saved)
