@@ -157,7 +157,8 @@ def test_captured_step_matches_the_eager_loop():
         assert abs(a - b) <= 2e-5 * abs(b), (replayed, eager)   # same kernels; split-K atomics reorder fp32 sums
     for (n, p), q in zip(model_a.named_parameters(), model_b.parameters()):
         if p.requires_grad:
-            assert (p - q).abs().max().item() <= 1e-6 + 1e-4 * p.abs().max().item(), n
+            # AdamW turns gradient noise (split-K atomic order) into a fraction of lr per step: bound 0.2 * lr * steps
+            assert (p - q).abs().max().item() <= 0.2 * LR * steps, n
     sd = opt_b.state_dict()
     assert float(sd["state"][0]["step"]) == steps
 
