@@ -47,6 +47,63 @@ void cdetr_set_error(const char* fmt, ...);
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------
+// Per-DEVICE (not per-process) launch configuration.  The dynamic-shared-memory opt-in is a per-device function
+// attribute and the SM count is a device property, so a process that drives several GPUs must not cache either in a
+// process-wide flag.  The caches below are indexed by the current device; races between host threads are benign
+// (the same value is written).  Tuning hooks (environment variables used by tools/ and the tests) are read ONCE.
+// ---------------------------------------------------------------------------------------------
+constexpr int CDETR_MAX_DEVICES = 64;
+struct DevAttrCache { int v[CDETR_MAX_DEVICES]; };
+template <typename K>
+static inline cudaError_t cdetr_ensure_smem(K kern, int bytes, DevAttrCache* c) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool cached = dev >= 0 && dev < CDETR_MAX_DEVICES;
+  if (cached && c->v[dev] >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && cached) c->v[dev] = bytes;
+  return e;
+}
+static inline cudaError_t cdetr_num_sms(int* out) {
+  static DevAttrCache cache = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool cached = dev >= 0 && dev < CDETR_MAX_DEVICES;
+  if (cached && cache.v[dev] > 0) { *out = cache.v[dev]; return cudaSuccess; }
+  e = cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess && cached) cache.v[dev] = *out;
+  return e;
+}
+struct CdetrTuning {
+  int gemm_pair;      // CDETR_GEMM_PAIR: -1 heuristic, 0 never, 1 whenever eligible
+  int gemm_tma_epi;   // CDETR_GEMM_TMA_EPI: 0 forces the generic epilogue
+  int gemm_resident;  // CDETR_GEMM_RESIDENT=1: resident-B schedule
+  int gemm_stages;    // CDETR_GEMM_STAGES: operand ring depth override (0 = auto)
+  int gemm_epi_debug; // CDETR_GEMM_EPI_DEBUG: epilogue ablation bits (tools/epi_debug.py)
+  int pdl;            // CDETR_PDL=1: programmatic dependent launch of the GEMM
+  int pdl_light;      // CDETR_PDL_LIGHT=1: ... of the light kernels
+  int mha_legacy;     // CDETR_MHA_LEGACY=1: CUDA-core decoder self-attention
+};
+static inline const CdetrTuning& cdetr_tuning() {
+  static const CdetrTuning t = [] {
+    auto geti = [](const char* name, int dflt) { const char* e = getenv(name); return e != nullptr ? atoi(e) : dflt; };
+    CdetrTuning x;
+    x.gemm_pair = geti("CDETR_GEMM_PAIR", -1);
+    x.gemm_tma_epi = geti("CDETR_GEMM_TMA_EPI", 1);
+    x.gemm_resident = geti("CDETR_GEMM_RESIDENT", 0);
+    x.gemm_stages = geti("CDETR_GEMM_STAGES", 0);
+    x.gemm_epi_debug = geti("CDETR_GEMM_EPI_DEBUG", 0);
+    x.pdl = geti("CDETR_PDL", 0);
+    x.pdl_light = geti("CDETR_PDL_LIGHT", 0);
+    x.mha_legacy = geti("CDETR_MHA_LEGACY", 0);
+    return x;
+  }();
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------
 // split-bf16 ("hi/lo planes") number format.
 //   x (fp32)  ->  hi = bf16_rn(x),  lo = bf16_rn(x - float(hi));   x ~= hi + lo (|err| <= 2^-18|x|)
 // Activations and packed weights are stored as two bf16 planes so that TMA can feed tcgen05
@@ -215,14 +272,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // (GEMM, attention cores: > 100 KB of shared memory) are launched normally - pre-resident heavy CTAs crowd out the
 // weight-gradient side stream (measured +0.6 ms) - but call pdl_trigger() so that light successors can pre-launch.
 // CDETR_PDL_LIGHT=1 enables the attribute (off by default: no measurable gain inside the captured graph).
-inline bool cdetr_pdl_light_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CDETR_PDL_LIGHT");
-    v = (e != nullptr && atoi(e) != 0) ? 1 : 0;   // opt-in: measured 21.67 (on) vs 21.57 ms (off) on the C3 step
-  }
-  return v != 0;
-}
+inline bool cdetr_pdl_light_enabled() { return cdetr_tuning().pdl_light != 0; }   // opt-in: 21.67 (on) vs 21.57 ms (off) on C3
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_light(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                 Args&&... args) {

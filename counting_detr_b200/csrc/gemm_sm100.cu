@@ -886,12 +886,9 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   CDETR_CHECK_ARG(g->out_f32 != nullptr || g->out_split.base != nullptr, "gemm: no output");
   const bool nt = g->mode == 1;
 
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    CDETR_CHECK_CUDA(cudaGetDevice(&dev));
-    CDETR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int num_sms = 0;
+  CDETR_CHECK_CUDA(cdetr_num_sms(&num_sms));
+  const CdetrTuning& tune = cdetr_tuning();
   int bn = g->block_n;
   if (bn <= 0) {
     // measured on B200 (tools/gemm_sweep.py, profiles/r01_gemm_sweep_v8.txt).  The GEMM family is bound by the
@@ -917,8 +914,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   // the L2 -> SM operand stream).  CDETR_GEMM_PAIR: 0 never, 1 whenever eligible, unset = heuristic below.
   bool pair = false;
   {
-    const char* e = getenv("CDETR_GEMM_PAIR");
-    const int pair_mode = e != nullptr ? atoi(e) : -1;
+    const int pair_mode = tune.gemm_pair;
     const bool eligible = !nt && g->N >= 256 && g->M >= 256 && g->split_k <= 1 && (g->block_n <= 0 || g->block_n == 256);
     if (pair_mode == 1) pair = eligible;
     else if (pair_mode == -1)   // tools/pair_sweep.py (profiles/r01_pair_sweep_v18.txt): 1.05-1.8x for K >= 512, <= 1.0x below
@@ -1012,8 +1008,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
                  (!has_os || tma_ok_split(g->out_split)) && (!has_as || tma_ok_split(g->add_split)) &&
                  (!has_af || tma_ok_f32(g->add_f32, g->ld_add_f32)) &&
                  (!has_mk || ((reinterpret_cast<uintptr_t>(g->mask.base) & 15) == 0 && g->mask.ld % 8 == 0));
-  if (const char* e = getenv("CDETR_GEMM_TMA_EPI"))
-    if (atoi(e) == 0) tma_epi = false;
+  if (tune.gemm_tma_epi == 0) tma_epi = false;
   const uint32_t old_staging = 8u * 32u * 33u * 4u;
   uint32_t epi_buf = 4096u + (has_mk ? 2048u : 0u) + ((has_of && has_os) ? 4096u : 0u);
   int epi_nb = 2;
@@ -1036,8 +1031,8 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   if (stages < 1) stages = 1;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2 && smem_budget >= 2 * stage_bytes) stages = 2;
-  if (const char* e = getenv("CDETR_GEMM_STAGES")) {  // tuning hook (tools/gemm_sweep.py)
-    const int f = atoi(e);
+  if (tune.gemm_stages > 0) {  // tuning hook (tools/gemm_sweep.py)
+    const int f = tune.gemm_stages;
     if (f >= 1 && f <= MAX_STAGES && (uint32_t)f * stage_bytes <= smem_budget) stages = f;
   }
   CDETR_CHECK_ARG((uint32_t)stages * stage_bytes <= smem_budget, "gemm: tile does not fit shared memory");
@@ -1050,8 +1045,8 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   // resident-B CTA per SM (8 epilogue warps) lost to two streaming CTAs (16 epilogue warps): 23.0 vs 21.6 ms of GEMM
   // per C3 step.  Off unless CDETR_GEMM_RESIDENT=1.
   bool resident = false;
-  if (const char* e = getenv("CDETR_GEMM_RESIDENT")) {
-    const int f = atoi(e);
+  {
+    const int f = tune.gemm_resident;
     if (f == 1) resident = !pair && !nt && !conv && splits == 1 && (uint32_t)num_kb * b_bytes + 2 * a_bytes + 8u * epi_buf <= smem_max;
   }
   ka.resident_b = 0;
@@ -1067,8 +1062,8 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
     }
     int st = budget > slab ? (int)((budget - slab) / a_bytes) : 0;
     if (st > MAX_STAGES) st = MAX_STAGES;
-    if (const char* e = getenv("CDETR_GEMM_STAGES")) {
-      const int f = atoi(e);
+    if (tune.gemm_stages > 0) {
+      const int f = tune.gemm_stages;
       if (f >= 1 && f <= st) st = f;
     }
     if (st >= 2) {
@@ -1087,10 +1082,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   ka.epi_off_mask = 4096u;
   ka.epi_off_out2 = 4096u + (has_mk ? 2048u : 0u);
   ka.epi_add_kind = has_as ? 1 : (has_af ? 2 : 0);
-  {
-    const char* e = getenv("CDETR_GEMM_EPI_DEBUG");
-    ka.epi_debug = e != nullptr ? atoi(e) : 0;
-  }
+  ka.epi_debug = tune.gemm_epi_debug;
   ka.dbg = (g_dbg_buf != nullptr && g_dbg_next < g_dbg_cap) ? g_dbg_buf + 8 * (g_dbg_next++) : nullptr;
   const size_t smem_bytes = operand_bytes + staging_bytes + tail_bytes + 1024;
 
@@ -1144,18 +1136,9 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   }
   dim3 grid(nctas);
   auto kern = nt ? gemm_split_kernel<true, false> : (pair ? gemm_split_kernel<false, true> : gemm_split_kernel<false, false>);
-  static size_t configured[3] = {0, 0, 0};
-  const int ki = nt ? 1 : (pair ? 2 : 0);
-  if (configured[ki] < smem_bytes) {
-    CDETR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          227 * 1024));
-    configured[ki] = 227 * 1024;
-  }
-  static int use_pdl = -1;
-  if (use_pdl < 0) {
-    const char* e = getenv("CDETR_PDL");
-    use_pdl = (e != nullptr && atoi(e) != 0) ? 1 : 0;   // opt-in: measured +0.6 ms on the C3 step (early CTAs of the successor crowd the side streams)
-  }
+  static DevAttrCache configured[3] = {};
+  CDETR_CHECK_CUDA(cdetr_ensure_smem(kern, 227 * 1024, &configured[nt ? 1 : (pair ? 2 : 0)]));
+  const int use_pdl = tune.pdl;   // opt-in: measured +0.6 ms on the C3 step (early CTAs of the successor crowd the side streams)
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;

@@ -291,7 +291,7 @@ extern "C" int cdetr_lsap(const float* cost, const int* tgt_off, int B, int Q, i
   const int stage_cost = base + slab <= 200 * 1024 ? 1 : 0;
   if (ncap <= 384) {
     const size_t smem = stage_cost ? base + slab : lsap_smem(ncap, 32);
-    { static bool once = false; if (!once) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(lsap_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); once = true; } }
+    { static DevAttrCache cfg = {}; CDETR_CHECK_CUDA(cdetr_ensure_smem(lsap_kernel<true>, 200 * 1024, &cfg)); }
     lsap_kernel<true><<<B, 32, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status, stage_cost, (int)base);
   } else {
     int nt = 256;
@@ -299,7 +299,7 @@ extern "C" int cdetr_lsap(const float* cost, const int* tgt_off, int B, int Q, i
     if (ncap > 2048) nt = 1024;
     const size_t smem = lsap_smem(ncap, nt);
     CDETR_CHECK_ARG(smem <= 200 * 1024, "lsap: problem too large for shared memory (n=%d)", ncap);
-    { static bool once_lsap_kernel_false_ = false; if (!once_lsap_kernel_false_) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(lsap_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); once_lsap_kernel_false_ = true; } }
+    { static DevAttrCache cfg = {}; CDETR_CHECK_CUDA(cdetr_ensure_smem(lsap_kernel<false>, 200 * 1024, &cfg)); }
     lsap_kernel<false><<<B, nt, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status, 0, 0);
   }
   CDETR_CHECK_LAUNCH();

@@ -232,14 +232,7 @@ __global__ void __launch_bounds__(QPB * SPLIT) mha_bwd_kv_kernel(const MhaArgs a
 }  // namespace
 
 // tensor-core path (mha_tc.cu) whenever one head fits in shared memory; CDETR_MHA_LEGACY=1 forces the CUDA-core kernels
-static bool use_tc(int L) {
-  static int legacy = -1;
-  if (legacy < 0) {
-    const char* e = getenv("CDETR_MHA_LEGACY");
-    legacy = (e != nullptr && atoi(e) != 0) ? 1 : 0;
-  }
-  return legacy == 0 && mha_tc_fits(L) != 0;
-}
+static bool use_tc(int L) { return cdetr_tuning().mha_legacy == 0 && mha_tc_fits(L) != 0; }
 
 extern "C" int cdetr_mha_fwd(int B, int L, int E, int nh, const float* q, const float* k, const float* v,
                              int64_t ldq, cdetr_split_t o, float* lse, cdetr_stream_t s) {

@@ -379,23 +379,17 @@ int mha_tc_fits(int L) {
 int mha_fwd_tc_launch(const MhaArgs& a, cudaStream_t s) {
   const int Lp = (a.L + 15) / 16 * 16;
   const size_t smem = smem_fwd(Lp);
-  static size_t configured = 0;
-  if (configured < smem) {
-    CDETR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    configured = SMEM_MAX;
-  }
+  static DevAttrCache cfg = {};
+  CDETR_CHECK_CUDA(cdetr_ensure_smem(mha_fwd_tc_kernel, (int)SMEM_MAX, &cfg));
   mha_fwd_tc_kernel<<<dim3(a.nh, a.B, 1), NTHREADS, smem, s>>>(a, Lp);   // ~160 registers x 320 threads: one CTA per SM
   CDETR_CHECK_LAUNCH();
   return 0;
 }
 int mha_bwd_tc_launch(const MhaArgs& a, cudaStream_t s) {
   const int Lp = (a.L + 15) / 16 * 16;
-  static bool configured = false;
-  if (!configured) {
-    CDETR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_q_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    CDETR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX));
-    configured = true;
-  }
+  static DevAttrCache cfg_q = {}, cfg_kv = {};
+  CDETR_CHECK_CUDA(cdetr_ensure_smem(mha_bwd_q_tc_kernel, (int)SMEM_MAX, &cfg_q));
+  CDETR_CHECK_CUDA(cdetr_ensure_smem(mha_bwd_kv_tc_kernel, (int)SMEM_MAX, &cfg_kv));
   mha_bwd_q_tc_kernel<<<dim3(a.nh, a.B, 1), NTHREADS, smem_bwd_q(Lp), s>>>(a, Lp);
   CDETR_CHECK_LAUNCH();
   mha_bwd_kv_tc_kernel<<<dim3(a.nh, a.B, 1), NTHREADS, smem_bwd_kv(Lp), s>>>(a, Lp);

@@ -450,7 +450,7 @@ extern "C" int cdetr_rcda_fwd(int B, int L, int H, int W, int E, int nh, const f
   CDETR_CHECK_ARG(fwd_smem(H, W, T, Hc) <= budget, "rcda_fwd: H=%d W=%d do not fit shared memory", H, W);
   a.Hc = Hc;
   const size_t smem = fwd_smem(H, W, T, Hc);
-  { static bool once_rcda_fwd_kernel = false; if (!once_rcda_fwd_kernel) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); once_rcda_fwd_kernel = true; } }
+  { static DevAttrCache cfg = {}; CDETR_CHECK_CUDA(cdetr_ensure_smem(rcda_fwd_kernel, 227 * 1024, &cfg)); }
   dim3 grid(cdiv(L, T), nh, B);
   rcda_fwd_kernel<<<grid, T, smem, reinterpret_cast<cudaStream_t>(s)>>>(a);
   CDETR_CHECK_LAUNCH();
@@ -489,12 +489,12 @@ extern "C" int cdetr_rcda_bwd(int B, int L, int H, int W, int E, int nh, const f
   while (Hc > 1 && bwdq_smem(H, W, T, Hc) > budget) --Hc;
   CDETR_CHECK_ARG(bwdq_smem(H, W, T, Hc) <= budget, "rcda_bwd: H=%d W=%d do not fit shared memory", H, W);
   a.Hc = Hc;
-  { static bool once_rcda_bwd_q_kernel = false; if (!once_rcda_bwd_q_kernel) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); once_rcda_bwd_q_kernel = true; } }
+  { static DevAttrCache cfg = {}; CDETR_CHECK_CUDA(cdetr_ensure_smem(rcda_bwd_q_kernel, 227 * 1024, &cfg)); }
   rcda_bwd_q_kernel<<<dim3(cdiv(L, T), nh, B), T, bwdq_smem(H, W, T, Hc), s>>>(a);
   CDETR_CHECK_LAUNCH();
   const int TV = 256;
   const size_t smem_v = sizeof(float) * ((size_t)TQ * HD + (size_t)(W + H) * (TQ + 1));
-  { static bool once_rcda_bwd_v_kernel = false; if (!once_rcda_bwd_v_kernel) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); once_rcda_bwd_v_kernel = true; } }
+  { static DevAttrCache cfg = {}; CDETR_CHECK_CUDA(cdetr_ensure_smem(rcda_bwd_v_kernel, 227 * 1024, &cfg)); }
   rcda_bwd_v_kernel<<<dim3(cdiv(H * W, TV), nh, B), TV, smem_v, s>>>(a);
   CDETR_CHECK_LAUNCH();
   launch_bwd_k(a, s);
@@ -523,7 +523,7 @@ extern "C" int cdetr_rcda_bwd_kv(int B, int L, int H, int W, int E, int nh, cons
   a.ld_g = dkr.ld;
   const int TV = 256;
   const size_t smem_v = sizeof(float) * ((size_t)TQ * HD + (size_t)(W + H) * (TQ + 1));
-  { static bool once = false; if (!once) { CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); once = true; } }
+  { static DevAttrCache cfg = {}; CDETR_CHECK_CUDA(cdetr_ensure_smem(rcda_bwd_v_kernel, 227 * 1024, &cfg)); }
   rcda_bwd_v_kernel<<<dim3(cdiv(H * W, TV), nh, B), TV, smem_v, s>>>(a);
   CDETR_CHECK_LAUNCH();
   launch_bwd_k(a, s);

@@ -16,7 +16,8 @@
 //               split-bf16 A operand of the main contraction (manual SWIZZLE_64B), then the epilogue:
 //               tcgen05.ld of T[q, h, 0:32] and acc += A_c[q,h] * T   (the only CUDA-core FMAs: 1/32 of the MACs)
 // The reference materialises [B*heads, L, W, 32] in HBM (A2/models/row_column_decoupled_attention.py:262-291);
-// here it lives in TMEM only.  Limits of this kernel: H, W <= 32 (512x512 inputs); larger maps use rcda.cu.
+// here it lives in TMEM only.  The kernels of this file keep the head's whole V slice resident: H, W <= 32 (512x512
+// inputs); 32 < max(H, W) <= 64 (800x800: 50x50) dispatches to the streaming variants in rcda_tc64.cu.
 #include "common.cuh"
 #include "../../include/cdetr.h"
 
@@ -653,7 +654,8 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
 // operand), the attention maps of those queries staged in shared memory, and for each 128-row tile of key
 // positions the compute warps build P[(h,w), q] = A_c A_r as a split-bf16 K-major A operand (SWIZZLE_128B,
 // double buffered) which one thread multiplies into the tile's 32 TMEM columns: the [L, H*W] outer-product
-// matrix exists only 32 KB at a time.  All ceil(HW/128) accumulators (<= 256 TMEM columns) stay resident.
+// matrix exists only 32 KB at a time.  The accumulators of a CTA's slice of key positions (<= 8 tiles = 256 TMEM
+// columns) stay resident; H, W <= 64 (the staged maps take max(H,W) rows: two CTAs per SM up to ~52 x 52).
 constexpr int VK = 64;                                   // queries per k block
 constexpr uint32_t P_TILE_BYTES = 128 * VK * 2;          // one plane of the P tile: 16 KB
 constexpr uint32_t DO_PLANE_BYTES = VK * HD * 2;         // 4 KB
@@ -666,7 +668,8 @@ struct TcBwdVArgs {
   __nv_bfloat16 *dv_hi, *dv_lo;
   int64_t ld_g;
   uint32_t idesc;
-  int tiles_per_cta;   // key-position tiles (of 128) per CTA: blockIdx.z selects the slice of positions
+  int tiles_per_cta;   // key-position tiles (of 128) per CTA: blockIdx.z selects the slice of positions (<= 8)
+  int kp;              // rows of the staged attention maps: max(H, W) rounded up to 8 (<= 64)
 };
 
 __global__ void __launch_bounds__(320, 2)
@@ -676,9 +679,9 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Ps = smem;                                    // [2 bufs][2 planes][128][64] bf16, SW128 K-major
   uint8_t* Ds = Ps + 4 * P_TILE_BYTES;                   // [2 bufs][2 planes][64 q][32 c] bf16, SW64
-  float* ars = reinterpret_cast<float*>(Ds + 4 * DO_PLANE_BYTES);   // [32][MAP_LD]
-  float* acs = ars + 32 * MAP_LD;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(acs + 32 * MAP_LD);
+  float* ars = reinterpret_cast<float*>(Ds + 4 * DO_PLANE_BYTES);   // [kp][MAP_LD]
+  float* acs = ars + a.kp * MAP_LD;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(acs + a.kp * MAP_LD);
   uint64_t* d_full = bars;       // [2]
   uint64_t* d_empty = bars + 2;  // [2]
   uint64_t* p_full = bars + 4;   // [2]
@@ -760,7 +763,7 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
     for (int kb = 0; kb < nkb; ++kb) {
       const int q0 = kb * VK;
       asm volatile("bar.sync 1, 256;" ::: "memory");     // previous block's tiles are all built
-      for (int i = ct; i < 32 * VK; i += 256) {
+      for (int i = ct; i < a.kp * VK; i += 256) {
         const int k = i / VK, qq = i % VK;
         const bool qok = q0 + qq < a.L;
         const int mo = k * MAP_LD + (qq >> 5) * 36 + (qq & 31);
@@ -853,16 +856,27 @@ EncodeTiledFn encode_fn() {
 
 }  // namespace
 
-// v: split [B*H*W, E] (the value projection); everything else as cdetr_rcda_fwd.  Requires H, W <= 32.
+// rcda_tc64.cu: the same kernels for 32 < max(H, W) <= 64 (V streamed through a TMA ring instead of resident)
+int rcda_fwd_tc64_launch(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc, const float* kr,
+                         const float* kc, cdetr_split_t v, const uint8_t* mask_row, const uint8_t* mask_col, float* ar,
+                         float* ac, cdetr_split_t o, cudaStream_t s);
+int rcda_bwd_q_tc64_launch(int B, int L, int H, int W, int E, int nh, const float* kr, const float* kc, cdetr_split_t v,
+                           const float* ar, const float* ac, const float* d_o, float* dsr, float* dsc, cdetr_split_t dqr,
+                           cdetr_split_t dqc, cudaStream_t s);
+
+// v: split [B*H*W, E] (the value projection); everything else as cdetr_rcda_fwd.  Requires H, W <= 64.
 extern "C" int cdetr_rcda_fwd_tc(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc,
                                  const float* kr, const float* kc, cdetr_split_t v, const uint8_t* mask_row,
                                  const uint8_t* mask_col, float* ar, float* ac, cdetr_split_t o,
                                  cdetr_stream_t s) {
   CDETR_CHECK_ARG(E == nh * HD, "rcda_fwd_tc: head dim must be 32");
-  CDETR_CHECK_ARG(H >= 1 && W >= 1 && H <= HP && W <= WP, "rcda_fwd_tc: H, W must be <= 32 (got %d x %d)", H, W);
+  CDETR_CHECK_ARG(H >= 1 && W >= 1 && H <= 64 && W <= 64, "rcda_fwd_tc: H, W must be <= 64 (got %d x %d)", H, W);
   CDETR_CHECK_ARG(qr && qc && kr && kc && v.base && ar && ac && o.base, "rcda_fwd_tc: null pointer");
   CDETR_CHECK_ARG(v.ld % 8 == 0 && v.plane % 8 == 0 && (reinterpret_cast<uintptr_t>(v.base) & 15) == 0,
                   "rcda_fwd_tc: V must be 16-byte aligned with ld/plane multiples of 8");
+  if (H > HP || W > WP)
+    return rcda_fwd_tc64_launch(B, L, H, W, E, nh, qr, qc, kr, kc, v, mask_row, mask_col, ar, ac, o,
+                                reinterpret_cast<cudaStream_t>(s));
   EncodeTiledFn fn = encode_fn();
   if (!fn) { cdetr_set_error("cuTensorMapEncodeTiled entry point unavailable"); return CDETR_ERR_CUDA; }
   CUtensorMap tm;
@@ -882,11 +896,8 @@ extern "C" int cdetr_rcda_fwd_tc(int B, int L, int H, int W, int E, int nh, cons
   a.idesc = make_idesc_bf16_f32(TQ, 256, 0, 1);
   a.idesc_s = make_idesc_bf16_f32(TQ, 32, 0, 0);
   const size_t smem = 2 * V_PLANE_BYTES + 4 * A_PLANE_BYTES + 2 * 32 * HD * sizeof(float) + 128 + 1024;
-  static bool once = false;
-  if (!once) {
-    CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    once = true;
-  }
+  static DevAttrCache cfg = {};
+  CDETR_CHECK_CUDA(cdetr_ensure_smem(rcda_fwd_tc_kernel, (int)smem, &cfg));
   rcda_fwd_tc_kernel<<<dim3(cdiv(L, 2 * TQ), nh, B), 320, smem, reinterpret_cast<cudaStream_t>(s)>>>(tm, a);
   CDETR_CHECK_LAUNCH();
   return 0;
@@ -914,9 +925,12 @@ extern "C" int cdetr_rcda_bwd_q_tc(int B, int L, int H, int W, int E, int nh, co
                                    cdetr_split_t v, const float* ar, const float* ac, const float* d_o, float* dsr,
                                    float* dsc, cdetr_split_t dqr, cdetr_split_t dqc, cdetr_stream_t s) {
   CDETR_CHECK_ARG(E == nh * HD, "rcda_bwd_q_tc: head dim must be 32");
-  CDETR_CHECK_ARG(H >= 1 && W >= 1 && H <= HP && W <= WP, "rcda_bwd_q_tc: H, W must be <= 32");
+  CDETR_CHECK_ARG(H >= 1 && W >= 1 && H <= 64 && W <= 64, "rcda_bwd_q_tc: H, W must be <= 64");
   CDETR_CHECK_ARG(kr && kc && v.base && ar && ac && d_o && dsr && dsc && dqr.base && dqc.base, "rcda_bwd_q_tc: null pointer");
   CDETR_CHECK_ARG(dqr.ld == dqc.ld, "rcda_bwd_q_tc: gradient tensors must share ld");
+  if (H > HP || W > WP)
+    return rcda_bwd_q_tc64_launch(B, L, H, W, E, nh, kr, kc, v, ar, ac, d_o, dsr, dsc, dqr, dqc,
+                                  reinterpret_cast<cudaStream_t>(s));
   CUtensorMap tm;
   int rc = make_v_map(&tm, v, B, H, W, E);
   if (rc) return rc;
@@ -929,11 +943,8 @@ extern "C" int cdetr_rcda_bwd_q_tc(int B, int L, int H, int W, int E, int nh, co
   a.idesc = make_idesc_bf16_f32(TQ, 256, 0, 0);
   a.idesc_q = make_idesc_bf16_f32(TQ, 32, 0, 1);
   const size_t smem = 2 * V_PLANE_BYTES + 4 * A_PLANE_BYTES + 4 * 32 * TQ * sizeof(float) + 128 + 1024;
-  static bool once = false;
-  if (!once) {
-    CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_q_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    once = true;
-  }
+  static DevAttrCache cfg = {};
+  CDETR_CHECK_CUDA(cdetr_ensure_smem(rcda_bwd_q_tc_kernel, (int)smem, &cfg));
   rcda_bwd_q_tc_kernel<<<dim3(cdiv(L, 2 * TQ), nh, B), 320, smem, reinterpret_cast<cudaStream_t>(s)>>>(tm, a);
   CDETR_CHECK_LAUNCH();
   return 0;
@@ -943,7 +954,7 @@ extern "C" int cdetr_rcda_bwd_q_tc(int B, int L, int H, int W, int E, int nh, co
 extern "C" int cdetr_rcda_bwd_v_tc(int B, int L, int H, int W, int E, int nh, const float* ar, const float* ac,
                                    cdetr_split_t d_o, cdetr_split_t dv, cdetr_stream_t s) {
   CDETR_CHECK_ARG(E == nh * HD, "rcda_bwd_v_tc: head dim must be 32");
-  CDETR_CHECK_ARG(H >= 1 && W >= 1 && H <= 32 && W <= 32, "rcda_bwd_v_tc: H, W must be <= 32");
+  CDETR_CHECK_ARG(H >= 1 && W >= 1 && H <= 64 && W <= 64, "rcda_bwd_v_tc: H, W must be <= 64");
   CDETR_CHECK_ARG(ar && ac && d_o.base && dv.base, "rcda_bwd_v_tc: null pointer");
   CDETR_CHECK_ARG(d_o.ld % 8 == 0 && d_o.plane % 8 == 0 && (reinterpret_cast<uintptr_t>(d_o.base) & 15) == 0,
                   "rcda_bwd_v_tc: dO must be 16-byte aligned with ld/plane multiples of 8");
@@ -962,22 +973,18 @@ extern "C" int cdetr_rcda_bwd_v_tc(int B, int L, int H, int W, int E, int nh, co
   a.B = B; a.L = L; a.H = H; a.W = W; a.E = E; a.nh = nh; a.ar = ar; a.ac = ac;
   a.dv_hi = reinterpret_cast<__nv_bfloat16*>(dv.base); a.dv_lo = a.dv_hi + dv.plane; a.ld_g = dv.ld;
   a.idesc = make_idesc_bf16_f32(128, HD, 0, 1);
-  const size_t smem = 4 * P_TILE_BYTES + 4 * DO_PLANE_BYTES + 2 * 32 * MAP_LD * sizeof(float) + 128 + 1024;
-  static bool once = false;
-  if (!once) {
-    CDETR_CHECK_CUDA(cudaFuncSetAttribute(rcda_bwd_v_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    once = true;
-  }
-  // split the key positions over enough CTAs to fill the machine at two CTAs per SM (one wave)
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    CDETR_CHECK_CUDA(cudaGetDevice(&dev));
-    CDETR_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  a.kp = ((H > W ? H : W) + 7) / 8 * 8;
+  const size_t smem = 4 * P_TILE_BYTES + 4 * DO_PLANE_BYTES + 2 * (size_t)a.kp * MAP_LD * sizeof(float) + 128 + 1024;
+  static DevAttrCache cfg = {};
+  CDETR_CHECK_CUDA(cdetr_ensure_smem(rcda_bwd_v_tc_kernel, 4 * P_TILE_BYTES + 4 * DO_PLANE_BYTES + 2 * 64 * MAP_LD * 4 + 128 + 1024, &cfg));
+  // split the key positions over enough CTAs to fill the machine at two CTAs per SM (one wave); a CTA keeps at most
+  // 8 position tiles (256 TMEM columns, two CTAs per SM) resident
+  int num_sms = 0;
+  CDETR_CHECK_CUDA(cdetr_num_sms(&num_sms));
   const int ntile = (H * W + 127) / 128;
   int nsplit = 1;
   while (nsplit * 2 <= ntile && nh * B * nsplit * 2 <= 2 * num_sms) nsplit *= 2;
+  while ((ntile + nsplit - 1) / nsplit > 8) ++nsplit;
   a.tiles_per_cta = (ntile + nsplit - 1) / nsplit;
   nsplit = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
   rcda_bwd_v_tc_kernel<<<dim3(nh, B, nsplit), 320, smem, reinterpret_cast<cudaStream_t>(s)>>>(tm, a);

@@ -186,6 +186,7 @@ class Engine:
         import os
         if os.environ.get("CDETR_NO_SIDE"):      # debugging / A-B measurements
             self.side_stream = None
+        self.rcda_legacy = bool(int(os.environ.get("CDETR_RCDA_LEGACY", "0")))   # A/B + tests of the CUDA-core RCDA
         self.aux_streams = [torch.cuda.Stream(device=device, priority=-1) for _ in range(2)] if device.type == "cuda" else []
 
     def fork_join(self, fns):
@@ -494,7 +495,8 @@ class Engine:
         kr = self.buf(q + ".kr", (B * W, E)); kc = self.buf(q + ".kc", (B * H, E))
         v = self.buf(q + ".v", (N, E))
         lin = self.lins[lin_in]
-        use_tc = H <= 32 and W <= 32      # tcgen05 kernel; larger feature maps use the CUDA-core kernel
+        # tcgen05 kernels up to 64 x 64 (V resident <= 32 x 32, streamed above); beyond that the CUDA-core kernels
+        use_tc = H <= 64 and W <= 64 and not self.rcda_legacy
         v_s = self.sbuf(q + ".v_s", N, E) if use_tc else None
 
         def small():

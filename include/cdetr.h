@@ -175,15 +175,15 @@ int cdetr_rcda_fwd(int B, int L, int H, int W, int E, int nh, const float* qr, c
                    const float* kc, const float* v, const uint8_t* mask_row, const uint8_t* mask_col, float* ar,
                    float* ac, cdetr_split_t o, cdetr_stream_t s);
 /* Same contract as cdetr_rcda_fwd with the contraction on tcgen05 tensor cores (V given as a split tensor
- * [B*H*W, E]); requires H, W <= 32. */
+ * [B*H*W, E]); requires H, W <= 64 (V resident in shared memory up to 32 x 32, streamed through a TMA ring above). */
 int cdetr_rcda_fwd_tc(int B, int L, int H, int W, int E, int nh, const float* qr, const float* qc, const float* kr,
                       const float* kc, cdetr_split_t v, const uint8_t* mask_row, const uint8_t* mask_col, float* ar,
                       float* ac, cdetr_split_t o, cdetr_stream_t s);
-/* Query-side backward on tensor cores (dS maps + dq); pair it with cdetr_rcda_bwd_kv for dK/dV.  H, W <= 32. */
+/* Query-side backward on tensor cores (dS maps + dq); pair it with cdetr_rcda_bwd_k + cdetr_rcda_bwd_v_tc.  H, W <= 64. */
 int cdetr_rcda_bwd_q_tc(int B, int L, int H, int W, int E, int nh, const float* kr, const float* kc, cdetr_split_t v,
                         const float* ar, const float* ac, const float* d_o, float* dsr, float* dsc,
                         cdetr_split_t dqr, cdetr_split_t dqc, cdetr_stream_t s);
-/* Value-side backward on tensor cores (d_o as a split tensor [B*L, E]); H, W <= 32. */
+/* Value-side backward on tensor cores (d_o as a split tensor [B*L, E]); H, W <= 64. */
 int cdetr_rcda_bwd_v_tc(int B, int L, int H, int W, int E, int nh, const float* ar, const float* ac,
                         cdetr_split_t d_o, cdetr_split_t dv, cdetr_stream_t s);
 /* Key-side backward only: dK_r, dK_c (split) from the dS maps. */

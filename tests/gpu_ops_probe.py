@@ -198,7 +198,8 @@ def rcda_ref(qr, qc, kr, kc, v, nh):
     tt = torch.einsum("bnlh,bhwnd->bnlwd", a_c, v.view(Bz, Hh, Ww, nh, d))
     return torch.einsum("bnlw,bnlwd->blnd", a_r, tt).reshape(Bz, Lq, E_), a_r, a_c
 
-for (Bz, Lq, Hh, Ww) in [(2, 300, 32, 32), (1, 70, 9, 13), (1, 1024, 32, 32), (1, 130, 50, 50)]:
+for (Bz, Lq, Hh, Ww) in [(2, 300, 32, 32), (1, 70, 9, 13), (1, 1024, 32, 32), (1, 130, 50, 50), (2, 500, 50, 50),
+                         (1, 2500, 50, 50), (1, 300, 38, 64), (1, 257, 64, 33), (1, 90, 20, 40)]:
     nh = 8
     qr, qc = [(torch.randn(Bz, Lq, E, device=dev) * 1.5).requires_grad_() for _ in range(2)]
     kr = (torch.randn(Bz, Ww, E, device=dev)).requires_grad_(); kc = torch.randn(Bz, Hh, E, device=dev).requires_grad_()
@@ -209,7 +210,7 @@ for (Bz, Lq, Hh, Ww) in [(2, 300, 32, 32), (1, 70, 9, 13), (1, 1024, 32, 32), (1
     tag = f"B{Bz} L{Lq} {Hh}x{Ww}"
     report(f"rcda_fwd {tag}", L.from_split(o).view(Bz, Lq, E), ref.detach(), 2e-5)
     report(f"rcda_fwd A_r {tag}", ar.permute(0, 1, 3, 2), a_r.detach(), 1e-5)
-    if Hh <= 32 and Ww <= 32:
+    if Hh <= 64 and Ww <= 64:
         ar2 = torch.empty_like(ar); ac2 = torch.empty_like(ac); o2 = zs(Bz * Lq, E)
         L.call("cdetr_rcda_fwd_tc", Bz, Lq, Hh, Ww, E, nh, qr, qc, kr, kc, S(v.detach()), None, None, ar2, ac2, o2)
         report(f"rcda_fwd_tc {tag}", L.from_split(o2).view(Bz, Lq, E), ref.detach(), 3e-5)
@@ -221,7 +222,7 @@ for (Bz, Lq, Hh, Ww) in [(2, 300, 32, 32), (1, 70, 9, 13), (1, 1024, 32, 32), (1
     dsr = torch.empty_like(ar); dsc = torch.empty_like(ac)
     dqr, dqc, dkr, dkc, dv = zs(Bz * Lq, E), zs(Bz * Lq, E), zs(Bz * Ww, E), zs(Bz * Hh, E), zs(Bz * Hh * Ww, E)
     L.call("cdetr_rcda_bwd", Bz, Lq, Hh, Ww, E, nh, qr, qc, kr, kc, v, ar, ac, dO, dsr, dsc, dqr, dqc, dkr, dkc, dv)
-    if Hh <= 32 and Ww <= 32:
+    if Hh <= 64 and Ww <= 64:
         dsr2 = torch.empty_like(ar); dsc2 = torch.empty_like(ac)
         dqr2, dqc2, dkr2, dkc2, dv2 = zs(Bz * Lq, E), zs(Bz * Lq, E), zs(Bz * Ww, E), zs(Bz * Hh, E), zs(Bz * Hh * Ww, E)
         L.call("cdetr_rcda_bwd_q_tc", Bz, Lq, Hh, Ww, E, nh, kr, kc, S(v.detach()), ar, ac, dO, dsr2, dsc2, dqr2, dqc2)
@@ -235,6 +236,7 @@ for (Bz, Lq, Hh, Ww) in [(2, 300, 32, 32), (1, 70, 9, 13), (1, 1024, 32, 32), (1
         report(f"rcda_bwd_tc dqr {tag}", L.from_split(dqr2).view_as(qr), qr.grad, 5e-5)
         report(f"rcda_bwd_tc dqc {tag}", L.from_split(dqc2).view_as(qc), qc.grad, 5e-5)
         report(f"rcda_bwd_tc dsr {tag}", dsr2, dsr, 5e-5)
+        report(f"rcda_bwd_tc dsc {tag}", dsc2, dsc, 5e-5)
         report(f"rcda_bwd_tc dkr {tag}", L.from_split(dkr2).view_as(kr), kr.grad, 5e-5)
         report(f"rcda_bwd_tc dkc {tag}", L.from_split(dkc2).view_as(kc), kc.grad, 5e-5)
         report(f"rcda_bwd_tc dv {tag}", L.from_split(dv2).view_as(v), v.grad, 5e-5)
@@ -243,19 +245,20 @@ for (Bz, Lq, Hh, Ww) in [(2, 300, 32, 32), (1, 70, 9, 13), (1, 1024, 32, 32), (1
     report(f"rcda_bwd dkr {tag}", L.from_split(dkr).view_as(kr), kr.grad, 5e-5)
     report(f"rcda_bwd dkc {tag}", L.from_split(dkc).view_as(kc), kc.grad, 5e-5)
     report(f"rcda_bwd dv {tag}", L.from_split(dv).view_as(v), v.grad, 5e-5)
-# masked RCDA
-Bz, Lq, Hh, Ww, nh = 1, 40, 6, 7, 8
-qr, qc = [torch.randn(Bz, Lq, E, device=dev) for _ in range(2)]
-kr, kc, v = torch.randn(Bz, Ww, E, device=dev), torch.randn(Bz, Hh, E, device=dev), torch.randn(Bz, Hh, Ww, E, device=dev)
-mr = torch.zeros(Bz, Ww, dtype=torch.uint8, device=dev); mr[:, 5:] = 1
-mc = torch.zeros(Bz, Hh, dtype=torch.uint8, device=dev); mc[:, 4:] = 1
-ar = torch.empty(Bz, nh, Ww, Lq, device=dev); ac = torch.empty(Bz, nh, Hh, Lq, device=dev); o = zs(Bz * Lq, E)
-L.call("cdetr_rcda_fwd", Bz, Lq, Hh, Ww, E, nh, qr, qc, kr, kc, v, mr, mc, ar, ac, o)
-ref, _, _ = rcda_ref(qr, qc, kr[:, :5], kc[:, :4], v[:, :4, :5], nh)
-report("rcda_fwd masked", L.from_split(o).view(Bz, Lq, E), ref, 2e-5)
-o2 = zs(Bz * Lq, E)
-L.call("cdetr_rcda_fwd_tc", Bz, Lq, Hh, Ww, E, nh, qr, qc, kr, kc, S(v), mr, mc, ar, ac, o2)
-report("rcda_fwd_tc masked", L.from_split(o2).view(Bz, Lq, E), ref, 3e-5)
+# masked RCDA (resident-V kernel: 6x7; streaming kernel: 40x50)
+for (Hh, Ww, hv, wv) in [(6, 7, 4, 5), (40, 50, 33, 41)]:
+    Bz, Lq, nh = 1, 140, 8
+    qr, qc = [torch.randn(Bz, Lq, E, device=dev) for _ in range(2)]
+    kr, kc, v = torch.randn(Bz, Ww, E, device=dev), torch.randn(Bz, Hh, E, device=dev), torch.randn(Bz, Hh, Ww, E, device=dev)
+    mr = torch.zeros(Bz, Ww, dtype=torch.uint8, device=dev); mr[:, wv:] = 1
+    mc = torch.zeros(Bz, Hh, dtype=torch.uint8, device=dev); mc[:, hv:] = 1
+    ar = torch.empty(Bz, nh, Ww, Lq, device=dev); ac = torch.empty(Bz, nh, Hh, Lq, device=dev); o = zs(Bz * Lq, E)
+    L.call("cdetr_rcda_fwd", Bz, Lq, Hh, Ww, E, nh, qr, qc, kr, kc, v, mr, mc, ar, ac, o)
+    ref, _, _ = rcda_ref(qr, qc, kr[:, :wv], kc[:, :hv], v[:, :hv, :wv], nh)
+    report(f"rcda_fwd masked {Hh}x{Ww}", L.from_split(o).view(Bz, Lq, E), ref, 2e-5)
+    o2 = zs(Bz * Lq, E)
+    L.call("cdetr_rcda_fwd_tc", Bz, Lq, Hh, Ww, E, nh, qr, qc, kr, kc, S(v), mr, mc, ar, ac, o2)
+    report(f"rcda_fwd_tc masked {Hh}x{Ww}", L.from_split(o2).view(Bz, Lq, E), ref, 3e-5)
 
 for (Bz, Lq) in [(2, 300), (1, 77), (1, 500)]:
     nh = 8; d = 32

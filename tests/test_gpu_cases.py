@@ -134,3 +134,15 @@ def test_bad_exemplar_rect_poisons_the_loss():
     out, _ = model(inp["image"].cuda(), None, inp["rects"].cuda())      # flag re-armed: the next step is clean
     ld = crit(out, targets)
     assert all(torch.isfinite(v).item() for v in ld.values())
+
+
+def test_cuda_core_rcda_fallback_still_matches_c4_golden(golden_dir, monkeypatch):
+    """CDETR_RCDA_LEGACY=1: the CUDA-core RCDA kernels (rcda.cu; maps beyond 64 x 64 would use them) on C4's shapes."""
+    from oracle.cases import compare
+    monkeypatch.setenv("CDETR_RCDA_LEGACY", "1")
+    name = "c4_stage2_S800_B2_Q500"
+    gold = torch.load(os.path.join(golden_dir, name + ".pt"))
+    got = cuda_case(name, gold["config"]["seed"])
+    fails, worst = compare(got, gold, tol_out=1e-3, tol_loss=1e-3, tol_grad_norm=2e-2, tol_grad_small=2e-2)
+    _report("cuda_vs_reference_golden[rcda_legacy]", name, worst, fails)
+    assert not fails, (fails[:10], worst)
