@@ -66,6 +66,7 @@ class GemmT(C.Structure):
         ("out_split", SplitT),
         ("conv_taps", C.c_int32), ("conv_H", C.c_int32), ("conv_W", C.c_int32), ("conv_C", C.c_int32),
         ("conv_dil", C.c_int32), ("conv_sign", C.c_int32),
+        ("pass_mask", C.c_int32),
     ]
 
 
@@ -82,7 +83,8 @@ CALL_TRACE = None      # when a list: (name, leading int args, start event, end 
 
 
 def gemm(a, b, M, N, K, mode=0, out_f32=None, out_split=None, bias=None, row_scale=None,
-         add_split=None, add_f32=None, mask=None, relu=False, accumulate=False, block_n=0, split_k=1, conv=None):
+         add_split=None, add_f32=None, mask=None, relu=False, accumulate=False, block_n=0, split_k=1, conv=None,
+         pass_mask=0):
     """cdetr_gemm: see include/cdetr.h. a, b, add_split, mask, out_split are split tensors [2, rows, ld].
     conv = (H, W, C, dil, sign) turns the conv operand (a in mode 0, b in mode 1) into an implicit 3x3 im2col."""
     g = GemmT()
@@ -92,6 +94,7 @@ def gemm(a, b, M, N, K, mode=0, out_f32=None, out_split=None, bias=None, row_sca
     g.mode, g.M, g.N, g.K = mode, M, N, K
     g.a, g.b = split_view(a), split_view(b)
     g.block_n, g.split_k = block_n, split_k
+    g.pass_mask = pass_mask
     g.row_scale, g.bias = _ptr(row_scale), _ptr(bias)
     g.add_split = split_view(add_split)
     g.add_f32 = _ptr(add_f32)

@@ -52,6 +52,7 @@ struct KernelArgs {
   int tiles_m, tiles_n, total_tiles;  // tile index = (split * tiles_m + mt) * tiles_n + nt
   int tile_m;                         // output rows per tile: 128, or 256 for a CTA pair (cta_group::2)
   uint32_t idesc;
+  uint32_t pass_mask;  // which of the three split-bf16 products are issued: 1 hi*hi, 2 hi_a*lo_b, 4 lo_a*hi_b (7 = all)
   uint32_t tmem_cols;  // columns of ONE accumulator buffer (two are allocated)
   // implicit 3x3 convolution (conv != 0): the conv operand (A in mode 0, B in mode 1) is an NHWC activation read
   // through a 5-D map {C, W, H, B, plane} with per-tap shifted windows; TMA zero-fills the out-of-image part
@@ -313,16 +314,17 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               b_hi = make_smem_desc_sw128(b_base + k * 2048, 16384, 1024);
               b_lo = make_smem_desc_sw128(b_base + 8192 + k * 2048, 16384, 1024);
             }
+            // small cross terms first, hi*hi last; pass_mask drops cross terms (precision policy)
             if (PAIR) {
-              umma_bf16_ss_pair(tmem_d, a_hi, b_lo, args.idesc, acc);
+              if (args.pass_mask & 2u) { umma_bf16_ss_pair(tmem_d, a_hi, b_lo, args.idesc, acc); acc = 1; }
+              if (args.pass_mask & 4u) { umma_bf16_ss_pair(tmem_d, a_lo, b_hi, args.idesc, acc); acc = 1; }
+              umma_bf16_ss_pair(tmem_d, a_hi, b_hi, args.idesc, acc);
               acc = 1;
-              umma_bf16_ss_pair(tmem_d, a_lo, b_hi, args.idesc, 1);
-              umma_bf16_ss_pair(tmem_d, a_hi, b_hi, args.idesc, 1);
             } else {
-              umma_bf16_ss(tmem_d, a_hi, b_lo, args.idesc, acc);
+              if (args.pass_mask & 2u) { umma_bf16_ss(tmem_d, a_hi, b_lo, args.idesc, acc); acc = 1; }
+              if (args.pass_mask & 4u) { umma_bf16_ss(tmem_d, a_lo, b_hi, args.idesc, acc); acc = 1; }
+              umma_bf16_ss(tmem_d, a_hi, b_hi, args.idesc, acc);
               acc = 1;
-              umma_bf16_ss(tmem_d, a_lo, b_hi, args.idesc, 1);
-              umma_bf16_ss(tmem_d, a_hi, b_hi, args.idesc, 1);
             }
           }
           // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
@@ -986,6 +988,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   ka.cH = conv ? g->conv_H : 1; ka.cW = conv ? g->conv_W : 1; ka.cC = conv ? g->conv_C : 1;
   ka.cdil = g->conv_dil; ka.csign = g->conv_sign;
   ka.idesc = make_idesc_bf16_f32(pair ? 2 * BM : BM, bn, nt ? 1 : 0, nt ? 1 : 0);
+  ka.pass_mask = (g->pass_mask > 0 && g->pass_mask <= 7) ? ((uint32_t)g->pass_mask | 1u) : 7u;
   ka.tile_m = pair ? 2 * BM : BM;
   uint32_t cols = 32;
   while ((int)cols < bn) cols <<= 1;

@@ -79,6 +79,10 @@ typedef struct {
    * H*W a multiple of 128 (a 128-row tile = whole image rows); callers lower other shapes through cdetr_im2col3x3. */
   int32_t conv_taps;
   int32_t conv_H, conv_W, conv_C, conv_dil, conv_sign;
+  /* Precision policy: which of the three split-bf16 partial products are issued (bit 0: hi_a*hi_b, always on; bit 1:
+   * hi_a*lo_b; bit 2: lo_a*hi_b).  0 or 7 = all three (fp32-equivalent, 2^-16 relative per product); 5 = operand b
+   * rounded to bf16; 3 = operand a rounded to bf16; 1 = plain bf16 product. */
+  int32_t pass_mask;
 } cdetr_gemm_t;
 
 int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream);

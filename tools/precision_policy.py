@@ -1,0 +1,142 @@
+#!/usr/bin/env python
+"""Precision-policy measurement (hard part 1).
+
+For every policy (which of the three split-bf16 partial products each GEMM group / attention kernel issues) run, in a
+fresh process (the policy is read once per process):
+  * C3 at its own size (B=16, S=512, Q=300, T=50, seed 0) against the fixture of the UNMODIFIED reference:
+    worst relative error of outputs / losses, matching-index flips, gradient errors;
+  * C3's shapes at B=4 for seeds 1..3 against the CPU oracle (computed once, cached): same figures;
+  * the fwd+loss+bwd step time of C3 (CUDA-graph replay, 10 steps).
+Prints one table; run on the GPU box:  python tools/precision_policy.py > gpurun_out/precision_policy.txt
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+NAME = "c3_stage2_S512_B16_Q300"
+SEEDS = (1, 2, 3)
+CACHE = "/tmp/cdetr_policy_oracle.pt"
+
+POLICIES = [
+    # tag, CDETR_GEMM_POLICY, CDETR_ATTN_PASSES, CDETR_ATTN_PASSES_BWD
+    ("3-pass everywhere (round 1)", "", 7, 7),
+    ("wgrad bf16 (1 pass)", "*.wgrad=1", 7, 7),
+    ("wgrad: act exact, dy bf16", "*.wgrad=3", 7, 7),
+    ("wgrad: dy exact, act bf16", "*.wgrad=5", 7, 7),
+    ("dgrad bf16", "*.dgrad=1", 7, 7),
+    ("dgrad: dy exact, W bf16", "*.dgrad=5", 7, 7),
+    ("dgrad + wgrad bf16", "*.dgrad=1,*.wgrad=1", 7, 7),
+    ("dgrad W-bf16 + wgrad bf16", "*.dgrad=5,*.wgrad=1", 7, 7),
+    ("attention bwd bf16", "", 7, 1),
+    ("all backward bf16 (GEMM + attn)", "*.dgrad=1,*.wgrad=1", 7, 1),
+    ("backbone fwd: W bf16", "backbone.fwd=5", 7, 7),
+    ("backbone fwd: act bf16", "backbone.fwd=3", 7, 7),
+    ("backbone fwd bf16", "backbone.fwd=1", 7, 7),
+    ("proj fwd: W bf16", "proj.fwd=5", 7, 7),
+    ("attn proj fwd: W bf16", "attn.fwd=5", 7, 7),
+    ("ffn fwd: W bf16", "ffn.fwd=5", 7, 7),
+    ("heads+pos fwd: W bf16", "heads.fwd=5,pos.fwd=5", 7, 7),
+    ("transformer fwd: W bf16", "proj.fwd=5,attn.fwd=5,ffn.fwd=5", 7, 7),
+    ("transformer fwd bf16", "proj.fwd=1,attn.fwd=1,ffn.fwd=1", 7, 7),
+    ("attention fwd: V/K bf16", "", 5, 7),
+    ("attention fwd: A/q bf16", "", 3, 7),
+    ("attention fwd bf16", "", 1, 7),
+    ("all fwd: W bf16", "*.fwd=5", 5, 7),
+    ("everything bf16", "*=1", 1, 1),
+]
+
+
+def child():
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_gpu_cases import cuda_case
+    from oracle.cases import compare
+    from oracle.make_golden import CASES
+    res = {}
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", NAME + ".pt"))
+    got = cuda_case(NAME, 0)
+    fails, worst = compare(got, gold)
+    flips = sum(1 for (a, b), (c, d) in zip(got["indices"], gold["indices"]) if not (torch.equal(a, c) and torch.equal(b, d)))
+    res["golden"] = dict(worst=worst, flips=flips, images=len(gold["indices"]))
+    cache = torch.load(CACHE)
+    saved = dict(CASES[NAME])
+    CASES[NAME]["B"] = 4
+    w2, fl2 = {}, 0
+    for s in SEEDS:
+        got = cuda_case(NAME, s)
+        g = cache[s]
+        _, w = compare(got, g)
+        for k, v in w.items():
+            w2[k] = max(w2.get(k, 0.0), v)
+        fl2 += sum(1 for (a, b), (c, d) in zip(got["indices"], g["indices"])
+                   if not (torch.equal(torch.as_tensor(a), torch.as_tensor(c)) and torch.equal(torch.as_tensor(b), torch.as_tensor(d))))
+    CASES[NAME].update(saved)
+    res["seeds"] = dict(worst=w2, flips=fl2, images=4 * len(SEEDS))
+    # step time
+    from counting_detr_b200 import synthetic as SY
+    from counting_detr_b200.models import build_model
+    from counting_detr_b200.step import CapturedStep
+    model, crit, _ = build_model(SY.default_args(2, num_query_position=300, device="cuda"))
+    model.load_state_dict(SY.make_state_dict(SY.SynthCfg(stage=2, num_query_position=300), 0), strict=True)
+    model.cuda().train()
+    inp = SY.make_inputs(16, 512, T=50, stage=2)
+    img, rects = inp["image"].cuda(), inp["rects"].cuda()
+    tg = [{k: v.cuda() for k, v in t.items()} for t in inp["targets"]]
+    st = CapturedStep(model, crit)
+    for _ in range(3):
+        st(img, tg, rects=rects)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        st(img, tg, rects=rects)
+    e1.record()
+    torch.cuda.synchronize()
+    res["ms"] = e0.elapsed_time(e1) / 10
+    print("RESULT " + json.dumps(res), flush=True)
+
+
+def main():
+    import torch
+    if not os.path.exists(CACHE):
+        from oracle import cases as OCS
+        from oracle.make_golden import CASES
+        saved = dict(CASES[NAME])
+        CASES[NAME]["B"] = 4
+        torch.save({s: OCS.oracle_case(NAME, s) for s in SEEDS}, CACHE)
+        CASES[NAME].update(saved)
+    only = sys.argv[1:]
+    hdr = (f"{'policy':34s} {'GEMM policy':34s} {'attn f/b':8s} {'ms/step':>8s} | {'out err':>9s} {'loss err':>9s} {'flips':>6s} "
+           f"{'g.norm':>8s} {'g.small':>8s} | {'out err':>9s} {'loss err':>9s} {'flips':>6s} {'g.norm':>8s} {'g.small':>8s}")
+    print("C3 (B=16, 512x512, Q=300, T=50).  Left block: seed 0 at B=16 vs the reference's own fixture; right block: seeds "
+          "1-3 at B=4 vs the CPU oracle.\nerr = worst relative error (outputs: max-abs / max; losses: relative); flips = "
+          "images whose matching indices differ; g.* = worst per-tensor gradient error (norm / whole small tensors).")
+    print(hdr)
+    for tag, pol, af, ab in POLICIES:
+        if only and not any(o in tag for o in only):
+            continue
+        env = dict(os.environ, CDETR_GEMM_POLICY=pol, CDETR_ATTN_PASSES=str(af), CDETR_ATTN_PASSES_BWD=str(ab))
+        p = subprocess.run([sys.executable, __file__, "--child"], env=env, capture_output=True, text=True, timeout=900)
+        line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+        if not line:
+            print(f"{tag:34s} FAILED: {(p.stdout + p.stderr)[-300:]}")
+            continue
+        r = json.loads(line[0][7:])
+
+        def blk(b):
+            w = b["worst"]
+            out = max(v for k, v in w.items() if k.startswith("out."))
+            loss = max(v for k, v in w.items() if k.startswith("loss."))
+            return (f"{out:9.2e} {loss:9.2e} {b['flips']:3d}/{b['images']:<2d} {w.get('grad.norm', 0):8.1e} "
+                    f"{w.get('grad.small', 0):8.1e}")
+        print(f"{tag:34s} {pol or '-':34s} {af}/{ab:<6d} {r['ms']:8.2f} | {blk(r['golden'])} | {blk(r['seeds'])}", flush=True)
+
+
+if __name__ == "__main__":
+    if "--child" in sys.argv:
+        child()
+    else:
+        main()
