@@ -175,6 +175,9 @@ _SIGS = {
     "cdetr_set_loss_bwd": "pppppplppp",
     "cdetr_bbox_loss_fwd": "ppplppp",
     "cdetr_bbox_loss_bwd": "ppplp",
+    "cdetr_postprocess_topk": "pppiiiippp",
+    "cdetr_infer_select": "pipppiifpppppp",
+    "cdetr_pseudo_label_format": "ppplpp",
     "cdetr_mt_grad_norm": "ppiifpp",
     "cdetr_mt_clip_scale": "ppiip",
     "cdetr_mt_adamw": "ppiipfffpp",

@@ -85,8 +85,6 @@ struct CdetrTuning {
   int pdl;            // CDETR_PDL=1: programmatic dependent launch of the GEMM
   int pdl_light;      // CDETR_PDL_LIGHT=1: ... of the light kernels
   int mha_legacy;     // CDETR_MHA_LEGACY=1: CUDA-core decoder self-attention
-  int attn_passes;    // CDETR_ATTN_PASSES: pass mask of the RCDA forward tensor-core products (7 = all three, see umma_split3)
-  int attn_passes_bwd;  // CDETR_ATTN_PASSES_BWD: ... of the RCDA backward kernels
 };
 static inline const CdetrTuning& cdetr_tuning() {
   static const CdetrTuning t = [] {
@@ -100,8 +98,6 @@ static inline const CdetrTuning& cdetr_tuning() {
     x.pdl = geti("CDETR_PDL", 0);
     x.pdl_light = geti("CDETR_PDL_LIGHT", 0);
     x.mha_legacy = geti("CDETR_MHA_LEGACY", 0);
-    x.attn_passes = (geti("CDETR_ATTN_PASSES", 7) & 7) | 1;
-    x.attn_passes_bwd = (geti("CDETR_ATTN_PASSES_BWD", 7) & 7) | 1;
     return x;
   }();
   return t;
@@ -331,14 +327,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
-}
-// One split-bf16 product D (+)= (a_hi + a_lo) * (b_hi + b_lo) without the lo*lo term: the two small cross products first,
-// hi*hi last.  pass_mask drops cross terms (bit 1: a_hi*b_lo, bit 2: a_lo*b_hi) for the precision-policy measurements.
-__device__ __forceinline__ void umma_split3(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
-                                            uint32_t idesc, uint32_t accumulate, uint32_t pass_mask) {
-  if (pass_mask & 2u) { umma_bf16_ss(d, a_hi, b_lo, idesc, accumulate); accumulate = 1; }
-  if (pass_mask & 4u) { umma_bf16_ss(d, a_lo, b_hi, idesc, accumulate); accumulate = 1; }
-  umma_bf16_ss(d, a_hi, b_hi, idesc, accumulate);
 }
 // TMEM -> registers: 32 lanes (this warp's quarter) x 16 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {

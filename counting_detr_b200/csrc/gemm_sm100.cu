@@ -103,7 +103,9 @@ __device__ __forceinline__ TileCoord decode_tile(const KernelArgs& a, int rank, 
   return t;
 }
 
-template <bool NT, bool PAIR>
+// MASKED = false: the product path, three back-to-back MMAs per k-step in straight-line code (no data-dependent branch
+// in the single-thread issue loop); MASKED = true: precision-policy variants that drop cross terms (args.pass_mask).
+template <bool NT, bool PAIR, bool MASKED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOutF, const __grid_constant__ CUtensorMap tmOutS,
@@ -314,16 +316,29 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               b_hi = make_smem_desc_sw128(b_base + k * 2048, 16384, 1024);
               b_lo = make_smem_desc_sw128(b_base + 8192 + k * 2048, 16384, 1024);
             }
-            // small cross terms first, hi*hi last; pass_mask drops cross terms (precision policy)
-            if (PAIR) {
-              if (args.pass_mask & 2u) { umma_bf16_ss_pair(tmem_d, a_hi, b_lo, args.idesc, acc); acc = 1; }
-              if (args.pass_mask & 4u) { umma_bf16_ss_pair(tmem_d, a_lo, b_hi, args.idesc, acc); acc = 1; }
-              umma_bf16_ss_pair(tmem_d, a_hi, b_hi, args.idesc, acc);
-              acc = 1;
-            } else {
-              if (args.pass_mask & 2u) { umma_bf16_ss(tmem_d, a_hi, b_lo, args.idesc, acc); acc = 1; }
-              if (args.pass_mask & 4u) { umma_bf16_ss(tmem_d, a_lo, b_hi, args.idesc, acc); acc = 1; }
-              umma_bf16_ss(tmem_d, a_hi, b_hi, args.idesc, acc);
+            // small cross terms first, hi*hi last
+            if constexpr (!MASKED) {
+              if (PAIR) {
+                umma_bf16_ss_pair(tmem_d, a_hi, b_lo, args.idesc, acc);
+                acc = 1;
+                umma_bf16_ss_pair(tmem_d, a_lo, b_hi, args.idesc, 1);
+                umma_bf16_ss_pair(tmem_d, a_hi, b_hi, args.idesc, 1);
+              } else {
+                umma_bf16_ss(tmem_d, a_hi, b_lo, args.idesc, acc);
+                acc = 1;
+                umma_bf16_ss(tmem_d, a_lo, b_hi, args.idesc, 1);
+                umma_bf16_ss(tmem_d, a_hi, b_hi, args.idesc, 1);
+              }
+            } else {   // pass_mask drops cross terms (precision-policy measurements)
+              if (PAIR) {
+                if (args.pass_mask & 2u) { umma_bf16_ss_pair(tmem_d, a_hi, b_lo, args.idesc, acc); acc = 1; }
+                if (args.pass_mask & 4u) { umma_bf16_ss_pair(tmem_d, a_lo, b_hi, args.idesc, acc); acc = 1; }
+                umma_bf16_ss_pair(tmem_d, a_hi, b_hi, args.idesc, acc);
+              } else {
+                if (args.pass_mask & 2u) { umma_bf16_ss(tmem_d, a_hi, b_lo, args.idesc, acc); acc = 1; }
+                if (args.pass_mask & 4u) { umma_bf16_ss(tmem_d, a_lo, b_hi, args.idesc, acc); acc = 1; }
+                umma_bf16_ss(tmem_d, a_hi, b_hi, args.idesc, acc);
+              }
               acc = 1;
             }
           }
@@ -1138,9 +1153,13 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
     nctas = cdiv(ka.total_tiles, ka.tiles_per_cta);
   }
   dim3 grid(nctas);
-  auto kern = nt ? gemm_split_kernel<true, false> : (pair ? gemm_split_kernel<false, true> : gemm_split_kernel<false, false>);
-  static DevAttrCache configured[3] = {};
-  CDETR_CHECK_CUDA(cdetr_ensure_smem(kern, 227 * 1024, &configured[nt ? 1 : (pair ? 2 : 0)]));
+  const bool masked = ka.pass_mask != 7u;
+  auto kern = masked ? (nt ? gemm_split_kernel<true, false, true>
+                           : (pair ? gemm_split_kernel<false, true, true> : gemm_split_kernel<false, false, true>))
+                     : (nt ? gemm_split_kernel<true, false, false>
+                           : (pair ? gemm_split_kernel<false, true, false> : gemm_split_kernel<false, false, false>));
+  static DevAttrCache configured[6] = {};
+  CDETR_CHECK_CUDA(cdetr_ensure_smem(kern, 227 * 1024, &configured[(masked ? 3 : 0) + (nt ? 1 : (pair ? 2 : 0))]));
   const int use_pdl = tune.pdl;   // opt-in: measured +0.6 ms on the C3 step (early CTAs of the successor crowd the side streams)
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

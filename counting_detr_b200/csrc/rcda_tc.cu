@@ -45,7 +45,6 @@ struct TcArgs {
   int64_t ld_o;
   uint32_t idesc;
   uint32_t idesc_s;   // logits MMA: [128 x 32] x [32 x 32]
-  uint32_t pm;        // pass mask (umma_split3)
 };
 
 // softmax over the first n entries of a logit row (entries >= n or masked get probability 0)
@@ -147,7 +146,9 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
             const uint64_t a_lo = make_smem_desc(a_base + A_PLANE_BYTES + ks * 32, 16, 512, 4);
             const uint64_t b_hi = make_smem_desc(k_base + ks * 32, 16, 512, 4);
             const uint64_t b_lo = make_smem_desc(k_base + K_PLANE_BYTES + ks * 32, 16, 512, 4);
-            umma_split3(d, a_hi, a_lo, b_hi, b_lo, a.idesc_s, ks > 0 ? 1u : 0u, a.pm);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc_s, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc_s, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc_s, 1);
           }
           umma_commit(&s_full[g]);
         }
@@ -171,7 +172,9 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
             const uint32_t vb = v_base + (uint32_t)p * 8u * (WP * 64) + ks * 1024;
             const uint64_t b_hi = make_smem_desc(vb, WP * 64, 512, 4);
             const uint64_t b_lo = make_smem_desc(vb + V_PLANE_BYTES, WP * 64, 512, 4);
-            umma_split3(d, a_hi, a_lo, b_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u, a.pm);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc, 1);
           }
           umma_commit(&t_full[g]);
         }
@@ -360,7 +363,6 @@ struct TcBwdArgs {
   int64_t ld_g;
   uint32_t idesc;
   uint32_t idesc_q;   // dq MMA: [128 x 32 keys] x [32 keys x 32 d], B MN-major
-  uint32_t pm;
 };
 
 __global__ void __launch_bounds__(320, 1)
@@ -431,7 +433,9 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
             const uint32_t vb = v_base + (uint32_t)p * 256u * 64u + ks * 32;
             const uint64_t b_hi = make_smem_desc(vb, 16, 512, 4);
             const uint64_t b_lo = make_smem_desc(vb + V_PLANE_BYTES, 16, 512, 4);
-            umma_split3(d, a_hi, a_lo, b_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u, a.pm);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc, 1);
           }
           umma_commit(&t_full[g]);
         }
@@ -451,7 +455,9 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
             const uint64_t a_lo = make_smem_desc(a_base + A_PLANE_BYTES + ks * 32, 16, 512, 4);
             const uint64_t b_hi = make_smem_desc(k_base + ks * 1024, 2048, 512, 4);
             const uint64_t b_lo = make_smem_desc(k_base + 2048 + ks * 1024, 2048, 512, 4);
-            umma_split3(d, a_hi, a_lo, b_hi, b_lo, a.idesc_q, ks > 0 ? 1u : 0u, a.pm);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc_q, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc_q, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc_q, 1);
           }
           umma_commit(&s_full[g]);
         }
@@ -664,7 +670,6 @@ struct TcBwdVArgs {
   uint32_t idesc;
   int tiles_per_cta;   // key-position tiles (of 128) per CTA: blockIdx.z selects the slice of positions (<= 8)
   int kp;              // rows of the staged attention maps: max(H, W) rounded up to 8 (<= 64)
-  uint32_t pm;
 };
 
 __global__ void __launch_bounds__(320, 2)
@@ -739,7 +744,9 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
             const uint64_t a_lo = make_smem_desc(p_base + P_TILE_BYTES + ks * 32, 16, 1024, 2);
             const uint64_t b_hi = make_smem_desc(d_base + ks * 1024, 4096, 512, 4);              // MN-major SW64
             const uint64_t b_lo = make_smem_desc(d_base + DO_PLANE_BYTES + ks * 1024, 4096, 512, 4);
-            umma_split3(d, a_hi, a_lo, b_hi, b_lo, a.idesc, (kb > 0 || ks > 0) ? 1u : 0u, a.pm);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc, 1);
           }
           umma_commit(&p_empty[pb]);
         }
@@ -887,7 +894,6 @@ extern "C" int cdetr_rcda_fwd_tc(int B, int L, int H, int W, int E, int nh, cons
   a.qr = qr; a.qc = qc; a.kr = kr; a.kc = kc; a.mask_row = mask_row; a.mask_col = mask_col; a.ar = ar; a.ac = ac;
   a.o_hi = reinterpret_cast<__nv_bfloat16*>(o.base); a.o_lo = a.o_hi + o.plane; a.ld_o = o.ld;
   a.idesc = make_idesc_bf16_f32(TQ, 256, 0, 1);
-  a.pm = (uint32_t)cdetr_tuning().attn_passes;
   a.idesc_s = make_idesc_bf16_f32(TQ, 32, 0, 0);
   const size_t smem = 2 * V_PLANE_BYTES + 4 * A_PLANE_BYTES + 2 * 32 * HD * sizeof(float) + 128 + 1024;
   static DevAttrCache cfg = {};
@@ -935,7 +941,6 @@ extern "C" int cdetr_rcda_bwd_q_tc(int B, int L, int H, int W, int E, int nh, co
   a.dqc_hi = reinterpret_cast<__nv_bfloat16*>(dqc.base); a.dqc_lo = a.dqc_hi + dqc.plane;
   a.ld_g = dqr.ld;
   a.idesc = make_idesc_bf16_f32(TQ, 256, 0, 0);
-  a.pm = (uint32_t)cdetr_tuning().attn_passes_bwd;
   a.idesc_q = make_idesc_bf16_f32(TQ, 32, 0, 1);
   const size_t smem = 2 * V_PLANE_BYTES + 4 * A_PLANE_BYTES + 4 * 32 * TQ * sizeof(float) + 128 + 1024;
   static DevAttrCache cfg = {};
@@ -968,7 +973,6 @@ extern "C" int cdetr_rcda_bwd_v_tc(int B, int L, int H, int W, int E, int nh, co
   a.B = B; a.L = L; a.H = H; a.W = W; a.E = E; a.nh = nh; a.ar = ar; a.ac = ac;
   a.dv_hi = reinterpret_cast<__nv_bfloat16*>(dv.base); a.dv_lo = a.dv_hi + dv.plane; a.ld_g = dv.ld;
   a.idesc = make_idesc_bf16_f32(128, HD, 0, 1);
-  a.pm = (uint32_t)cdetr_tuning().attn_passes_bwd;
   a.kp = ((H > W ? H : W) + 7) / 8 * 8;
   const size_t smem = 4 * P_TILE_BYTES + 4 * DO_PLANE_BYTES + 2 * (size_t)a.kp * MAP_LD * sizeof(float) + 128 + 1024;
   static DevAttrCache cfg = {};

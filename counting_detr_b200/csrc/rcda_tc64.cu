@@ -36,7 +36,7 @@ struct Fwd64Args {
   float *ar, *ac;              // [B,nh,W,L], [B,nh,H,L]
   __nv_bfloat16 *o_hi, *o_lo;
   int64_t ld_o;
-  uint32_t idesc, idesc_s, pm;
+  uint32_t idesc, idesc_s;
 };
 
 struct Bwd64Args {
@@ -45,7 +45,7 @@ struct Bwd64Args {
   float *dsr, *dsc;            // [B,nh,W,L], [B,nh,H,L]
   __nv_bfloat16 *dqr_hi, *dqr_lo, *dqc_hi, *dqc_lo;
   int64_t ld_g;
-  uint32_t idesc, idesc_q, pm;
+  uint32_t idesc, idesc_q;
 };
 
 // softmax over the first n of 64 logits (entries >= n or masked get probability 0)
@@ -200,7 +200,9 @@ rcda_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmV, const Fwd64Args a)
             const uint64_t a_lo = make_smem_desc(a_base + Q_PLANE + ks * 32, 16, 512, 4);
             const uint64_t b_hi = make_smem_desc(k_base + ks * 32, 16, 512, 4);
             const uint64_t b_lo = make_smem_desc(k_base + K_PLANE + ks * 32, 16, 512, 4);
-            umma_split3(d, a_hi, a_lo, b_hi, b_lo, a.idesc_s, ks > 0 ? 1u : 0u, a.pm);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc_s, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc_s, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc_s, 1);
           }
           umma_commit(&s_full[g]);
         }
@@ -226,7 +228,9 @@ rcda_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmV, const Fwd64Args a)
             const uint32_t vb = v_base + ks * 1024;
             const uint64_t b_hi = make_smem_desc(vb, KP * 64, 512, 4);
             const uint64_t b_lo = make_smem_desc(vb + V_PLANE, KP * 64, 512, 4);
-            umma_split3(d, a_hi, a_lo, b_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u, a.pm);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc, 1);
           }
           umma_commit(&t_full[g * 2 + u]);
         }
@@ -452,7 +456,9 @@ rcda_bwd_q_tc64_kernel(const __grid_constant__ CUtensorMap tmV, const Bwd64Args 
             // V as K-major B: row n = h_local*64 + w at 64-byte pitch (8-row groups 512 B apart), k-step of 16 c = +32 B
             const uint64_t b_hi = make_smem_desc(v_base + ks * 32, 16, 512, 4);
             const uint64_t b_lo = make_smem_desc(v_base + V_PLANE + ks * 32, 16, 512, 4);
-            umma_split3(d, a_hi, a_lo, b_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u, a.pm);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc, 1);
           }
           umma_commit(&t_full[g]);
         }
@@ -473,7 +479,9 @@ rcda_bwd_q_tc64_kernel(const __grid_constant__ CUtensorMap tmV, const Bwd64Args 
             const uint64_t a_lo = make_smem_desc(a_base + AR_PLANE + ks * 32, 16, 1024, 2);
             const uint64_t b_hi = make_smem_desc(k_base + ks * 1024, K_PLANE, 512, 4);
             const uint64_t b_lo = make_smem_desc(k_base + K_PLANE + ks * 1024, K_PLANE, 512, 4);
-            umma_split3(d, a_hi, a_lo, b_hi, b_lo, a.idesc_q, ks > 0 ? 1u : 0u, a.pm);
+            umma_bf16_ss(d, a_hi, b_lo, a.idesc_q, ks > 0 ? 1u : 0u);
+            umma_bf16_ss(d, a_lo, b_hi, a.idesc_q, 1);
+            umma_bf16_ss(d, a_hi, b_hi, a.idesc_q, 1);
           }
           umma_commit(&s_full[g]);
         }
@@ -674,7 +682,6 @@ int rcda_fwd_tc64_launch(int B, int L, int H, int W, int E, int nh, const float*
   a.qr = qr; a.qc = qc; a.kr = kr; a.kc = kc; a.mask_row = mask_row; a.mask_col = mask_col; a.ar = ar; a.ac = ac;
   a.o_hi = reinterpret_cast<__nv_bfloat16*>(o.base); a.o_lo = a.o_hi + o.plane; a.ld_o = o.ld;
   a.idesc = make_idesc_bf16_f32(TQ, HB * HD, 0, 1);
-  a.pm = (uint32_t)cdetr_tuning().attn_passes;
   a.idesc_s = make_idesc_bf16_f32(TQ, KP, 0, 0);
   const int smem = (int)FWD_SMEM + 256 + 1024;
   static DevAttrCache cfg = {};
@@ -697,7 +704,6 @@ int rcda_bwd_q_tc64_launch(int B, int L, int H, int W, int E, int nh, const floa
   a.dqc_hi = reinterpret_cast<__nv_bfloat16*>(dqc.base); a.dqc_lo = a.dqc_hi + dqc.plane;
   a.ld_g = dqr.ld;
   a.idesc = make_idesc_bf16_f32(TQ, HB * KP, 0, 0);
-  a.pm = (uint32_t)cdetr_tuning().attn_passes_bwd;
   a.idesc_q = make_idesc_bf16_f32(TQ, HD, 0, 1);
   const int smem = (int)BWD_SMEM + 256 + 1024;
   static DevAttrCache cfg = {};

@@ -880,10 +880,9 @@ class Engine:
             have_dtgt = True
         # ---- pattern embedding: tgt0[b, p*Qp + j] = pattern[p]
         gpat = self.grad_views[self._pattern_key()]
-        for b in range(B):
-            for p_ in range(P):
-                r0 = b * Q + p_ * Qp
-                L.call("cdetr_colsum", dtgt[r0:r0 + Qp], None, E, Qp, E, gpat[p_])
+        dpat = self.buf("dpattern_tmp", (B * P, E))       # sum over the Qp queries of each (sample, pattern), then over b
+        L.call("cdetr_reduce_axis", dtgt, B * P, Qp, 1, E, 1, 1.0, None, 0, dpat, None)
+        L.call("cdetr_reduce_axis", dpat, 1, B, P, E, 1, 1.0, None, 1, gpat, None)
         # ---- memory gradient: add the mean-over-H/W key paths accumulated over decoder layers
         dpe = self.buf("dpe1", (B * W + B * H + 2 * Q, E), zero=True)
         dpe_row, dpe_col = dpe[: B * W], dpe[B * W: B * W + B * H]

@@ -634,24 +634,22 @@ class BoundingBoxCriterion(nn.Module):
 
 
 class PostProcess(nn.Module):
-    """PostProcess (A2/models/anchor_detr.py:370-402): top-100 over the flattened (query, class) scores.
-    Not on the training hot path (no live caller in the reference); plain tensor ops."""
+    """PostProcess (A2/models/anchor_detr.py:370-402): sigmoid, top-100 over the flattened (query, class) scores,
+    labels, xyxy boxes in pixels -- one kernel (cdetr_postprocess_topk), results stay on the device."""
 
     @torch.no_grad()
     def forward(self, outputs, target_sizes):
         out_logits, out_bbox = outputs["pred_logits"], outputs["pred_boxes"]
         assert len(out_logits) == len(target_sizes)
         assert target_sizes.shape[1] == 2
-        prob = out_logits.sigmoid()
-        scores, idx = torch.topk(prob.view(out_logits.shape[0], -1), 100, dim=1)
-        qi = idx // out_logits.shape[2]
-        labels = idx % out_logits.shape[2]
-        cx, cy, w, h = out_bbox.unbind(-1)
-        xyxy = torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], -1)
-        xyxy = torch.gather(xyxy, 1, qi.unsqueeze(-1).repeat(1, 1, 4))
-        img_h, img_w = target_sizes.unbind(1)
-        xyxy = xyxy * torch.stack([img_w, img_h, img_w, img_h], dim=1)[:, None, :]
-        return [{"scores": s, "labels": l, "boxes": b} for s, l, b in zip(scores, labels, xyxy)]
+        dev = out_logits.device
+        B, Q, C = out_logits.shape
+        k = 100
+        scores = torch.empty(B, k, device=dev); labels = torch.empty(B, k, dtype=torch.int64, device=dev)
+        boxes = torch.empty(B, k, 4, device=dev)
+        L.call("cdetr_postprocess_topk", out_logits.detach().float().contiguous(), out_bbox.detach().float().contiguous(),
+               target_sizes.to(dev, torch.float32).contiguous(), B, Q, C, k, scores, labels, boxes)
+        return [{"scores": s, "labels": l, "boxes": b} for s, l, b in zip(scores, labels, boxes)]
 
 
 def _stage_of(args):

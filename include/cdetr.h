@@ -238,6 +238,25 @@ int cdetr_bbox_loss_bwd(const float* upstream2, const float* g_wh, const float* 
                         cdetr_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------
+ * Output formats of the two-stage recipe on the device; the reference copies every prediction tensor
+ * to the host and formats with numpy.  sizes_hw: fp32 [B,2] = (height, width) per image, like `target_sizes`.
+ *   cdetr_postprocess_topk: PostProcess.forward, A2/models/anchor_detr.py:370-402 (sigmoid, top-k over the flattened
+ *     [Q*C] scores in descending order, ties by ascending index; labels = idx % C; xyxy boxes in pixels); k <= Q*C <= 16384.
+ *   cdetr_infer_select: A2/infer.py:74-118: queries with sigmoid(logit[..., 0]) >= threshold, compacted in query order
+ *     (torch.where); out_* rows [B, Q]: query index, score, bbox = int([cx*w, cy*h, bw*w, bh*h]), area = int(bw*w * bh*h),
+ *     point = int(ref * [w, h]) -- the integers of the reference's int() on numpy float32 scalars; out_count[b] rows valid.
+ *   cdetr_pseudo_label_format: A1/engine.py:148-166: bbox = int([x*s0, y*s1, w*s0, h*s1]), area = int(w*s0 * h*s1) for n
+ *     (point, predicted wh) pairs; size2 = device fp32 [2] = orig_size as the reference indexes it.
+ * --------------------------------------------------------------------------------------------- */
+int cdetr_postprocess_topk(const float* logits, const float* boxes, const float* sizes_hw, int B, int Q, int C, int k,
+                           float* out_scores, int64_t* out_labels, float* out_boxes, cdetr_stream_t s);
+int cdetr_infer_select(const float* logits, int C, const float* boxes, const float* ref_points, const float* sizes_hw,
+                       int B, int Q, float threshold, int* out_count, int* out_query, float* out_score, int* out_bbox,
+                       int* out_area, int* out_point, cdetr_stream_t s);
+int cdetr_pseudo_label_format(const float* points, const float* whs, const float* size2, int64_t n, int* out_bbox,
+                              int* out_area, cdetr_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
  * Optimizer tail: multi-tensor gradient-norm clipping + AdamW.  Replace
  *   A2/engine.py:53-56  torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
  *   A2/engine.py:57 / A2/main.py:188  torch.optim.AdamW(param_dicts, lr, weight_decay).step()

@@ -61,6 +61,28 @@ run_nt(256, 256, 16384, split_k=16)
 run_nt(200, 72, 1000, split_k=3)  # ragged
 run_nt(64, 192, 512)
 
+# precision-policy variants (cdetr_gemm_t.pass_mask, the MASKED kernel instantiations): each must equal the exact product
+# of the correspondingly ROUNDED operands (5: b -> bf16, 3: a -> bf16, 1: both), which also proves no term is lost at 7
+def run_masked(M, N, K, pm, mode=0, **kw):
+    if mode == 0:
+        A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev)
+    else:
+        A = torch.randn(K, M, device=dev); B = torch.randn(K, N, device=dev)
+    As, Bs = L.to_split(A), L.to_split(B)
+    a_eff = L.from_split(As).double() if pm & 4 else As[0].double()
+    b_eff = L.from_split(Bs).double() if pm & 2 else Bs[0].double()
+    ref = a_eff @ b_eff.t() if mode == 0 else a_eff.t() @ b_eff
+    out = torch.zeros((M, N), device=dev)
+    L.gemm(As, Bs, M, N, K, mode=mode, out_f32=out, pass_mask=pm, accumulate=(mode == 1), **kw)
+    torch.cuda.synchronize()
+    return report(f"masked pm={pm} mode={mode} M={M} N={N} K={K} {kw}", out, ref)
+
+
+for pm in (5, 3, 1):
+    run_masked(384, 256, 320, pm)
+    run_masked(16384, 512, 1024, pm)          # CTA-pair shape
+    run_masked(256, 2304, 4096, pm, mode=1, split_k=8)
+
 # epilogue: bias + residual(split) + relu + split output; relu-mask; row_scale
 M, N, K = 512, 256, 320
 A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev)
