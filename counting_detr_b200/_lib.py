@@ -178,11 +178,13 @@ _SIGS = {
     "cdetr_postprocess_topk": "pppiiiippp",
     "cdetr_infer_select": "pipppiifpppppp",
     "cdetr_pseudo_label_format": "ppplpp",
+    "cdetr_normalize_u8": "piiiHHp",
     "cdetr_mt_grad_norm": "ppiifpp",
     "cdetr_mt_clip_scale": "ppiip",
     "cdetr_mt_adamw": "ppiipfffpp",
 }
-_CT = {"p": C.c_void_p, "i": C.c_int32, "l": C.c_int64, "f": C.c_float, "S": SplitT}
+_CT = {"p": C.c_void_p, "i": C.c_int32, "l": C.c_int64, "f": C.c_float, "S": SplitT,
+       "H": C.c_void_p}    # H = HOST pointer to a small float array (ctypes array)
 _bound = {}
 
 
@@ -206,6 +208,8 @@ def call(name, *args):
             conv.append(None if a is None else (a.data_ptr() if isinstance(a, torch.Tensor) else a))
         elif c == "S":
             conv.append(a if isinstance(a, SplitT) else split_view(a))
+        elif c == "H":
+            conv.append(C.cast(a, C.c_void_p))
         elif c == "f":
             conv.append(float(a))
         else:

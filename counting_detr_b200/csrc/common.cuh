@@ -256,6 +256,12 @@ __device__ __forceinline__ void bulk_wait_group() {        // <= N groups not ye
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ------------------------------- cp.async (LDGSTS) ---------------------------------------------
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ------------------------------- programmatic dependent launch -------------------------------
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its stream predecessor
 // is still running; it must execute pdl_wait() before touching anything the predecessor wrote.  pdl_trigger() lets

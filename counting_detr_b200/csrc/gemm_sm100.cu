@@ -53,6 +53,7 @@ struct KernelArgs {
   int tile_m;                         // output rows per tile: 128, or 256 for a CTA pair (cta_group::2)
   uint32_t idesc;
   uint32_t pass_mask;  // which of the three split-bf16 products are issued: 1 hi*hi, 2 hi_a*lo_b, 4 lo_a*hi_b (7 = all)
+  uint32_t tx_a, tx_b; // bytes one k-block's TMA loads deliver per operand (a lo plane no product reads is not loaded)
   uint32_t tmem_cols;  // columns of ONE accumulator buffer (two are allocated)
   // implicit 3x3 convolution (conv != 0): the conv operand (A in mode 0, B in mode 1) is an NHWC activation read
   // through a 5-D map {C, W, H, B, plane} with per-tap shifted windows; TMA zero-fills the out-of-image part
@@ -218,13 +219,13 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint8_t* a_s = RB ? smem + slab_bytes + (size_t)s * a_bytes : smem + (size_t)s * stage_bytes;
           uint8_t* b_s = a_s + a_bytes;
           if (RB) {
-            mbar_arrive_expect_tx(&full_bar[s], a_bytes);
+            mbar_arrive_expect_tx(&full_bar[s], args.tx_a);
             tma_load_3d(a_s, &tmA, &full_bar[s], kb * BK, m0, 0);  // box {64, BM, 2}
             continue;
           }
           if (PAIR) {
             // the leader's barrier collects the bytes of both CTAs' loads (its own arrive carries the expectation)
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_bytes);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (args.tx_a + args.tx_b));
             if (args.conv) {
               const int k0 = kb * BK;
               const int tap = k0 / args.cC;
@@ -236,7 +237,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tma_load_3d_pair(b_s, &tmB, &full_bar[s], kb * BK, n0 + rank * BNL, 0);  // box {64, BN/2, 2}
             continue;
           }
-          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          mbar_arrive_expect_tx(&full_bar[s], args.tx_a + args.tx_b);
           if (!NT) {
             if (args.conv) {   // box {64 c, W, 128/W, 1, 2}: rows of the tile = pixels (h, w) of image cb, shifted by the tap
               const int k0 = kb * BK;
@@ -784,7 +785,7 @@ EncodeTiledFn get_encode_fn() {
 
 // 3-D map over a split matrix: dim0 = contiguous index (extent inner), dim1 = rows, dim2 = plane.
 int make_split_map(CUtensorMap* map, const cdetr_split_t& t, int64_t inner, int64_t rows,
-                   int box_inner, int box_rows) {
+                   int box_inner, int box_rows, int planes = 2) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     cdetr_set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -797,7 +798,7 @@ int make_split_map(CUtensorMap* map, const cdetr_split_t& t, int64_t inner, int6
                   (long long)t.ld, (long long)t.plane);
   cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)rows, 2};
   cuuint64_t gstride[2] = {(cuuint64_t)t.ld * 2, (cuuint64_t)t.plane * 2};
-  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, (cuuint32_t)planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t.base, gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -811,7 +812,8 @@ int make_split_map(CUtensorMap* map, const cdetr_split_t& t, int64_t inner, int6
 }
 
 // 5-D map over an NHWC split activation [B*H*W, C]: dims {C, W, H, B, plane}; box {64, box_w, box_h, 1, 2}.
-int make_conv_map(CUtensorMap* map, const cdetr_split_t& t, int C, int W, int H, int B, int box_w, int box_h) {
+int make_conv_map(CUtensorMap* map, const cdetr_split_t& t, int C, int W, int H, int B, int box_w, int box_h,
+                  int planes = 2) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) {
     cdetr_set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -824,7 +826,7 @@ int make_conv_map(CUtensorMap* map, const cdetr_split_t& t, int C, int W, int H,
   cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 2};
   cuuint64_t gstride[4] = {(cuuint64_t)t.ld * 2, (cuuint64_t)W * t.ld * 2, (cuuint64_t)H * W * t.ld * 2,
                            (cuuint64_t)t.plane * 2};
-  cuuint32_t box[5] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, (cuuint32_t)planes};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, t.base, gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -980,18 +982,21 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
 
   CUtensorMap tmA, tmB;
   int rc;
+  // precision policy: an operand's lo plane is only loaded when a product reads it (bit 2: lo_a * hi_b, bit 1: hi_a * lo_b)
+  const uint32_t pmask = (g->pass_mask > 0 && g->pass_mask <= 7) ? ((uint32_t)g->pass_mask | 1u) : 7u;
+  const int pl_a = (pmask & 4u) ? 2 : 1, pl_b = (pmask & 2u) ? 2 : 1;
   if (!nt) {
     if (conv) {
-      if ((rc = make_conv_map(&tmA, g->a, g->conv_C, g->conv_W, g->conv_H, conv_B, g->conv_W, BM / g->conv_W)) != 0)
+      if ((rc = make_conv_map(&tmA, g->a, g->conv_C, g->conv_W, g->conv_H, conv_B, g->conv_W, BM / g->conv_W, pl_a)) != 0)
         return rc;
-    } else if ((rc = make_split_map(&tmA, g->a, g->K, g->M, BK, BM)) != 0) return rc;
-    if ((rc = make_split_map(&tmB, g->b, g->K, g->N, BK, pair ? bn / 2 : bn)) != 0) return rc;
+    } else if ((rc = make_split_map(&tmA, g->a, g->K, g->M, BK, BM, pl_a)) != 0) return rc;
+    if ((rc = make_split_map(&tmB, g->b, g->K, g->N, BK, pair ? bn / 2 : bn, pl_b)) != 0) return rc;
   } else {
-    if ((rc = make_split_map(&tmA, g->a, g->M, g->K, 64, BK)) != 0) return rc;
+    if ((rc = make_split_map(&tmA, g->a, g->M, g->K, 64, BK, pl_a)) != 0) return rc;
     if (conv) {
       const int bw = g->conv_W < 64 ? g->conv_W : 64;
-      if ((rc = make_conv_map(&tmB, g->b, g->conv_C, g->conv_W, g->conv_H, conv_B, bw, 64 / bw)) != 0) return rc;
-    } else if ((rc = make_split_map(&tmB, g->b, g->N, g->K, 64, BK)) != 0) return rc;
+      if ((rc = make_conv_map(&tmB, g->b, g->conv_C, g->conv_W, g->conv_H, conv_B, bw, 64 / bw, pl_b)) != 0) return rc;
+    } else if ((rc = make_split_map(&tmB, g->b, g->N, g->K, 64, BK, pl_b)) != 0) return rc;
   }
 
   KernelArgs ka;
@@ -1003,7 +1008,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   ka.cH = conv ? g->conv_H : 1; ka.cW = conv ? g->conv_W : 1; ka.cC = conv ? g->conv_C : 1;
   ka.cdil = g->conv_dil; ka.csign = g->conv_sign;
   ka.idesc = make_idesc_bf16_f32(pair ? 2 * BM : BM, bn, nt ? 1 : 0, nt ? 1 : 0);
-  ka.pass_mask = (g->pass_mask > 0 && g->pass_mask <= 7) ? ((uint32_t)g->pass_mask | 1u) : 7u;
+  ka.pass_mask = pmask;
   ka.tile_m = pair ? 2 * BM : BM;
   uint32_t cols = 32;
   while ((int)cols < bn) cols <<= 1;
@@ -1011,6 +1016,8 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   const uint32_t a_bytes = 2u * BM * 128u;
   const uint32_t b_bytes = nt ? (uint32_t)((bn + 63) / 64) * 16384u : 2u * (uint32_t)(pair ? bn / 2 : bn) * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
+  ka.tx_a = a_bytes / 2u * (uint32_t)pl_a;     // both operands are laid out [hi | lo] per tile / per 64-wide chunk
+  ka.tx_b = b_bytes / 2u * (uint32_t)pl_b;
   const uint32_t tail_bytes = (2 * MAX_STAGES + 6 + 16) * 8 + 16;
   const uint32_t smem_max = 227u * 1024u - 1024u - tail_bytes;   // dynamic smem minus alignment slack and barriers
 
@@ -1065,7 +1072,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   bool resident = false;
   {
     const int f = tune.gemm_resident;
-    if (f == 1) resident = !pair && !nt && !conv && splits == 1 && (uint32_t)num_kb * b_bytes + 2 * a_bytes + 8u * epi_buf <= smem_max;
+    if (f == 1) resident = pmask == 7u && !pair && !nt && !conv && splits == 1 && (uint32_t)num_kb * b_bytes + 2 * a_bytes + 8u * epi_buf <= smem_max;
   }
   ka.resident_b = 0;
   ka.tiles_per_cta = 0;

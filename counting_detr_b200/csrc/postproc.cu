@@ -165,3 +165,35 @@ extern "C" int cdetr_pseudo_label_format(const float* points, const float* whs, 
   CDETR_CHECK_LAUNCH();
   return 0;
 }
+
+// ------------------------------------------------------------------ input side
+// transforms.ToTensor() + transforms.Normalize(mean, std) of the reference's datasets (A2/data/fsc147.py:22-24,82,
+// A1/datasets/fscd_147.py) on the device: uint8 HWC pixels (what PIL hands over after the resize) -> fp32 NCHW
+//   y[b,c,h,w] = ((float(u8) / 255) - mean[c]) / std[c]        same fp32 operation order as torchvision -> bit-identical
+// so a batch crosses PCIe as 1 byte per value instead of 4.  One thread per 4 consecutive pixels of a row.
+namespace {
+__global__ void normalize_u8_kernel(const uint8_t* __restrict__ src, int B, int H, int W, float m0, float m1, float m2,
+                                    float s0, float s1, float s2, float* __restrict__ dst) {
+  const int64_t npix = (int64_t)B * H * W;
+  const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = p / ((int64_t)H * W), hw = p - b * (int64_t)H * W;
+    const uint8_t* s = src + p * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      dst[(b * 3 + c) * (int64_t)H * W + hw] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)s[c], 255.0f), mean[c]), stdv[c]);
+  }
+}
+}  // namespace
+
+extern "C" int cdetr_normalize_u8(const uint8_t* src_hwc, int B, int H, int W, const float* mean3_host,
+                                  const float* std3_host, float* dst_nchw, cdetr_stream_t s) {
+  CDETR_CHECK_ARG(src_hwc && dst_nchw && mean3_host && std3_host && B > 0 && H > 0 && W > 0, "normalize_u8: bad args");
+  const int64_t npix = (int64_t)B * H * W;
+  int grid = (int)((npix + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  normalize_u8_kernel<<<grid, 256, 0, STREAM(s)>>>(src_hwc, B, H, W, mean3_host[0], mean3_host[1], mean3_host[2],
+                                                   std3_host[0], std3_host[1], std3_host[2], dst_nchw);
+  CDETR_CHECK_LAUNCH();
+  return 0;
+}

@@ -670,6 +670,8 @@ struct TcBwdVArgs {
   uint32_t idesc;
   int tiles_per_cta;   // key-position tiles (of 128) per CTA: blockIdx.z selects the slice of positions (<= 8)
   int kp;              // rows of the staged attention maps: max(H, W) rounded up to 8 (<= 64)
+  int map_bufs;        // 2: the next query block's maps are prefetched (cp.async) while this block's tiles are built
+  int d_bufs;          // dO stages (2 when shared memory allows two CTAs per SM with it)
 };
 
 __global__ void __launch_bounds__(320, 2)
@@ -678,10 +680,10 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Ps = smem;                                    // [2 bufs][2 planes][128][64] bf16, SW128 K-major
-  uint8_t* Ds = Ps + 4 * P_TILE_BYTES;                   // [2 bufs][2 planes][64 q][32 c] bf16, SW64
-  float* ars = reinterpret_cast<float*>(Ds + 4 * DO_PLANE_BYTES);   // [kp][MAP_LD]
-  float* acs = ars + a.kp * MAP_LD;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(acs + a.kp * MAP_LD);
+  uint8_t* Ds = Ps + 4 * P_TILE_BYTES;                   // [d_bufs][2 planes][64 q][32 c] bf16, SW64
+  float* maps = reinterpret_cast<float*>(Ds + a.d_bufs * 2 * DO_PLANE_BYTES);   // [map_bufs][A_r | A_c][kp][MAP_LD]
+  const int map_stride = 2 * a.kp * MAP_LD;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(maps + a.map_bufs * map_stride);
   uint64_t* d_full = bars;       // [2]
   uint64_t* d_empty = bars + 2;  // [2]
   uint64_t* p_full = bars + 4;   // [2]
@@ -718,8 +720,8 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
   if (warp == 0) {
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb & 1;
-        if (kb >= 2) mbar_wait(&d_empty[s], (uint32_t)((kb >> 1) - 1) & 1u);
+        const int s = kb % a.d_bufs;
+        if (kb >= a.d_bufs) mbar_wait(&d_empty[s], (uint32_t)(kb / a.d_bufs - 1) & 1u);
         mbar_arrive_expect_tx(&d_full[s], 2 * DO_PLANE_BYTES);
         tma_load_3d(Ds + s * 2 * DO_PLANE_BYTES, &tmD, &d_full[s], head * HD, b * a.L + kb * VK, 0);
         tma_load_3d(Ds + s * 2 * DO_PLANE_BYTES + DO_PLANE_BYTES, &tmD, &d_full[s], head * HD, b * a.L + kb * VK, 1);
@@ -729,8 +731,8 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
     if (lane == 0) {
       int u = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb & 1;
-        mbar_wait(&d_full[s], (uint32_t)(kb >> 1) & 1u);
+        const int s = kb % a.d_bufs;
+        mbar_wait(&d_full[s], (uint32_t)(kb / a.d_bufs) & 1u);
         const uint32_t d_base = smem_u32(Ds) + (uint32_t)s * 2u * DO_PLANE_BYTES;
         for (int mt = mt_begin; mt < mt_end; ++mt, ++u) {
           const int pb = u & 1;
@@ -760,17 +762,35 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
     const int qh = ct & 1;                  // which half (32 queries) of the k block
     const int64_t bh = (int64_t)b * a.nh + head;
     int u = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int q0 = kb * VK;
-      asm volatile("bar.sync 1, 256;" ::: "memory");     // previous block's tiles are all built
+    // maps of one block of 64 queries -> shared memory, asynchronously (cp.async, 4 bytes each: rows of the transposed
+    // maps are only 4-byte aligned for odd L); out-of-range entries are zeros
+    auto stage_maps = [&](int kb2, float* dst) {
+      const int q0 = kb2 * VK;
       for (int i = ct; i < a.kp * VK; i += 256) {
         const int k = i / VK, qq = i % VK;
         const bool qok = q0 + qq < a.L;
         const int mo = k * MAP_LD + (qq >> 5) * 36 + (qq & 31);
-        ars[mo] = (qok && k < a.W) ? __ldg(a.ar + (bh * a.W + k) * a.L + q0 + qq) : 0.0f;
-        acs[mo] = (qok && k < a.H) ? __ldg(a.ac + (bh * a.H + k) * a.L + q0 + qq) : 0.0f;
+        if (qok && k < a.W) cp_async_4(dst + mo, a.ar + (bh * a.W + k) * a.L + q0 + qq); else dst[mo] = 0.0f;
+        if (qok && k < a.H) cp_async_4(dst + a.kp * MAP_LD + mo, a.ac + (bh * a.H + k) * a.L + q0 + qq);
+        else dst[a.kp * MAP_LD + mo] = 0.0f;
       }
+    };
+    if (a.map_bufs == 2) {
+      stage_maps(0, maps);
+      cp_async_wait_all();
       asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    for (int kb = 0; kb < nkb; ++kb) {
+      float* ars = maps + ((a.map_bufs == 2) ? (kb & 1) * map_stride : 0);
+      float* acs = ars + a.kp * MAP_LD;
+      if (a.map_bufs == 1) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // previous block's tiles are all built
+        stage_maps(kb, maps);
+        cp_async_wait_all();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      } else if (kb + 1 < nkb) {
+        stage_maps(kb + 1, maps + ((kb + 1) & 1) * map_stride);   // in flight while this block's tiles are built
+      }
       for (int mt = mt_begin; mt < mt_end; ++mt, ++u) {
         const int pb = u & 1;
         if (u >= 2) mbar_wait(&p_empty[pb], (uint32_t)((u >> 1) - 1) & 1u);
@@ -804,6 +824,10 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[pb]);
+      }
+      if (a.map_bufs == 2) {     // next block's maps have landed; everyone is done reading this block's
+        cp_async_wait_all();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
     // ---- epilogue: accumulators -> dV (split)
@@ -974,9 +998,16 @@ extern "C" int cdetr_rcda_bwd_v_tc(int B, int L, int H, int W, int E, int nh, co
   a.dv_hi = reinterpret_cast<__nv_bfloat16*>(dv.base); a.dv_lo = a.dv_hi + dv.plane; a.ld_g = dv.ld;
   a.idesc = make_idesc_bf16_f32(128, HD, 0, 1);
   a.kp = ((H > W ? H : W) + 7) / 8 * 8;
-  const size_t smem = 4 * P_TILE_BYTES + 4 * DO_PLANE_BYTES + 2 * (size_t)a.kp * MAP_LD * sizeof(float) + 128 + 1024;
+  // shared-memory plan: keep two CTAs per SM (<= ~112 KB each); spend what is left on prefetching the next query
+  // block's maps (double-buffered maps) and on a second dO stage
+  const size_t map_bytes = 2 * (size_t)a.kp * MAP_LD * sizeof(float);
+  const size_t fixed = 4 * P_TILE_BYTES + 128 + 1024;
+  const size_t budget = 112 * 1024;
+  a.map_bufs = fixed + 2 * DO_PLANE_BYTES + 2 * map_bytes <= budget ? 2 : 1;
+  a.d_bufs = fixed + 4 * DO_PLANE_BYTES + a.map_bufs * map_bytes <= budget ? 2 : 1;
+  const size_t smem = fixed + (size_t)a.d_bufs * 2 * DO_PLANE_BYTES + a.map_bufs * map_bytes;
   static DevAttrCache cfg = {};
-  CDETR_CHECK_CUDA(cdetr_ensure_smem(rcda_bwd_v_tc_kernel, 4 * P_TILE_BYTES + 4 * DO_PLANE_BYTES + 2 * 64 * MAP_LD * 4 + 128 + 1024, &cfg));
+  CDETR_CHECK_CUDA(cdetr_ensure_smem(rcda_bwd_v_tc_kernel, 4 * P_TILE_BYTES + 4 * DO_PLANE_BYTES + 2 * 2 * 64 * MAP_LD * 4 + 128 + 1024, &cfg));
   // split the key positions over enough CTAs to fill the machine at two CTAs per SM (one wave); a CTA keeps at most
   // 8 position tiles (256 TMEM columns, two CTAs per SM) resident
   int num_sms = 0;

@@ -8,7 +8,28 @@ batch on a dedicated copy stream while the caller works on the current one, and 
 safe to use on the current stream (event-ordered; double-buffered so that a batch is never overwritten while a step
 still reads it).  The host only ever waits for a copy issued `depth` batches earlier (before re-using its pinned staging buffer).
 """
+import ctypes as C
+
 import torch
+
+from . import _lib as L
+
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      # A2/data/fsc147.py:23
+
+
+def normalize_u8(images_u8, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
+    """transforms.ToTensor() + transforms.Normalize(mean, std) (A2/data/fsc147.py:22-24,82) on the device: uint8
+    [B,H,W,3] (or [H,W,3]) CUDA tensor -> fp32 [B,3,H,W], bit-identical to torchvision's result.  Ship the decoded,
+    resized uint8 pixels to the GPU (DevicePrefetcher) and normalise there: a quarter of the H2D bytes."""
+    x = images_u8 if images_u8.dim() == 4 else images_u8[None]
+    assert x.dtype == torch.uint8 and x.shape[-1] == 3 and x.is_cuda, "uint8 [B,H,W,3] CUDA tensor expected"
+    x = x.contiguous()
+    B, H, W, _ = x.shape
+    if out is None:
+        out = torch.empty(B, 3, H, W, device=x.device)
+    m = (C.c_float * 3)(*[float(v) for v in mean]); s = (C.c_float * 3)(*[float(v) for v in std])
+    L.call("cdetr_normalize_u8", x, B, H, W, m, s, out)
+    return out
 
 
 class DevicePrefetcher:

@@ -255,6 +255,11 @@ int cdetr_infer_select(const float* logits, int C, const float* boxes, const flo
                        int* out_area, int* out_point, cdetr_stream_t s);
 int cdetr_pseudo_label_format(const float* points, const float* whs, const float* size2, int64_t n, int* out_bbox,
                               int* out_area, cdetr_stream_t s);
+/* Input side: transforms.ToTensor() + Normalize(mean, std) of the reference's datasets
+ * (A2/data/fsc147.py:22-24,82) on the device: uint8 [B,H,W,3] pixels -> fp32 [B,3,H,W], y = ((u8 / 255) - mean[c]) / std[c]
+ * in torchvision's fp32 operation order (bit-identical); mean3 / std3 are HOST arrays of 3 floats. */
+int cdetr_normalize_u8(const uint8_t* src_hwc, int B, int H, int W, const float* mean3_host, const float* std3_host,
+                       float* dst_nchw, cdetr_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------
  * Optimizer tail: multi-tensor gradient-norm clipping + AdamW.  Replace

@@ -64,3 +64,17 @@ def test_postprocess_kernel_matches_oracle_and_torch_topk():
             assert torch.equal(a["labels"].cpu(), b["labels"])
             assert torch.allclose(a["boxes"].cpu(), b["boxes"], atol=1e-4)
             assert (a["scores"][1:] <= a["scores"][:-1]).all()
+
+
+def test_normalize_u8_is_bit_identical_to_totensor_normalize():
+    """transforms.ToTensor() + Normalize (A2/data/fsc147.py:22-24,82; torchvision functional: to float32, div(255),
+    sub_(mean), div_(std)) restated with plain torch ops on the CPU; the device kernel must match bit for bit."""
+    from counting_detr_b200.data import IMAGENET_MEAN, IMAGENET_STD, DevicePrefetcher, normalize_u8
+    g = torch.Generator().manual_seed(0)
+    u8 = torch.randint(0, 256, (3, 96, 160, 3), generator=g, dtype=torch.uint8)
+    ref = u8.permute(0, 3, 1, 2).contiguous().to(torch.float32).div(255)
+    mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1); std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+    ref = ref.sub_(mean).div_(std)
+    for batch in DevicePrefetcher([{"image": u8}], "cuda"):
+        got = normalize_u8(batch["image"])
+    assert torch.equal(got.cpu(), ref)

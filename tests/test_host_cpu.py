@@ -32,8 +32,8 @@ def test_binding_signatures_match_header(built_lib):
         assert len(args) == len(sig) + 1, n
         for a, c in zip(args, sig):
             t = "S" if "cdetr_split_t" in a else "p" if "*" in a else "f" if a.startswith("float") else "l" if "int64_t" in a else "i"
-            assert t == c, (n, a, c)
-    assert ctypes.sizeof(L.GemmT) == 224
+            assert t == ("p" if c == "H" else c), (n, a, c)      # H = host pointer (small float array)
+    assert ctypes.sizeof(L.GemmT) == 232
 
 
 def test_sass_uses_tcgen05_and_tma(built_lib):
