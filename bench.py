@@ -405,29 +405,33 @@ def run_ours(args):
         eager = {"ms_per_step": timed(eager_step, min(steps, 10)), "what": "same step, ~1000 eager ctypes launches per step"}
         eager["value"] = B * world / eager["ms_per_step"] * 1e3
 
+    # ---- roofline: the tcgen05 GEMM family (all forward / dgrad / wgrad GEMMs of one step), instrumented step.  Every
+    # rank runs it (the criterion's num_boxes all-reduce is a collective); rank 0 records the events.
+    eng = model.engine()
+    saved_streams = (eng.side_stream, eng.aux_streams)
+    eng.side_stream, eng.aux_streams = None, []      # serialise: each GEMM timed alone on one stream
+    b0 = devb[0]
+
+    def plain_step():
+        if st == 2:
+            o, _ = model(b0["image"], None, b0["rects"])
+        else:
+            o = model(b0["image"], b0["points"])
+        ld = crit(o, b0["targets"])
+        sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict).backward()
+
+    plain_step()
+    if rank == 0:
+        L.GEMM_TRACE, L.CALL_TRACE = [], []
+    plain_step()
+    torch.cuda.synchronize()
+    trace, L.GEMM_TRACE = L.GEMM_TRACE, None
+    atrace, L.CALL_TRACE = L.CALL_TRACE, None
+    eng.side_stream, eng.aux_streams = saved_streams
+    barrier()
+
     line = None
     if rank == 0:
-        # ---- roofline: the tcgen05 GEMM family (all forward / dgrad / wgrad GEMMs of one step), instrumented step
-        eng = model.engine()
-        saved_streams = (eng.side_stream, eng.aux_streams)
-        eng.side_stream, eng.aux_streams = None, []      # serialise: each GEMM timed alone on one stream
-        b0 = devb[0]
-
-        def plain_step():
-            if st == 2:
-                o, _ = model(b0["image"], None, b0["rects"])
-            else:
-                o = model(b0["image"], b0["points"])
-            ld = crit(o, b0["targets"])
-            sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict).backward()
-
-        plain_step()
-        L.GEMM_TRACE, L.CALL_TRACE = [], []
-        plain_step()
-        torch.cuda.synchronize()
-        trace, L.GEMM_TRACE = L.GEMM_TRACE, None
-        atrace, L.CALL_TRACE = L.CALL_TRACE, None
-        eng.side_stream, eng.aux_streams = saved_streams
         flops = sum(2.0 * m * n * k for (m, n, k, _, _) in trace)
         gemm_ms = sum(a.elapsed_time(b) for (_, _, _, a, b) in trace)
         peaks = {}

@@ -124,7 +124,15 @@ class CapturedStep:
         self.model.engine().pack_weights()
         self.model._param_version = self.model._current_version()
 
+    def _prep(self):
+        """hoisted 1-float num_boxes all-reduce (A2/models/anchor_detr.py:321-325): issued OUTSIDE any capture, the
+        criterion's forward then finds the device-resident value prepared for exactly these target tensors"""
+        crit = self.criterion
+        if hasattr(crit, "prepare_num_boxes"):
+            crit.prepare_num_boxes(self._static["targets"], next(self.model.parameters()).device, self.group)
+
     def _eager_step(self):
+        self._prep()
         out = self._body()
         if self.group is not None:
             self.model.allreduce_grads(self.group)
@@ -150,6 +158,7 @@ class CapturedStep:
         torch.cuda.current_stream().wait_stream(self._stream)
         torch.cuda.synchronize(dev)
         c0 = L.COUNTER["launches"]
+        self._prep()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=self._stream):
             self._out = self._body()
@@ -175,22 +184,18 @@ class CapturedStep:
         model, crit = self.model, self.criterion
         dev = next(model.parameters()).device
         key = self._sig(samples, targets, rects, points)
-        hoist = hasattr(crit, "prepare_num_boxes")
         if key != self._key:
             self._static = self._make_static(samples, targets, rects, points, dev)
             self._fill(samples, targets, rects, points)
-            if hoist:
-                crit.prepare_num_boxes(self._static["targets"], dev, self.group)
             self._capture(dev)
             self._key = key
             self._version = model._current_version()
         self._fill(samples, targets, rects, points)
-        if hoist:
-            crit.prepare_num_boxes(self._static["targets"], dev, self.group)   # hoisted 1-float all-reduce (world > 1)
         if self.optimizer is not None:
             self.optimizer.sync_hyper()          # LR scheduler changes reach the device hyper-parameter array
         if self._graph is None:
             return self._eager_step()
+        self._prep()
         ver = model._current_version()
         if ver != self._version:                 # someone else changed the weights (load_state_dict, ...): re-pack
             model.engine().pack_weights()
