@@ -402,7 +402,16 @@ def run_ours(args):
             if world > 1:
                 model.allreduce_grads(group)
         eager_step(0)
-        eager = {"ms_per_step": timed(eager_step, min(steps, 10)), "what": "same step, ~1000 eager ctypes launches per step"}
+        for i in range(4):        # lets the model capture its forward / backward launch sequences (automatic after 2 runs)
+            eager_step(i)
+        eager = {"ms_per_step": timed(eager_step, min(steps, 10)),
+                 "what": "the reference's own loop body: model(...) -> criterion(...) -> losses.backward() called eagerly; the "
+                         "model replays its forward / backward launch sequences as CUDA graphs after two runs of a signature"}
+        model._auto_graph = False
+        model._graphs.clear()
+        eager_step(0)
+        eager["ms_per_step_no_graphs"] = timed(eager_step, min(steps, 10))
+        model._auto_graph = True
         eager["value"] = B * world / eager["ms_per_step"] * 1e3
 
     # ---- roofline: the tcgen05 GEMM family (all forward / dgrad / wgrad GEMMs of one step), instrumented step.  Every
@@ -420,6 +429,7 @@ def run_ours(args):
         ld = crit(o, b0["targets"])
         sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict).backward()
 
+    model._auto_graph = False            # every launch of the instrumented step is timed on its own: no graph replay
     plain_step()
     if rank == 0:
         L.GEMM_TRACE, L.CALL_TRACE = [], []

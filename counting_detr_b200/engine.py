@@ -610,9 +610,12 @@ class Engine:
             ref = self.params["transformer.position.weight"]
         elif cfg.spatial_prior == "grid":
             n = round(math.sqrt(cfg.num_query_position))
-            g = (torch.arange(n, dtype=torch.float32) + 0.5) / n
-            gx, gy = torch.meshgrid(g, g, indexing="ij")
-            ref = torch.stack([gx.reshape(-1), gy.reshape(-1)], -1).to(self.dev)
+            key = ("grid_ref", (n,), None)
+            ref = self._bufs.get(key)
+            if ref is None:               # constant: built once (also keeps the forward free of host -> device copies)
+                g = (torch.arange(n, dtype=torch.float32) + 0.5) / n
+                gx, gy = torch.meshgrid(g, g, indexing="ij")
+                ref = self._bufs[key] = torch.stack([gx.reshape(-1), gy.reshape(-1)], -1).to(self.dev).contiguous()
         elif cfg.spatial_prior in ("defined", "sampled"):
             # A1/models/transformer.py:114-121 (points [1,Q,2] tensor), A2 :125-133 (ndarray [Q,2] / tensor [Q,2])
             assert points is not None, f"{cfg.spatial_prior}, provide points"

@@ -191,6 +191,10 @@ class AnchorDETR(nn.Module):
         self._param_version = None
         self._grad_group = None
         self._alias_grads = False
+        self._auto_graph = os.environ.get("CDETR_AUTO_GRAPH", "1") != "0"
+        self._graphs = {}
+        self._pack_graph = None
+        self._cap_stream = None
 
     def enable_grad_sync(self, group):
         """Average parameter gradients over `group` (torch.distributed, NCCL) at the end of every backward."""
@@ -230,7 +234,27 @@ class AnchorDETR(nn.Module):
             buffers = {n: b for n, b in self.named_buffers()}
             self._engine = Engine(self.cfg, params, buffers, dev, train_backbone=self.train_backbone)
             self._names = [n for n, _ in self.named_parameters()]
+            self._graphs, self._pack_graph = {}, None
         return self._engine
+
+    def _capture_stream(self, dev):
+        if self._cap_stream is None or self._cap_stream.device != dev:
+            self._cap_stream = torch.cuda.Stream(device=dev, priority=-1)
+        return self._cap_stream
+
+    def _pack_weights_graphed(self, eng):
+        """The re-pack of the weights an optimizer step changed (125 pack + 53 FrozenBN-fold launches) as one graph
+        replay; parameter storages are fixed (load_state_dict copies in place), checked by their pointers."""
+        key = tuple(p.data_ptr() for p in self.parameters())
+        if self._pack_graph is None or self._pack_graph[0] != key:
+            eng.pack_weights()                       # eager once: allocates the packed buffers
+            torch.cuda.synchronize(eng.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self._capture_stream(eng.dev)):
+                eng.pack_weights()
+            self._pack_graph = (key, g)
+        self._pack_graph[1].replay()
+        eng.packed = True
 
     def _current_version(self):
         return tuple(p._version for p in self.parameters())
@@ -339,15 +363,67 @@ class _EngineCfg:
         self.aux_loss = aux_loss
 
 
+class _GraphEntry:
+    """CUDA graphs of the engine's forward / backward launch sequences for one input signature (see _ModelFn)."""
+
+    def __init__(self):
+        self.seen = 0
+        self.image = self.mask = None        # static inputs the captured kernels read
+        self.fwd = self.bwd = None           # torch.cuda.CUDAGraph
+        self.outs = self.dims = None         # engine output buffers (static) of the captured forward
+        self.gpattern = self.gbufs = None    # which output gradients exist + their static buffers
+        self.failed = False
+
+
+_AUTO_GRAPH_WARMUP = 2       # eager runs of a signature before its launch sequences are captured
+_AUTO_GRAPH_MAX = 4          # signatures kept per model (LRU)
+
+
 class _ModelFn(torch.autograd.Function):
-    """One autograd node for the whole network: forward and backward are the engine's kernel sequences."""
+    """One autograd node for the whole network: forward and backward are the engine's kernel sequences.
+
+    The reference's unmodified loop (A2/engine.py:24-63) calls model(...) / losses.backward() eagerly: ~600 + ~330 C-ABI
+    launches per step through ctypes, ~7 ms of host time at C3.  Because every buffer of the engine lives at a fixed
+    address and nothing reads device data on the host, the two launch sequences are captured into CUDA graphs after an
+    input signature (shapes, train/eval) has been seen twice, and replayed from then on: the eager API runs at nearly
+    the speed of a whole-step capture (counting_detr_b200.step.CapturedStep) without the caller changing a line.
+    Signatures that keep changing (bs=1 with varying image sizes) simply stay eager.  CDETR_AUTO_GRAPH=0 disables it."""
+
+    @staticmethod
+    def _entry(module, image, rects0, points, mask):
+        if not module._auto_graph or points is not None or torch.cuda.is_current_stream_capturing():
+            return None
+        if L.GEMM_TRACE is not None or L.CALL_TRACE is not None:
+            return None                      # instrumented runs time individual launches
+        sig = (tuple(image.shape), None if mask is None else tuple(mask.shape),
+               None if rects0 is None else tuple(rects0.shape), module.training, torch.is_grad_enabled())
+        g = module._graphs
+        e = g.get(sig)
+        if e is None:
+            if len(g) >= _AUTO_GRAPH_MAX:
+                g.pop(next(iter(g)))
+            e = g[sig] = _GraphEntry()
+        else:
+            g[sig] = g.pop(sig)              # LRU order
+        e.seen += 1
+        return None if (e.failed or e.seen <= _AUTO_GRAPH_WARMUP) else e
+
+    @staticmethod
+    def _run_forward(module, eng, image, has_rects, mask):
+        yx = None
+        if has_rects:
+            H, W = feat_size(image.shape[2]), feat_size(image.shape[3])
+            L.call("cdetr_exemplar_centres", module._rects_dev, module._rects_dev.shape[0], H, W, module._centres_dev,
+                   status_flag(eng.dev))
+            yx = module._centres_dev
+        eng.zero_grad()
+        return eng.forward(image, yx, None, mask)
 
     @staticmethod
     def forward(ctx, module, image, rects0, points, mask, *params):
         eng = module.engine()
         dev = eng.dev
         image = image.to(dev, torch.float32)
-        yx = None
         if rects0 is not None:
             # static device buffers updated in place (fixed addresses: a captured step stays valid when the rects
             # change); the centres are computed on the device, so device-resident rects cost no host read
@@ -357,13 +433,45 @@ class _ModelFn(torch.autograd.Function):
                 module._rects_dev = torch.zeros(n_ex, 4, device=dev)
                 module._centres_dev = torch.zeros(n_ex, 2, dtype=torch.int32, device=dev)
             module._rects_dev.copy_(r.reshape(n_ex, 4), non_blocking=True)
-            H, W = feat_size(image.shape[2]), feat_size(image.shape[3])
-            L.call("cdetr_exemplar_centres", module._rects_dev, n_ex, H, W, module._centres_dev, status_flag(dev))
-            yx = module._centres_dev
         if mask is not None:
             mask = mask.to(dev).to(torch.uint8).contiguous()
-        eng.zero_grad()
-        outs, dims = eng.forward(image, yx, points, mask)
+        entry = _ModelFn._entry(module, image, rects0, points, mask)
+        if entry is not None:
+            try:
+                if not eng.packed:
+                    module._pack_weights_graphed(eng)
+                if entry.fwd is None:
+                    torch.cuda.synchronize(dev)
+                    entry.image = image.clone()
+                    entry.mask = None if mask is None else mask.clone()
+                    eng._plan_backbone(image.shape[2], image.shape[3])
+                    if not eng.packed:
+                        eng.pack_weights()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=module._capture_stream(dev)):
+                        entry.outs, entry.dims = _ModelFn._run_forward(module, eng, entry.image, rects0 is not None, entry.mask)
+                    entry.fwd = g
+                else:
+                    entry.image.copy_(image, non_blocking=True)
+                    if mask is not None:
+                        entry.mask.copy_(mask, non_blocking=True)
+                entry.fwd.replay()
+                outs, dims = entry.outs, entry.dims
+            except Exception as e:           # capture is an optimisation: never let it break the step
+                warnings.warn(f"CUDA-graph capture of the forward disabled for this input signature: {type(e).__name__}: {e}")
+                entry.failed = True
+                entry.fwd = entry.bwd = None
+                torch.cuda.synchronize(dev)
+                entry = None
+        if entry is None:
+            yx = None
+            if rects0 is not None:
+                H, W = feat_size(image.shape[2]), feat_size(image.shape[3])
+                L.call("cdetr_exemplar_centres", module._rects_dev, module._rects_dev.shape[0], H, W, module._centres_dev,
+                       status_flag(dev))
+                yx = module._centres_dev
+            eng.zero_grad()
+            outs, dims = eng.forward(image, yx, points, mask)
         B, Q = dims["B"], dims["Q"]
         flat = []
         for o in outs:
@@ -373,6 +481,7 @@ class _ModelFn(torch.autograd.Function):
                 flat.append(o["vars"].view(B, Q, 2).clone())
         ref = eng.saved["ref"].unsqueeze(0).expand(B, Q, 2).clone()
         ctx.module = module
+        ctx.entry = entry
         ctx.n_out = len(outs)
         ctx.mark_non_differentiable(ref)
         return tuple(flat) + (ref,)
@@ -382,25 +491,53 @@ class _ModelFn(torch.autograd.Function):
         module = ctx.module
         eng = module.engine()
         n_per = 3 if module.stage == 2 else 2
+        names = ("logits", "boxes", "vars")
+        widths = (2, 4, 2)
         grads = []
         for i in range(ctx.n_out):
             g = gouts[i * n_per:(i + 1) * n_per]
             d = {}
-            if g[0] is not None:
-                d["logits"] = g[0].contiguous().view(-1, 2)
-            if g[1] is not None:
-                d["boxes"] = g[1].contiguous().view(-1, 4)
-            if module.stage == 2 and g[2] is not None:
-                d["vars"] = g[2].contiguous().view(-1, 2)
+            for j in range(n_per):
+                if g[j] is not None:
+                    d[names[j]] = g[j].contiguous().view(-1, widths[j])
             grads.append(d)
-        eng.backward(grads)
+        entry = ctx.entry
+        if entry is not None and not entry.failed and not torch.cuda.is_current_stream_capturing():
+            pattern = tuple(tuple(sorted(d)) for d in grads)
+            try:
+                if entry.bwd is None:
+                    torch.cuda.synchronize(eng.dev)
+                    entry.gpattern = pattern
+                    entry.gbufs = [{k: v.clone() for k, v in d.items()} for d in grads]
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=module._capture_stream(eng.dev)):
+                        eng.backward(entry.gbufs)
+                    entry.bwd = g
+                elif pattern != entry.gpattern:
+                    raise RuntimeError("gradient pattern changed")
+                else:
+                    for sd, d in zip(entry.gbufs, grads):
+                        for k, v in d.items():
+                            sd[k].copy_(v, non_blocking=True)
+                entry.bwd.replay()
+            except Exception as e:
+                warnings.warn(f"CUDA-graph capture of the backward disabled for this input signature: {type(e).__name__}: {e}")
+                entry.failed = True
+                entry.fwd = entry.bwd = None
+                torch.cuda.synchronize(eng.dev)
+                eng.backward(grads)
+        else:
+            eng.backward(grads)
         if module._grad_group is not None:
             # data parallel: one all-reduce of the flat gradient buffer (the path shards by image)
             from .parallel import average_flat_grads
             average_flat_grads(eng.grad_flat[: eng.n_param_grad], module._grad_group,
                                scale_fn=lambda t, s: L.call("cdetr_scale", t, t.numel(), s))
-        # parameter gradients live in the engine's flat buffer (one allocation: all-reduce friendly)
+        # parameter gradients live in the engine's flat buffer (one allocation: all-reduce friendly).  Autograd must
+        # own what it accumulates into p.grad (the next forward clears the flat buffer), so ONE copy of the flat buffer
+        # is taken and each parameter receives a fresh view of it (AccumulateGrad adopts it without another copy)
         out = []
+        snap = None if module._alias_grads else eng.grad_flat[: eng.n_param_grad].clone()
         for n, p in zip(module._names, module.parameters()):
             gv = eng.grad_views.get(n)
             if gv is None or not p.requires_grad:
@@ -410,7 +547,8 @@ class _ModelFn(torch.autograd.Function):
                     p.grad = gv
                 out.append(None)
             else:
-                out.append(gv)
+                off = (gv.data_ptr() - eng.grad_flat.data_ptr()) // 4
+                out.append(snap[off:off + gv.numel()].view(gv.shape))
         return (None, None, None, None, None) + tuple(out)
 
 
