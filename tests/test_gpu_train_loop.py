@@ -157,8 +157,12 @@ def test_captured_step_matches_the_eager_loop():
         assert abs(a - b) <= 2e-5 * abs(b), (replayed, eager)   # same kernels; split-K atomics reorder fp32 sums
     for (n, p), q in zip(model_a.named_parameters(), model_b.parameters()):
         if p.requires_grad:
-            # AdamW turns gradient noise (split-K atomic order) into a fraction of lr per step: bound 0.2 * lr * steps
-            assert (p - q).abs().max().item() <= 0.2 * LR * steps, n
+            # AdamW normalises every gradient element by its own magnitude, so an element whose gradient is at the
+            # noise floor of the fp32 atomics (split-K summation order differs from run to run) can move by up to lr per
+            # step in either direction: bound the worst element by that, and require the bulk to agree to 1 % of a step
+            d = (p - q).abs()
+            assert d.max().item() <= 2 * LR * steps, n
+            assert d.mean().item() <= 0.01 * LR, (n, d.mean().item())
     sd = opt_b.state_dict()
     assert float(sd["state"][0]["step"]) == steps
 
