@@ -153,6 +153,7 @@ class Engine:
         self.E, self.nh, self.F = cfg.hidden_dim, cfg.nheads, cfg.dim_feedforward
         assert self.E == 256 and self.E // self.nh == 32, "kernels are specialised for E=256, head_dim=32"
         self._bufs = {}
+        self._sig_keys, self._cur_sig, self.evictions = {}, None, 0
         self.saved = {}
         # ---- which parameters receive gradients (A2/models/backbone.py:93-95: conv1 + layer1 frozen, BN frozen)
         self.trainable = []
@@ -267,7 +268,28 @@ class Engine:
             self._bufs[key] = t
         elif zero:
             t.zero_()
+        if self._cur_sig is not None:
+            self._sig_keys[self._cur_sig].add(key)
         return t
+
+    MAX_SIGNATURES = 3      # input signatures (batch, image size, queries) whose buffer sets are kept
+
+    def _enter_signature(self, sig):
+        """Every intermediate is cached per shape at a fixed address (graph capture needs that), so a workload whose
+        image size changes from step to step (the reference's bs=1 FSCD-147 loop) would grow the cache for a whole epoch:
+        keep the buffer sets of the MAX_SIGNATURES most recent signatures and free the rest.  `evictions` lets holders
+        of captured graphs (which reference those addresses) notice and re-capture."""
+        keys = self._sig_keys.pop(sig, None)
+        self._sig_keys[sig] = keys if keys is not None else set()      # most recent last
+        self._cur_sig = sig
+        while len(self._sig_keys) > self.MAX_SIGNATURES:
+            old, old_keys = next(iter(self._sig_keys.items()))
+            del self._sig_keys[old]
+            live = set().union(*self._sig_keys.values()) if self._sig_keys else set()
+            for k in old_keys - live:
+                self._bufs.pop(k, None)
+            self.saved = {}
+            self.evictions += 1
 
     def sbuf(self, name, rows, cols):
         return self.buf(name, (2, rows, _r8(cols)), torch.bfloat16)
@@ -367,6 +389,7 @@ class Engine:
             if not blk["c2"].implicit:
                 max_col = max(max_col, B * Hs * Ws * _r8(9 * blk["planes"]))
         colbuf = self.buf("col_scratch", (2, max(max_col, 8)), torch.bfloat16)
+        sv["col_scratch"] = colbuf
         for blk in self.blocks:
             n, p_, s, d = blk["name"], blk["planes"], blk["stride"], blk["dil"]
             Min = B * H * W
@@ -404,7 +427,7 @@ class Engine:
     def _backbone_bwd(self, g, B):
         """g: split grad w.r.t. the last block's output, already masked by that output's ReLU."""
         sv = self.saved
-        col2buf = self.buf("col_scratch", self._bufs_key_shape("col_scratch"), torch.bfloat16)  # free after the forward
+        col2buf = sv["col_scratch"]      # the forward's im2col scratch is free again: reused for the col2im input
         for blk in reversed(self.blocks):
             if not blk["train"]:
                 break
@@ -448,12 +471,6 @@ class Engine:
                 for k in ("c1", "c2", "c3", "ds"):
                     if blk[k] is not None:
                         blk[k].finish_grad()
-
-    def _bufs_key_shape(self, name):
-        for (n, shape, _), _t in self._bufs.items():
-            if n == name:
-                return shape
-        raise KeyError(name)
 
     # ------------------------------------------------------------------ small helpers
     def _mlp2_fwd(self, key, e0, n, tag):
@@ -627,12 +644,16 @@ class Engine:
     def forward(self, image, centres_yx=None, points=None, mask_img=None):
         """image [B,3,S1,S2] fp32 cuda; centres_yx device int32 [n_ex,2] (stage 2); mask_img device uint8 [B,S1,S2]
         (1 = padded pixel) or None; returns the per-layer head outputs (fp32)."""
+        self._enter_signature((tuple(image.shape), None if points is None else tuple(torch.as_tensor(points).shape)))
         self._plan_backbone(image.shape[2], image.shape[3])
         if not self.packed:
             self.pack_weights()
         cfg, E, sv = self.cfg, self.E, self.saved
         B = image.shape[0]
         feat, H, W = self._backbone_fwd(image.contiguous())
+        if max(H, W) > 64 and torch.is_grad_enabled():
+            raise NotImplementedError(f"training on a {H}x{W} feature map: the RCDA backward kernels cover maps up to 64x64 "
+                                      "(inputs up to 1024 px per side); larger images run forward-only (CUDA-core RCDA)")
         N = H * W
         M = B * N
         sv["dims"] = dict(B=B, H=H, W=W)

@@ -193,6 +193,7 @@ class AnchorDETR(nn.Module):
         self._alias_grads = False
         self._auto_graph = os.environ.get("CDETR_AUTO_GRAPH", "1") != "0"
         self._graphs = {}
+        self._graph_evictions = 0
         self._pack_graph = None
         self._cap_stream = None
 
@@ -234,7 +235,7 @@ class AnchorDETR(nn.Module):
             buffers = {n: b for n, b in self.named_buffers()}
             self._engine = Engine(self.cfg, params, buffers, dev, train_backbone=self.train_backbone)
             self._names = [n for n, _ in self.named_parameters()]
-            self._graphs, self._pack_graph = {}, None
+            self._graphs, self._pack_graph, self._graph_evictions = {}, None, 0
         return self._engine
 
     def _capture_stream(self, dev):
@@ -397,6 +398,10 @@ class _ModelFn(torch.autograd.Function):
             return None                      # instrumented runs time individual launches
         sig = (tuple(image.shape), None if mask is None else tuple(mask.shape),
                None if rects0 is None else tuple(rects0.shape), module.training, torch.is_grad_enabled())
+        eng = module.engine()
+        if eng.evictions != module._graph_evictions:      # buffers of an old signature were freed: captured addresses are stale
+            module._graphs.clear()
+            module._graph_evictions = eng.evictions
         g = module._graphs
         e = g.get(sig)
         if e is None:

@@ -39,6 +39,7 @@ class CapturedStep:
         self._out = None
         self._stream = None
         self._version = None
+        self._evictions = 0
         self.launches_per_step = None
         model.alias_param_grads(True)      # p.grad = views of the flat gradient buffer: fixed addresses, no copies
         if optimizer is not None and not hasattr(optimizer, "note_replayed_step"):
@@ -184,11 +185,13 @@ class CapturedStep:
         model, crit = self.model, self.criterion
         dev = next(model.parameters()).device
         key = self._sig(samples, targets, rects, points)
-        if key != self._key:
+        eng = model.engine()
+        if key != self._key or eng.evictions != self._evictions:     # new shapes, or the engine freed this capture's buffers
             self._static = self._make_static(samples, targets, rects, points, dev)
             self._fill(samples, targets, rects, points)
             self._capture(dev)
             self._key = key
+            self._evictions = eng.evictions
             self._version = model._current_version()
         self._fill(samples, targets, rects, points)
         if self.optimizer is not None:
