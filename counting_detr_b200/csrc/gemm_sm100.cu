@@ -424,6 +424,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (mrow >= args.M || nbase >= args.N) continue;   // warp-uniform, same predicate as chunk_valid
         const int b = nb == 2 ? (ci & 1) : 0;
         uint8_t* buf = wbuf + (uint32_t)b * args.epi_buf_bytes;
+        const uint32_t sbuf = smem_u32(buf);
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr_row + (uint32_t)cl, r);
         if (nb == 1) {   // single buffer: the previous chunk's store must have drained before its inputs may land
@@ -440,18 +441,18 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const uint32_t off = row64 + (((uint32_t)c ^ sw64) << 4);
-              ain[c] = *reinterpret_cast<const uint4*>(buf + off);
-              ain[4 + c] = *reinterpret_cast<const uint4*>(buf + 2048 + off);
+              ain[c] = lds128u(sbuf + off);            // explicit LDS / STS throughout: `buf` has lost its address space
+              ain[4 + c] = lds128u(sbuf + 2048 + off);
             }
           } else if (add_kind == 2) {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-              ain[c] = *reinterpret_cast<const uint4*>(buf + row128 + (((uint32_t)c ^ sw128) << 4));
+              ain[c] = lds128u(sbuf + row128 + (((uint32_t)c ^ sw128) << 4));
           }
           if (has_mask) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              amk[c] = *reinterpret_cast<const uint4*>(buf + args.epi_off_mask + row64 + (((uint32_t)c ^ sw64) << 4));
+              amk[c] = lds128u(sbuf + args.epi_off_mask + row64 + (((uint32_t)c ^ sw64) << 4));
           }
         }
         if (nb == 2) {
@@ -532,12 +533,14 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           continue;
         }
         uint8_t* sdst = buf;
+        uint32_t ssdst = sbuf;
         if (ep.out_f32 != nullptr) {
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<float4*>(buf + row128 + (((uint32_t)c ^ sw128) << 4)) =
-                make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            sts128(sbuf + row128 + (((uint32_t)c ^ sw128) << 4), __float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
+                   __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
           sdst = buf + args.epi_off_out2;
+          ssdst = sbuf + args.epi_off_out2;
         }
         if (ep.out_hi != nullptr) {
 #pragma unroll
@@ -546,8 +549,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 4; ++j) split_bf16_pair(v[8 * c + 2 * j], v[8 * c + 2 * j + 1], hw[j], lw[j]);
             const uint32_t off = row64 + (((uint32_t)c ^ sw64) << 4);
-            *reinterpret_cast<uint4*>(sdst + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            *reinterpret_cast<uint4*>(sdst + 2048 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            sts128(ssdst + off, hw[0], hw[1], hw[2], hw[3]);
+            sts128(ssdst + 2048 + off, lw[0], lw[1], lw[2], lw[3]);
           }
         }
         fence_proxy_async();   // generic-proxy writes above -> visible to the TMA unit

@@ -73,8 +73,8 @@ __device__ __forceinline__ void write_operand_row32(uint8_t* dst, uint32_t plane
 #pragma unroll
     for (int i = 0; i < 4; ++i) split_bf16_pair(x[8 * j + 2 * i], x[8 * j + 2 * i + 1], hw[i], lw[i]);
     const uint32_t off = (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4);
-    *reinterpret_cast<uint4*>(dst + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(dst + plane_bytes + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    sts128(smem_u32(dst + off), hw[0], hw[1], hw[2], hw[3]);
+    sts128(smem_u32(dst + plane_bytes + off), lw[0], lw[1], lw[2], lw[3]);
   }
 }
 
@@ -205,8 +205,8 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
       for (int i = 0; i < 4; ++i) split_bf16_pair(x[2 * i], x[2 * i + 1], hw[i], lw[i]);
       uint8_t* kd = Kb + (size_t)side * 2 * K_PLANE_BYTES;
       const uint32_t off = (uint32_t)k * 64u + (uint32_t)((j ^ ((k >> 1) & 3)) << 4);
-      *reinterpret_cast<uint4*>(kd + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-      *reinterpret_cast<uint4*>(kd + K_PLANE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      sts128(smem_u32(kd + off), hw[0], hw[1], hw[2], hw[3]);
+      sts128(smem_u32(kd + K_PLANE_BYTES + off), lw[0], lw[1], lw[2], lw[3]);
       fence_proxy_async();
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -472,8 +472,9 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
     const bool ok = q < a.L;
     const bool active = q_cta + g * TQ < a.L;
     const int64_t bh = (int64_t)b * a.nh + head;
-    float* acg = acs + g * 32 * TQ;
-    float* dacg = dacs + g * 32 * TQ;
+    // per-thread columns of the two [32][128] fp32 arrays, addressed as explicit shared memory (LDS / STS, not generic)
+    const uint32_t acg = smem_u32(acs + g * 32 * TQ) + 4u * (uint32_t)r;
+    const uint32_t dacg = smem_u32(dacs + g * 32 * TQ) + 4u * (uint32_t)r;
     float ar[32], dar[32];
     if (active) {
       uint8_t* Ag = As + (size_t)g * 2 * A_PLANE_BYTES;
@@ -498,8 +499,8 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
             split_bf16_pair(dov[8 * j + 2 * i], dov[8 * j + 2 * i + 1], hw[i], lw[i]);
           }
           const uint32_t off = (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4);
-          *reinterpret_cast<uint4*>(Ag + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint4*>(Ag + A_PLANE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          sts128(smem_u32(Ag + off), hw[0], hw[1], hw[2], hw[3]);
+          sts128(smem_u32(Ag + A_PLANE_BYTES + off), lw[0], lw[1], lw[2], lw[3]);
         }
         fence_proxy_async();
         __syncwarp();
@@ -508,8 +509,8 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
         ar[k] = (ok && k < a.W) ? __ldg(a.ar + (bh * a.W + k) * a.L + q) : 0.0f;
-        acg[k * TQ + r] = (ok && k < a.H) ? __ldg(a.ac + (bh * a.H + k) * a.L + q) : 0.0f;
-        dacg[k * TQ + r] = 0.0f;
+        sts32(acg + 4u * TQ * k, (ok && k < a.H) ? __ldg(a.ac + (bh * a.H + k) * a.L + q) : 0.0f);
+        sts32(dacg + 4u * TQ * k, 0.0f);
         dar[k] = 0.0f;
       }
       const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)g * 256u;
@@ -523,7 +524,7 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
             uint32_t t[32];
             tmem_ld_32x32b_x32(taddr_row + (uint32_t)hi * 32u, t);
             tmem_ld_wait();
-            const float cc = acg[(p * 8 + hi) * TQ + r];
+            const float cc = lds32(acg + 4u * TQ * (p * 8 + hi));
             float2 s2 = make_float2(0.0f, 0.0f);
             const float2 cc2 = make_float2(cc, cc);
 #pragma unroll
@@ -533,7 +534,7 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
               const float2 d2 = __ffma2_rn(cc2, g2, make_float2(dar[w], dar[w + 1]));
               dar[w] = d2.x; dar[w + 1] = d2.y;
             }
-            dacg[(p * 8 + hi) * TQ + r] = s2.x + s2.y;
+            sts32(dacg + 4u * TQ * (p * 8 + hi), s2.x + s2.y);
           }
           tc_fence_before();
           __syncwarp();
@@ -561,8 +562,8 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
       for (int i = 0; i < 4; ++i) split_bf16_pair(x[2 * i], x[2 * i + 1], hw[i], lw[i]);
       uint8_t* kd = Vs + (size_t)side * 4096;
       const uint32_t off = (uint32_t)k * 64u + (uint32_t)((j ^ ((k >> 1) & 3)) << 4);
-      *reinterpret_cast<uint4*>(kd + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-      *reinterpret_cast<uint4*>(kd + 2048 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      sts128(smem_u32(kd + off), hw[0], hw[1], hw[2], hw[3]);
+      sts128(smem_u32(kd + 2048 + off), lw[0], lw[1], lw[2], lw[3]);
       fence_proxy_async();
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -589,10 +590,10 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
       {   // column side while the tensor core works on the row side
         float dot = 0.0f;
 #pragma unroll
-        for (int h = 0; h < 32; ++h) dot += acg[h * TQ + r] * dacg[h * TQ + r];
+        for (int h = 0; h < 32; ++h) dot += lds32(acg + 4u * TQ * h) * lds32(dacg + 4u * TQ * h);
 #pragma unroll
         for (int h = 0; h < 32; ++h) {
-          ds[h] = acg[h * TQ + r] * (dacg[h * TQ + r] - dot);
+          ds[h] = lds32(acg + 4u * TQ * h) * (lds32(dacg + 4u * TQ * h) - dot);
           if (ok && h < a.H) a.dsc[(bh * a.H + h) * a.L + q] = ds[h];
         }
       }
@@ -797,13 +798,14 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
         const int m = mt * 128 + ml;
         const bool mok = m < HW;
         const int h = mok ? m / a.W : 0, w = mok ? m % a.W : 0;
-        const float4* cr = reinterpret_cast<const float4*>(acs + h * MAP_LD + qh * 36);
-        const float4* rr = reinterpret_cast<const float4*>(ars + w * MAP_LD + qh * 36);
-        uint8_t* Pb = Ps + (size_t)pb * 2 * P_TILE_BYTES;
+        const uint32_t cr = smem_u32(acs + h * MAP_LD + qh * 36);     // explicit LDS / STS: see lds128()
+        const uint32_t rr = smem_u32(ars + w * MAP_LD + qh * 36);
+        const uint32_t Pb = smem_u32(Ps) + (uint32_t)pb * 2u * P_TILE_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {        // 4 chunks of 8 queries
           float pv[8];
-          const float4 c0 = cr[2 * j], c1 = cr[2 * j + 1], r0 = rr[2 * j], r1 = rr[2 * j + 1];
+          const float4 c0 = lds128(cr + 32 * j), c1 = lds128(cr + 32 * j + 16);
+          const float4 r0 = lds128(rr + 32 * j), r1 = lds128(rr + 32 * j + 16);
           {
             const float2 p01 = __fmul2_rn(make_float2(c0.x, c0.y), make_float2(r0.x, r0.y));
             const float2 p23 = __fmul2_rn(make_float2(c0.z, c0.w), make_float2(r0.z, r0.w));
@@ -818,8 +820,8 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
             split_bf16_pair(mok ? pv[2 * i] : 0.0f, mok ? pv[2 * i + 1] : 0.0f, hw[i], lw[i]);
           }
           const uint32_t off = (uint32_t)ml * 128u + (uint32_t)(((qh * 4 + j) ^ (ml & 7)) << 4);
-          *reinterpret_cast<uint4*>(Pb + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint4*>(Pb + P_TILE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          sts128(Pb + off, hw[0], hw[1], hw[2], hw[3]);
+          sts128(Pb + P_TILE_BYTES + off, lw[0], lw[1], lw[2], lw[3]);
         }
         fence_proxy_async();
         __syncwarp();

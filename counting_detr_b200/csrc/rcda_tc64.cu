@@ -74,8 +74,8 @@ __device__ __forceinline__ void write_row32_sw64(uint8_t* dst, uint32_t plane_by
 #pragma unroll
     for (int i = 0; i < 4; ++i) split_bf16_pair(x[8 * j + 2 * i], x[8 * j + 2 * i + 1], hw[i], lw[i]);
     const uint32_t off = (uint32_t)r * 64u + (uint32_t)((j ^ ((r >> 1) & 3)) << 4);
-    *reinterpret_cast<uint4*>(dst + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(dst + plane_bytes + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    sts128(smem_u32(dst + off), hw[0], hw[1], hw[2], hw[3]);
+    sts128(smem_u32(dst + plane_bytes + off), lw[0], lw[1], lw[2], lw[3]);
   }
 }
 // 64 values -> split-bf16 K-major SWIZZLE_128B operand row r (128-byte rows, 16-byte chunk j at j ^ (r & 7))
@@ -86,8 +86,8 @@ __device__ __forceinline__ void write_row64_sw128(uint8_t* dst, uint32_t plane_b
 #pragma unroll
     for (int i = 0; i < 4; ++i) split_bf16_pair(x[8 * j + 2 * i], x[8 * j + 2 * i + 1], hw[i], lw[i]);
     const uint32_t off = (uint32_t)r * 128u + (uint32_t)((j ^ (r & 7)) << 4);
-    *reinterpret_cast<uint4*>(dst + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(dst + plane_bytes + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    sts128(smem_u32(dst + off), hw[0], hw[1], hw[2], hw[3]);
+    sts128(smem_u32(dst + plane_bytes + off), lw[0], lw[1], lw[2], lw[3]);
   }
 }
 // the two key tiles K_r [W,32], K_c [H,32] of this (sample, head) -> [2 sides][2 planes][64 keys][32] SWIZZLE_64B
@@ -109,8 +109,8 @@ __device__ __forceinline__ void stage_key_tiles(uint8_t* Kb, const float* kr, co
     for (int i = 0; i < 4; ++i) split_bf16_pair(x[2 * i], x[2 * i + 1], hw[i], lw[i]);
     uint8_t* kd = Kb + (size_t)side * 2 * K_PLANE;
     const uint32_t off = (uint32_t)k * 64u + (uint32_t)((j ^ ((k >> 1) & 3)) << 4);
-    *reinterpret_cast<uint4*>(kd + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(kd + K_PLANE + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    sts128(smem_u32(kd + off), hw[0], hw[1], hw[2], hw[3]);
+    sts128(smem_u32(kd + K_PLANE + off), lw[0], lw[1], lw[2], lw[3]);
   }
   fence_proxy_async();
 }
