@@ -372,6 +372,18 @@ constexpr size_t SMEM_MAX = 227 * 1024;
 
 // Host launchers used by cdetr_mha_fwd / cdetr_mha_bwd (mha.cu).  Return 1 when the head does not fit in shared
 // memory (L > ~700): the caller then falls back to the CUDA-core kernels.
+// One CTA per (sample, head) leaves SMs idle when B * heads < #SMs (C4: 64 CTAs on 148 SMs; inference at B = 1: 8):
+// the strips of 16 rows are dealt round-robin over gridDim.z CTAs, each staging the head's K / V (or Q / dO) itself.
+static int mha_query_split(const MhaArgs& a) {
+  int num_sms = 148;
+  if (cdetr_num_sms(&num_sms) != cudaSuccess) num_sms = 148;
+  const int strips = (a.L + 15) / 16;
+  int nsplit = num_sms / (a.nh * a.B > 0 ? a.nh * a.B : 1);
+  const int max_split = (strips + NWARPS - 1) / NWARPS;      // below one round of strips per CTA there is nothing to gain
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit > 4) nsplit = 4;
+  return nsplit < 1 ? 1 : nsplit;
+}
 int mha_tc_fits(int L) {
   const int Lp = (L + 15) / 16 * 16;
   return smem_bwd_kv(Lp) <= SMEM_MAX && smem_bwd_q(Lp) <= SMEM_MAX ? 1 : 0;
@@ -381,7 +393,8 @@ int mha_fwd_tc_launch(const MhaArgs& a, cudaStream_t s) {
   const size_t smem = smem_fwd(Lp);
   static DevAttrCache cfg = {};
   CDETR_CHECK_CUDA(cdetr_ensure_smem(mha_fwd_tc_kernel, (int)SMEM_MAX, &cfg));
-  mha_fwd_tc_kernel<<<dim3(a.nh, a.B, 1), NTHREADS, smem, s>>>(a, Lp);   // ~160 registers x 320 threads: one CTA per SM
+  const int nsplit = mha_query_split(a);
+  mha_fwd_tc_kernel<<<dim3(a.nh, a.B, nsplit), NTHREADS, smem, s>>>(a, Lp);   // ~160 registers x 320 threads: one CTA per SM
   CDETR_CHECK_LAUNCH();
   return 0;
 }
@@ -390,9 +403,10 @@ int mha_bwd_tc_launch(const MhaArgs& a, cudaStream_t s) {
   static DevAttrCache cfg_q = {}, cfg_kv = {};
   CDETR_CHECK_CUDA(cdetr_ensure_smem(mha_bwd_q_tc_kernel, (int)SMEM_MAX, &cfg_q));
   CDETR_CHECK_CUDA(cdetr_ensure_smem(mha_bwd_kv_tc_kernel, (int)SMEM_MAX, &cfg_kv));
-  mha_bwd_q_tc_kernel<<<dim3(a.nh, a.B, 1), NTHREADS, smem_bwd_q(Lp), s>>>(a, Lp);
+  const int nsplit = mha_query_split(a);
+  mha_bwd_q_tc_kernel<<<dim3(a.nh, a.B, nsplit), NTHREADS, smem_bwd_q(Lp), s>>>(a, Lp);
   CDETR_CHECK_LAUNCH();
-  mha_bwd_kv_tc_kernel<<<dim3(a.nh, a.B, 1), NTHREADS, smem_bwd_kv(Lp), s>>>(a, Lp);
+  mha_bwd_kv_tc_kernel<<<dim3(a.nh, a.B, nsplit), NTHREADS, smem_bwd_kv(Lp), s>>>(a, Lp);
   CDETR_CHECK_LAUNCH();
   return 0;
 }

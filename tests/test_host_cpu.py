@@ -156,3 +156,35 @@ def test_models_shim_is_the_reference_import_line():
         for k in [k for k in _sys.modules if k == "models" or k.startswith("models.")]:
             del _sys.modules[k]
         _sys.modules.update(saved)
+
+
+def test_precision_policy_parsing_and_default():
+    from counting_detr_b200.engine import Engine
+    pol = Engine._parse_policy("backbone.dgrad=1, *.wgrad=5;ffn=3")
+    assert pol == {("backbone", "dgrad"): 1, ("*", "wgrad"): 5, ("ffn", "*"): 3}
+
+    class E:
+        policy = pol
+    assert Engine.policy_mask(E, "backbone", "dgrad") == 1 and Engine.policy_mask(E, "backbone", "wgrad") == 5
+    assert Engine.policy_mask(E, "ffn", "fwd") == 3 and Engine.policy_mask(E, "attn", "fwd") == 0
+    # the adopted policy: only weight-gradient GEMMs drop the cross terms
+    assert Engine._parse_policy(Engine.DEFAULT_POLICY) == {("*", "wgrad"): 1}
+
+
+def test_buffer_cache_keeps_three_signatures():
+    """Engine._enter_signature: buffer sets of the 3 most recent input signatures stay, older ones are freed and the
+    eviction counter tells holders of captured graphs to re-capture (unbounded growth at bs=1 / varying sizes)."""
+    from counting_detr_b200.engine import Engine
+
+    class E:
+        MAX_SIGNATURES = Engine.MAX_SIGNATURES
+        _bufs, _sig_keys, _cur_sig, evictions, saved, dev = {}, {}, None, 0, {}, torch.device("cpu")
+    e = E()
+    e._bufs, e._sig_keys, e.saved = {}, {}, {}
+    for i, s in enumerate([64, 96, 128, 160, 96]):
+        Engine._enter_signature(e, ((1, 3, s, s), None))
+        Engine.buf(e, "act", (s, 8))
+        Engine.buf(e, "shared", (4,))              # same shape under every signature: must survive evictions
+    assert e.evictions == 1 and len(e._sig_keys) == 3
+    shapes = sorted(k[1][0] for k in e._bufs if k[0] == "act")
+    assert shapes == [96, 128, 160] and ("shared", (4,), torch.float32) in e._bufs
