@@ -51,6 +51,13 @@ def split_view(t):
     return SplitT(t.data_ptr(), t.stride(1), t.stride(0))
 
 
+class PackEntryT(C.Structure):
+    """cdetr_pack_entry_t"""
+    _fields_ = [("w", C.c_void_p), ("bn_w", C.c_void_p), ("bn_b", C.c_void_p), ("bn_rm", C.c_void_p), ("bn_rv", C.c_void_p),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("dst", SplitT), ("dst_t", SplitT), ("dst_d", SplitT),
+                ("cout", C.c_int32), ("cin", C.c_int32), ("taps", C.c_int32), ("pad_", C.c_int32)]
+
+
 class GemmT(C.Structure):
     """cdetr_gemm_t"""
     _fields_ = [
@@ -135,6 +142,7 @@ _SIGS = {
     "cdetr_pack_weight": "piiipSS",
     "cdetr_pack_weight_dgrad": "piiipS",
     "cdetr_unpack_conv_grad": "piiip",
+    "cdetr_mt_pack_weights": "ppiif",
     "cdetr_to_split": "plilS",
     "cdetr_from_split": "Slipl",
     "cdetr_stem_im2col": "piiiS",

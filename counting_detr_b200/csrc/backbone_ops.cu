@@ -104,6 +104,50 @@ __global__ void pack_weight_dgrad_kernel(const float* __restrict__ w, int cout, 
   }
 }
 
+// every weight of the model in one launch: block table (entry, chunk), see cdetr_mt_pack_weights in cdetr.h
+__global__ void __launch_bounds__(256)
+mt_pack_weights_kernel(const cdetr_pack_entry_t* __restrict__ table, const int32_t* __restrict__ blocks, int chunk,
+                       float eps) {
+  const int t = blocks[2 * blockIdx.x], ck = blocks[2 * blockIdx.x + 1];
+  const cdetr_pack_entry_t e = table[t];
+  const int64_t n = (int64_t)e.cout * e.cin * e.taps;
+  const int64_t begin = (int64_t)ck * chunk, end = min(n, begin + chunk);
+  const bool bn = e.bn_w != nullptr;
+  if (bn && ck == 0) {
+    for (int o = threadIdx.x; o < e.cout; o += blockDim.x) {
+      const float sc = e.bn_w[o] * rsqrtf(e.bn_rv[o] + eps);      // same expression as bn_fold_kernel
+      e.scale[o] = sc;
+      e.shift[o] = e.bn_b[o] - e.bn_rm[o] * sc;
+    }
+  }
+  __nv_bfloat16* d_hi = reinterpret_cast<__nv_bfloat16*>(e.dst.base);
+  __nv_bfloat16* t_hi = reinterpret_cast<__nv_bfloat16*>(e.dst_t.base);
+  __nv_bfloat16* g_hi = reinterpret_cast<__nv_bfloat16*>(e.dst_d.base);
+  for (int64_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    const int tp = (int)(i % e.taps);
+    const int c = (int)((i / e.taps) % e.cin);
+    const int o = (int)(i / ((int64_t)e.taps * e.cin));
+    float x = e.w[i];
+    if (bn) x *= e.bn_w[o] * rsqrtf(e.bn_rv[o] + eps);
+    __nv_bfloat16 h, l;
+    split_bf16(x, h, l);
+    const int64_t k = (int64_t)tp * e.cin + c;
+    if (d_hi) {
+      d_hi[(int64_t)o * e.dst.ld + k] = h;
+      d_hi[e.dst.plane + (int64_t)o * e.dst.ld + k] = l;
+    }
+    if (t_hi) {
+      t_hi[k * e.dst_t.ld + o] = h;
+      t_hi[e.dst_t.plane + k * e.dst_t.ld + o] = l;
+    }
+    if (g_hi) {
+      const int64_t kd = (int64_t)tp * e.cout + o;
+      g_hi[(int64_t)c * e.dst_d.ld + kd] = h;
+      g_hi[e.dst_d.plane + (int64_t)c * e.dst_d.ld + kd] = l;
+    }
+  }
+}
+
 // grad[cout, cin, taps] += g[cout, taps*cin]
 __global__ void unpack_conv_grad_kernel(const float* __restrict__ g, int cout, int cin, int taps,
                                         float* __restrict__ grad) {
@@ -358,6 +402,14 @@ extern "C" int cdetr_pack_weight_dgrad(const float* w, int cout, int cin, int ta
   CDETR_CHECK_ARG(dst.ld >= (int64_t)taps * cout, "pack_weight_dgrad: dst ld too small");
   pack_weight_dgrad_kernel<<<grid_for((int64_t)cout * cin * taps), 256, 0, STREAM(s)>>>(
       w, cout, cin, taps, row_scale, sp(dst));
+  CDETR_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cdetr_mt_pack_weights(const cdetr_pack_entry_t* table, const int32_t* blocks, int nblocks, int chunk_elems,
+                                     float eps, cdetr_stream_t s) {
+  CDETR_CHECK_ARG(table && blocks && nblocks > 0 && chunk_elems > 0, "mt_pack_weights: bad args");
+  mt_pack_weights_kernel<<<nblocks, 256, 0, STREAM(s)>>>(table, blocks, chunk_elems, eps);
   CDETR_CHECK_LAUNCH();
   return 0;
 }

@@ -51,23 +51,19 @@ class Lin:
         self.bias = None
         self.stage = None  # fp32 [n_out, taps*cin] wgrad staging for taps > 1
 
-    def pack(self):
+    def refresh_bias(self):
+        """bias the GEMM epilogue adds: the FrozenBN shift, or the layer's bias parameter (no copy: the tensor itself)."""
         p = self.eng.params
         if self.bn:
-            L.call("cdetr_bn_fold", p[self.bn + ".weight"], p[self.bn + ".bias"], p[self.bn + ".running_mean"],
-                   p[self.bn + ".running_var"], 1e-5, self.n_out, self.scale, self.shift)
             self.bias = self.shift
         elif self.bname:
             b = p[self.bname]
-            # stage-1 cls bias has shape [1] and broadcasts over the two logits (A1/models/transformer.py:84-88)
-            self.bias = b if b.numel() == self.n_out else b.expand(self.n_out).contiguous()
-        if self.implicit and self.need_t:
-            if self.wd is None:
-                self.wd = torch.zeros(2, self.cin, _r8(self.taps * self.n_out), device=self.w.device, dtype=torch.bfloat16)
-            L.call("cdetr_pack_weight", p[self.wname], self.n_out, self.cin, self.taps, self.scale, self.w, None)
-            L.call("cdetr_pack_weight_dgrad", p[self.wname], self.n_out, self.cin, self.taps, self.scale, self.wd)
-        else:
-            L.call("cdetr_pack_weight", p[self.wname], self.n_out, self.cin, self.taps, self.scale, self.w, self.wt)
+            if b.numel() == self.n_out:
+                self.bias = b
+            else:   # stage-1 cls bias has shape [1] and broadcasts over the two logits (A1/models/transformer.py:84-88)
+                if self.bias is None or self.bias.numel() != self.n_out or self.bias.data_ptr() == b.data_ptr():
+                    self.bias = torch.empty(self.n_out, device=b.device)
+                self.bias.copy_(b.expand(self.n_out))
 
     # y[M, rows] = a[M, K] @ W[rows, :]^T + bias[rows]
     def fwd(self, a, M, rows=None, **kw):
@@ -347,10 +343,44 @@ class Engine:
                 self._lin(f"{h}.{j}", f"{t}.{h}.0.layers.{j}.weight", f"{t}.{h}.0.layers.{j}.bias", group="heads")
         del self.grad_views
 
+    PACK_CHUNK = 16384      # elements per block of the multi-tensor pack
+
     def pack_weights(self):
-        """Re-pack every weight into split-bf16 (call after each optimizer step)."""
-        for l in self.lins.values():
-            l.pack()
+        """Re-pack every weight into split-bf16 (after each optimizer step): ONE launch over a (weight, chunk) block
+        table (cdetr_mt_pack_weights: FrozenBN fold + forward / dgrad / implicit-conv-dgrad layouts), instead of 125
+        cdetr_pack_weight + 53 cdetr_bn_fold launches."""
+        import ctypes as C
+        p = self.params
+        lins = list(self.lins.values())
+        key = tuple((l.implicit, p[l.wname].data_ptr()) for l in lins)
+        if getattr(self, "_pack_key", None) != key:
+            arr = (L.PackEntryT * len(lins))()
+            blocks = []
+            for i, l in enumerate(lins):
+                if l.implicit and l.need_t and l.wd is None:
+                    l.wd = torch.zeros(2, l.cin, _r8(l.taps * l.n_out), device=l.w.device, dtype=torch.bfloat16)
+                e = arr[i]
+                e.w = p[l.wname].data_ptr()
+                if l.bn:
+                    e.bn_w, e.bn_b = p[l.bn + ".weight"].data_ptr(), p[l.bn + ".bias"].data_ptr()
+                    e.bn_rm, e.bn_rv = p[l.bn + ".running_mean"].data_ptr(), p[l.bn + ".running_var"].data_ptr()
+                    e.scale, e.shift = l.scale.data_ptr(), l.shift.data_ptr()
+                e.dst = L.split_view(l.w)
+                use_d = l.implicit and l.need_t
+                e.dst_t = L.split_view(None if use_d else l.wt)
+                e.dst_d = L.split_view(l.wd if use_d else None)
+                e.cout, e.cin, e.taps = l.n_out, l.cin, l.taps
+                n = l.n_out * l.cin * l.taps
+                for c in range((n + self.PACK_CHUNK - 1) // self.PACK_CHUNK):
+                    blocks += [i, c]
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._pack_table = raw.to(self.dev)
+            self._pack_blocks = torch.tensor(blocks, dtype=torch.int32).to(self.dev)
+            self._pack_key = key
+        L.call("cdetr_mt_pack_weights", self._pack_table, self._pack_blocks, self._pack_blocks.numel() // 2,
+               self.PACK_CHUNK, 1e-5)
+        for l in lins:
+            l.refresh_bias()
         self.packed = True
 
     def zero_grad(self):

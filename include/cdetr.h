@@ -103,6 +103,22 @@ int cdetr_pack_weight(const float* w, int cout, int cin, int taps, const float* 
 /* w [cout, cin, taps] fp32 -> dst [cin, taps*cout] (row_scale[cout] folded): B operand of the implicit-conv dgrad */
 int cdetr_pack_weight_dgrad(const float* w, int cout, int cin, int taps, const float* row_scale,
                             cdetr_split_t dst, cdetr_stream_t s);
+/* All weights of the model in ONE launch (the re-pack that follows every optimizer step: 125 cdetr_pack_weight + 53
+ * cdetr_bn_fold calls otherwise).  table: device array, one entry per weight; blocks: device int32 [nblocks][2] =
+ * (entry, chunk): a block converts elements [chunk*chunk_elems, +chunk_elems) of its entry.  Per entry: the FrozenBN fold
+ * (scale = bn_w * rsqrt(bn_rv + eps), shift = bn_b - bn_rm * scale; written by the entry's first block) and any of the
+ * three packed layouts cdetr_pack_weight / cdetr_pack_weight_dgrad produce (NULL base = not wanted). */
+typedef struct {
+  const float* w;                                  /* [cout, cin, taps] fp32 master weight */
+  const float *bn_w, *bn_b, *bn_rm, *bn_rv;        /* FrozenBatchNorm buffers or NULL */
+  float *scale, *shift;                            /* fold outputs [cout] (with bn_w) */
+  cdetr_split_t dst;                               /* [cout, taps*cin]   forward operand */
+  cdetr_split_t dst_t;                             /* [taps*cin, cout]   dgrad operand */
+  cdetr_split_t dst_d;                             /* [cin, taps*cout]   implicit-conv dgrad operand */
+  int32_t cout, cin, taps, pad_;
+} cdetr_pack_entry_t;
+int cdetr_mt_pack_weights(const cdetr_pack_entry_t* table, const int32_t* blocks, int nblocks, int chunk_elems, float eps,
+                          cdetr_stream_t s);
 /* grad [cout, cin, taps] += g [cout, taps*cin] */
 int cdetr_unpack_conv_grad(const float* g, int cout, int cin, int taps, float* grad, cdetr_stream_t s);
 int cdetr_to_split(const float* x, int64_t rows, int cols, int64_t ld_x, cdetr_split_t dst, cdetr_stream_t s);
