@@ -334,12 +334,29 @@ def run_ours(args):
     # ---- (2) e2e: the same step through the public API from pinned HOST batches: counting_detr_b200.data.DevicePrefetcher
     # (H2D of batch i+1 on a copy stream under the compute of batch i) -> CapturedStep -> loss.item() EVERY step (the
     # reference's loop reads the loss each iteration, A2/engine.py:44); all of it inside the timed region
-    def e2e_run(stepper, n):
+    loss_pin = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_run(stepper, n, lagged=False):
+        """lagged=False: loss.item() right after every step (the reference's loop, A2/engine.py:44).  lagged=True: the loss
+        of step i leaves through an async copy into pinned memory and is read while step i+1 runs (still one read per
+        step, the last one inside the timed region): the host never leaves the device idle."""
         pf = DevicePrefetcher((host[i & 1] for i in range(n)), dev)
         last = None
-        for b in pf:
+        for k, b in enumerate(pf):
             _, total = call(stepper, b)
-            last = total.item()
+            if not lagged:
+                last = total.item()
+                continue
+            slot = k & 1
+            loss_pin[slot].copy_(total, non_blocking=True)
+            loss_ev[slot].record()
+            if k >= 1:
+                loss_ev[slot ^ 1].synchronize()
+                last = float(loss_pin[slot ^ 1])
+        if lagged and n >= 1:
+            loss_ev[(n - 1) & 1].synchronize()
+            last = float(loss_pin[(n - 1) & 1])
         return last, pf.h2d_bytes
 
     e2e_run(step_fb, 3)
@@ -354,9 +371,22 @@ def run_ours(args):
         t = torch.tensor([ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t)
+    e2e_run(step_fb, 2, lagged=True)
+    barrier()
+    e0.record()
+    e2e_run(step_fb, steps, lagged=True)
+    e1.record()
+    barrier()
+    ms_e2e_lag = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms_e2e_lag], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e_lag = float(t)
     e2e = {"value": B * world / ms_e2e * 1e3, "unit": "images/s", "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": int(h2d_total // steps), "d2h_bytes_per_step": 4,
-           "path": "DevicePrefetcher(pinned host batches) -> CapturedStep(model, criterion) -> loss.item() every step"}
+           "path": "DevicePrefetcher(pinned host batches) -> CapturedStep(model, criterion) -> loss.item() every step",
+           "value_async_loss_read": B * world / ms_e2e_lag * 1e3,
+           "async_note": "same path, but the loss of step i is read (from pinned memory) while step i+1 runs"}
 
     # ---- (3) the whole iteration of the reference's loop: + clip_grad_norm_(0.1) + AdamW (fused) + weight re-pack
     full = None

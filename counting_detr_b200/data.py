@@ -33,18 +33,61 @@ def normalize_u8(images_u8, mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
 
 
 class DevicePrefetcher:
-    def __init__(self, iterable, device, depth=2):
+    """see the module docstring.  Small host tensors of a batch (boxes, labels, rects, sizes ...: everything below
+    `pack_below` bytes) are packed into ONE pinned staging buffer and cross PCIe as one copy; the device tensors handed
+    out are 256-byte-aligned views of one device buffer.  Large tensors (the image batch) are copied on their own,
+    straight from the caller's pinned memory when it is pinned."""
+
+    def __init__(self, iterable, device, depth=2, pack_below=1 << 16):
         self.it = iterable
         self.dev = torch.device(device)
         self.depth = max(int(depth), 2)
+        self.pack_below = int(pack_below)
         self.stream = torch.cuda.Stream(device=self.dev)
-        self._slots = [dict(pin={}, dev={}, ready=torch.cuda.Event(), free=None) for _ in range(self.depth)]
+        self._slots = [dict(pin={}, dev={}, ready=torch.cuda.Event(), free=None, pack_pin=None, pack_dev=None)
+                       for _ in range(self.depth)]
         self.h2d_bytes = 0
+        self.h2d_copies = 0
 
-    def _stage(self, obj, slot, path):
+    # ---- pass 1: collect the small leaves; pass 2: rebuild the structure with device tensors
+    def _collect(self, obj, small):
+        if isinstance(obj, torch.Tensor):
+            if obj.device.type != "cuda" and obj.numel() * obj.element_size() < self.pack_below:
+                small.append(obj)
+        elif isinstance(obj, dict):
+            for v in obj.values():
+                self._collect(v, small)
+        elif isinstance(obj, (list, tuple)):
+            for v in obj:
+                self._collect(v, small)
+
+    def _stage_small(self, small, slot):
+        offs, total = [], 0
+        for t in small:
+            offs.append(total)
+            total += (t.numel() * t.element_size() + 255) // 256 * 256
+        if total == 0:
+            return {}
+        if slot["pack_pin"] is None or slot["pack_pin"].numel() < total:
+            slot["pack_pin"] = torch.empty(total, dtype=torch.uint8).pin_memory()
+            slot["pack_dev"] = torch.empty(total, dtype=torch.uint8, device=self.dev)
+        pin, dev = slot["pack_pin"], slot["pack_dev"]
+        out = {}
+        for t, o in zip(small, offs):
+            nb = t.numel() * t.element_size()
+            pin[o:o + nb].view(t.dtype).view(t.shape).copy_(t.contiguous())          # host memcpy, a few hundred bytes
+            out[id(t)] = dev[o:o + nb].view(t.dtype).view(t.shape)
+        dev[:total].copy_(pin[:total], non_blocking=True)
+        self.h2d_bytes += sum(t.numel() * t.element_size() for t in small)
+        self.h2d_copies += 1
+        return out
+
+    def _stage(self, obj, slot, path, packed):
         if isinstance(obj, torch.Tensor):
             if obj.device.type == "cuda":
                 return obj
+            if id(obj) in packed:
+                return packed[id(obj)]
             key = (path, tuple(obj.shape), obj.dtype)
             d = slot["dev"].get(key)
             if d is None:
@@ -58,11 +101,12 @@ class DevicePrefetcher:
                 src = p
             d.copy_(src, non_blocking=True)
             self.h2d_bytes += obj.numel() * obj.element_size()
+            self.h2d_copies += 1
             return d
         if isinstance(obj, dict):
-            return {k: self._stage(v, slot, path + (k,)) for k, v in obj.items()}
+            return {k: self._stage(v, slot, path + (k,), packed) for k, v in obj.items()}
         if isinstance(obj, (list, tuple)):
-            return type(obj)(self._stage(v, slot, path + (i,)) for i, v in enumerate(obj))
+            return type(obj)(self._stage(v, slot, path + (i,), packed) for i, v in enumerate(obj))
         return obj
 
     def _issue(self, batch, i):
@@ -71,8 +115,11 @@ class DevicePrefetcher:
             slot["ready"].synchronize()              # this slot's previous H2D has left its pinned staging buffers
         if slot["free"] is not None:
             self.stream.wait_event(slot["free"])     # the step that used this slot's tensors has been enqueued & done
+        small = []
+        self._collect(batch, small)
         with torch.cuda.stream(self.stream):
-            out = self._stage(batch, slot, ())
+            packed = self._stage_small(small, slot)
+            out = self._stage(batch, slot, (), packed)
             slot["ready"].record(self.stream)
         return out, slot
 

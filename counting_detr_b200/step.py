@@ -97,8 +97,12 @@ class CapturedStep:
             for k, v in targets.items():
                 st["targets"][k].copy_(v, non_blocking=True)
         else:
-            for s, t in zip(st["targets"], targets):
-                s["boxes"].copy_(t["boxes"], non_blocking=True)
+            src = [t["boxes"] for t in targets]
+            if all(x.is_cuda and x.dtype == torch.float32 for x in src):
+                torch._foreach_copy_([s["boxes"] for s in st["targets"]], src)      # one multi-tensor launch
+            else:
+                for s, t in zip(st["targets"], targets):
+                    s["boxes"].copy_(t["boxes"], non_blocking=True)
         if isinstance(points, torch.Tensor):
             st["points"].copy_(points, non_blocking=True)
 
