@@ -341,11 +341,12 @@ def run_ours(args):
         """lagged=False: loss.item() right after every step (the reference's loop, A2/engine.py:44).  lagged=True: the loss
         of step i leaves through an async copy into pinned memory and is read while step i+1 runs (still one read per
         step, the last one inside the timed region): the host never leaves the device idle."""
-        pf = DevicePrefetcher((host[i & 1] for i in range(n)), dev)
+        pf = DevicePrefetcher((host[i & 1] for i in range(n)), dev, defer=not lagged)
         last = None
         for k, b in enumerate(pf):
             _, total = call(stepper, b)
             if not lagged:
+                pf.kick()            # next batch's H2D is issued after this step's launch, before the blocking read
                 last = total.item()
                 continue
             slot = k & 1

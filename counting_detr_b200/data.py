@@ -38,11 +38,13 @@ class DevicePrefetcher:
     out are 256-byte-aligned views of one device buffer.  Large tensors (the image batch) are copied on their own,
     straight from the caller's pinned memory when it is pinned."""
 
-    def __init__(self, iterable, device, depth=2, pack_below=1 << 16):
+    def __init__(self, iterable, device, depth=2, pack_below=1 << 16, defer=False):
         self.it = iterable
         self.dev = torch.device(device)
         self.depth = max(int(depth), 2)
         self.pack_below = int(pack_below)
+        self.defer = bool(defer)      # True: the caller issues the next batch itself with kick() (see there)
+        self._it, self._i, self._pending = None, 0, None
         self.stream = torch.cuda.Stream(device=self.dev)
         self._slots = [dict(pin={}, dev={}, ready=torch.cuda.Event(), free=None, pack_pin=None, pack_dev=None)
                        for _ in range(self.depth)]
@@ -123,22 +125,34 @@ class DevicePrefetcher:
             slot["ready"].record(self.stream)
         return out, slot
 
-    def __iter__(self):
-        it = iter(self.it)
-        i = 0
-        try:
-            nxt = self._issue(next(it), i)
-        except StopIteration:
-            return
-        while nxt is not None:
-            cur, slot = nxt
-            i += 1
+    def kick(self):
+        """Issue the next batch's copies NOW.  A loop that reads a result synchronously every step (the reference reads
+        the loss) should call this right after launching its step: the copies then overlap the step instead of sitting,
+        together with their host-side set-up, between the read and the next launch.  Without kick() the next batch is
+        issued just before the current one is handed out (always overlapped, but on the host's critical path)."""
+        if self._pending is None and self._it is not None:
             try:
-                nxt = self._issue(next(it), i)       # next batch travels while the caller computes on this one
+                self._pending = self._issue(next(self._it), self._i)
+                self._i += 1
             except StopIteration:
-                nxt = None
+                self._it = None
+
+    def __iter__(self):
+        self._it = iter(self.it)
+        self._i = 0
+        self._pending = None
+        self.kick()
+        first = True
+        while self._pending is not None:
+            cur, slot = self._pending
+            self._pending = None
+            if not self.defer or first:
+                self.kick()                          # next batch travels while the caller computes on this one
+            first = False
             torch.cuda.current_stream(self.dev).wait_event(slot["ready"])
             yield cur
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.dev))   # everything the caller enqueued on this batch
             slot["free"] = ev
+            if self._pending is None:
+                self.kick()                          # deferred mode and the caller did not kick: issue now
