@@ -168,6 +168,15 @@ class Engine:
         import os
         self.policy = self._parse_policy(os.environ.get("CDETR_GEMM_POLICY", self.DEFAULT_POLICY))
         self._build_lins(train_backbone)
+        # decoder memory-side projections, hoisted out of the layer loop (they depend on the encoder memory only):
+        # value rows of all layers as ONE forward operand [D*E, E] and the value / key-row / key-column rows of all layers
+        # as dgrad operands [E, D*E] (one GEMM over K = D*E replaces D dependent GEMMs + D accumulations)
+        D, E_ = cfg.dec_layers, cfg.hidden_dim
+        bf = torch.bfloat16
+        self.dec_wv = torch.zeros(2, D * E_, E_, device=device, dtype=bf)
+        self.dec_bv = torch.zeros(D * E_, device=device)
+        self.dec_wt = {k: torch.zeros(2, E_, D * E_, device=device, dtype=bf) for k in ("kr", "kc", "v")}
+        self.hoist_dec = not os.environ.get("CDETR_NO_DEC_HOIST")
         stage_sizes = [(l, l.n_out * l.k) for l in self.lins.values() if l.trainable and l.taps > 1]
         total = sum(_r8(s) for s in sizes) + sum(_r8(s) for _, s in stage_sizes)
         self.grad_flat = torch.zeros(total, device=device)
@@ -245,6 +254,32 @@ class Engine:
         for st in used:
             ev = torch.cuda.Event()
             ev.record(st)
+            main.wait_event(ev)
+
+    def fork(self, fns):
+        """Start independent launch sequences on the auxiliary streams (forked from 'now') WITHOUT waiting for them;
+        returns the events join() waits on.  Inside a captured graph this is a branch that rejoins later."""
+        if not self.aux_streams:
+            for fn in fns:
+                fn()
+            return []
+        main = torch.cuda.current_stream()
+        ev0 = torch.cuda.Event()
+        ev0.record(main)
+        evs = []
+        for i, fn in enumerate(fns):
+            st = self.aux_streams[i % len(self.aux_streams)]
+            st.wait_event(ev0)
+            with torch.cuda.stream(st):
+                fn()
+            ev = torch.cuda.Event()
+            ev.record(st)
+            evs.append(ev)
+        return evs
+
+    def join(self, evs):
+        main = torch.cuda.current_stream()
+        for ev in evs:
             main.wait_event(ev)
 
     def join_side_stream(self):
@@ -373,7 +408,22 @@ class Engine:
                 n = l.n_out * l.cin * l.taps
                 for c in range((n + self.PACK_CHUNK - 1) // self.PACK_CHUNK):
                     blocks += [i, c]
-            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            # hoisted decoder operands: row blocks of each layer's cross_attn.in_proj_weight (order q_row, q_col, k_row, k_col, v)
+            E_, D = self.E, self.cfg.dec_layers
+            extra = (L.PackEntryT * (3 * D))()
+            for i in range(D):
+                wp = p[f"transformer.decoder_layers.{i}.cross_attn.in_proj_weight"]
+                for j, (name, blk) in enumerate((("kr", 2), ("kc", 3), ("v", 4))):
+                    e = extra[3 * i + j]
+                    e.w = wp.data_ptr() + blk * E_ * E_ * 4
+                    e.dst = L.split_view(self.dec_wv[:, i * E_:(i + 1) * E_] if name == "v" else None)
+                    e.dst_t = L.split_view(self.dec_wt[name][:, :, i * E_:(i + 1) * E_])
+                    e.dst_d = L.split_view(None)
+                    e.cout, e.cin, e.taps = E_, E_, 1
+                    base = len(lins) + 3 * i + j
+                    for c in range((E_ * E_ + self.PACK_CHUNK - 1) // self.PACK_CHUNK):
+                        blocks += [base, c]
+            raw = torch.frombuffer(bytearray(bytes(arr) + bytes(extra)), dtype=torch.uint8)
             self._pack_table = raw.to(self.dev)
             self._pack_blocks = torch.tensor(blocks, dtype=torch.int32).to(self.dev)
             self._pack_key = key
@@ -381,6 +431,10 @@ class Engine:
                self.PACK_CHUNK, 1e-5)
         for l in lins:
             l.refresh_bias()
+        E_ = self.E
+        if self.cfg.dec_layers:
+            torch.cat([p[f"transformer.decoder_layers.{i}.cross_attn.in_proj_bias"][4 * E_:]
+                       for i in range(self.cfg.dec_layers)], out=self.dec_bv)
         self.packed = True
 
     def zero_grad(self):
@@ -568,24 +622,30 @@ class Engine:
         self.lins[q + ".l1"].dgrad(dh, M, out_f32=dx, add_f32=dz)
         return dx
 
-    def _rcda_fwd(self, q, lin_in, lin_out, B, Lq, H, W, qr_in, qc_in, kr_in, kc_in, v_in, masks):
+    def _rcda_fwd(self, q, lin_in, lin_out, B, Lq, H, W, qr_in, qc_in, kr_in, kc_in, v_in, masks, pre=None):
+        """pre = dict(kr, kc, v_s): memory-side projections already computed (decoder hoist); only q_row / q_col remain."""
         E = self.E
         M, N = B * Lq, B * H * W
         qr = self.buf(q + ".qr", (M, E)); qc = self.buf(q + ".qc", (M, E))
-        kr = self.buf(q + ".kr", (B * W, E)); kc = self.buf(q + ".kc", (B * H, E))
-        v = self.buf(q + ".v", (N, E))
         lin = self.lins[lin_in]
         # tcgen05 kernels up to 64 x 64 (V resident <= 32 x 32, streamed above); beyond that the CUDA-core kernels
         use_tc = H <= 64 and W <= 64 and not self.rcda_legacy
-        v_s = self.sbuf(q + ".v_s", N, E) if use_tc else None
+        if pre is not None:
+            kr, kc, v, v_s = pre["kr"], pre["kc"], None, pre["v_s"]
+            self.fork_join([lambda: lin.fwd(qr_in, M, rows=(0, E), out_f32=qr),
+                            lambda: lin.fwd(qc_in, M, rows=(E, 2 * E), out_f32=qc)])
+        else:
+            kr = self.buf(q + ".kr", (B * W, E)); kc = self.buf(q + ".kc", (B * H, E))
+            v = self.buf(q + ".v", (N, E))
+            v_s = self.sbuf(q + ".v_s", N, E) if use_tc else None
 
-        def small():
-            lin.fwd(kr_in, B * W, rows=(2 * E, 3 * E), out_f32=kr)
-            lin.fwd(kc_in, B * H, rows=(3 * E, 4 * E), out_f32=kc)
-            lin.fwd(qc_in, M, rows=(E, 2 * E), out_f32=qc)
+            def small():
+                lin.fwd(kr_in, B * W, rows=(2 * E, 3 * E), out_f32=kr)
+                lin.fwd(kc_in, B * H, rows=(3 * E, 4 * E), out_f32=kc)
+                lin.fwd(qc_in, M, rows=(E, 2 * E), out_f32=qc)
 
-        self.fork_join([lambda: lin.fwd(qr_in, M, rows=(0, E), out_f32=qr), small,
-                        lambda: lin.fwd(v_in, N, rows=(4 * E, 5 * E), out_f32=v, out_split=v_s)])
+            self.fork_join([lambda: lin.fwd(qr_in, M, rows=(0, E), out_f32=qr), small,
+                            lambda: lin.fwd(v_in, N, rows=(4 * E, 5 * E), out_f32=v, out_split=v_s)])
         ar = self.buf(q + ".ar", (B, self.nh, W, Lq)); ac = self.buf(q + ".ac", (B, self.nh, H, Lq))
         o = self.sbuf(q + ".o", M, E)
         if use_tc:
@@ -598,9 +658,11 @@ class Engine:
                                        kr_in=kr_in, kc_in=kc_in, v_in=v_in, B=B, L=Lq, H=H, W=W)
         return attn
 
-    def _rcda_bwd(self, q, lin_in, lin_out, dattn_s, dv_add=None):
+    def _rcda_bwd(self, q, lin_in, lin_out, dattn_s, dv_add=None, hoist=None):
         """dattn_s: split grad of the attention output. Returns fp32 grads (dqr_in, dqc_in, dkr_in, dkc_in, dv_in);
-        dv_in has dv_add (fp32, e.g. the residual stream) accumulated into it when given."""
+        dv_in has dv_add (fp32, e.g. the residual stream) accumulated into it when given.
+        hoist = dict(dv, dkr, dkc): column slices of the decoder-wide [rows, D*E] gradient tensors; the memory-side input
+        gradients are then produced after the layer loop by one GEMM each (None is returned for them here)."""
         t = self.saved[q + ".rcda"]
         E, B, Lq, H, W = self.E, t["B"], t["L"], t["H"], t["W"]
         M, N = B * Lq, B * H * W
@@ -610,15 +672,20 @@ class Engine:
         self.lins[lin_out].dgrad(dattn_s, M, out_f32=dO, out_split=dO_s)
         dsr = self.buf(q + ".dsr", (B, self.nh, W, Lq)); dsc = self.buf(q + ".dsc", (B, self.nh, H, Lq))
         dqr = self.sbuf(q + ".dqr", M, E); dqc = self.sbuf(q + ".dqc", M, E)
-        dkr = self.sbuf(q + ".dkr", B * W, E); dkc = self.sbuf(q + ".dkc", B * H, E); dv = self.sbuf(q + ".dv", N, E)
         lin = self.lins[lin_in]
         g_qr = self.buf(q + ".g_qr", (M, E)); g_qc = self.buf(q + ".g_qc", (M, E))
-        g_kr = self.buf(q + ".g_kr", (B * W, E)); g_kc = self.buf(q + ".g_kc", (B * H, E))
-        g_v = self.buf(q + ".g_v", (N, E))
+        if hoist is not None:
+            dkr, dkc, dv = hoist["dkr"], hoist["dkc"], hoist["dv"]
+            g_kr = g_kc = g_v = None
+        else:
+            dkr = self.sbuf(q + ".dkr", B * W, E); dkc = self.sbuf(q + ".dkc", B * H, E); dv = self.sbuf(q + ".dv", N, E)
+            g_kr = self.buf(q + ".g_kr", (B * W, E)); g_kc = self.buf(q + ".g_kc", (B * H, E))
+            g_v = self.buf(q + ".g_v", (N, E))
 
         def v_dgrad():
             lin.wgrad(dv, t["v_in"], N, rows=(4 * E, 5 * E))
-            lin.dgrad(dv, N, rows=(4 * E, 5 * E), out_f32=g_v, add_f32=dv_add)
+            if hoist is None:
+                lin.dgrad(dv, N, rows=(4 * E, 5 * E), out_f32=g_v, add_f32=dv_add)
 
         def qk_dgrads():
             lin.wgrad(dqr, t["qr_in"], M, rows=(0, E))
@@ -627,8 +694,9 @@ class Engine:
             lin.wgrad(dkc, t["kc_in"], B * H, rows=(3 * E, 4 * E))
             lin.dgrad(dqr, M, rows=(0, E), out_f32=g_qr)
             lin.dgrad(dqc, M, rows=(E, 2 * E), out_f32=g_qc)
-            lin.dgrad(dkr, B * W, rows=(2 * E, 3 * E), out_f32=g_kr)
-            lin.dgrad(dkc, B * H, rows=(3 * E, 4 * E), out_f32=g_kc)
+            if hoist is None:
+                lin.dgrad(dkr, B * W, rows=(2 * E, 3 * E), out_f32=g_kr)
+                lin.dgrad(dkc, B * H, rows=(3 * E, 4 * E), out_f32=g_kc)
 
         if t["v_s"] is not None:
             # tcgen05 kernels.  The value side (dV, then the v-projection dgrad) only needs dO and the saved maps, so
@@ -645,6 +713,7 @@ class Engine:
 
             self.fork_join([query_key_side, value_side])
         else:
+            assert hoist is None
             L.call("cdetr_rcda_bwd", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], t["kr"], t["kc"], t["v"], t["ar"],
                    t["ac"], dO, dsr, dsc, dqr, dqc, dkr, dkc, dv)
             self.fork_join([qk_dgrads, v_dgrad])
@@ -767,6 +836,31 @@ class Engine:
         tgt_s = self.sbuf("tgt0_s", MQ, E)
         L.call("cdetr_to_split", tgt, MQ, E, E, tgt_s)
         outs = []
+        # memory-side projections of all decoder layers up front (they depend on the encoder output only): the value
+        # rows of the six cross-attention blocks as ONE GEMM (N = D*E), the twelve small key projections beside it on the
+        # auxiliary streams, all of it under the first layer's self-attention instead of on every layer's critical path
+        D = cfg.dec_layers
+        hoist = self.hoist_dec and D > 0 and H <= 64 and W <= 64 and not self.rcda_legacy
+        pre, hoist_join = [None] * D, None
+        if hoist:
+            pm = self.policy_mask("attn", "fwd")
+            v_all = self.sbuf("dec.v_all", M, D * E)
+            for i in range(D):
+                q = f"transformer.decoder_layers.{i}"
+                pre[i] = dict(kr=self.buf(q + ".kr", (B * W, E)), kc=self.buf(q + ".kc", (B * H, E)),
+                              v_s=v_all[:, :, i * E:(i + 1) * E])
+
+            def v_proj():
+                L.gemm(mem_s, self.dec_wv, M, D * E, E, mode=0, bias=self.dec_bv, out_split=v_all, pass_mask=pm)
+
+            def k_proj():
+                for i in range(D):
+                    lin = self.lins[f"transformer.decoder_layers.{i}.ca_in"]
+                    lin.fwd(krin_d, B * W, rows=(2 * E, 3 * E), out_f32=pre[i]["kr"])
+                    lin.fwd(kcin_d, B * H, rows=(3 * E, 4 * E), out_f32=pre[i]["kc"])
+
+            hoist_join = self.fork([v_proj, k_proj])
+        sv["dec_hoist"] = hoist
         for i in range(cfg.dec_layers):
             q = f"transformer.decoder_layers.{i}"
             qk = self.sbuf(q + ".qk", MQ, E)
@@ -784,7 +878,11 @@ class Engine:
             qr_in = self.sbuf(q + ".qr_in", MQ, E); qc_in = self.sbuf(q + ".qc_in", MQ, E)
             L.call("cdetr_add_bcast", t1, qx, MQ, E, 3, 1, 1, Q, None, qr_in)
             L.call("cdetr_add_bcast", t1, qy, MQ, E, 3, 1, 1, Q, None, qc_in)
-            ca = self._rcda_fwd(q, q + ".ca_in", q + ".ca_out", B, Q, H, W, qr_in, qc_in, krin_d, kcin_d, mem_s, masks)
+            if hoist_join is not None:
+                self.join(hoist_join)
+                hoist_join = None
+            ca = self._rcda_fwd(q, q + ".ca_in", q + ".ca_out", B, Q, H, W, qr_in, qc_in, krin_d, kcin_d, mem_s, masks,
+                                pre=pre[i])
             t2, t2s = self._ln_fwd(ca, t1, MQ, q + ".norm1", q + ".ln1")
             tgt, tgt_s = self._ffn_fwd(t2, t2s, MQ, q)
             if cfg.aux_loss or i == cfg.dec_layers - 1:
@@ -888,6 +986,13 @@ class Engine:
         g_krd = self.buf("dec.g_kr_acc", (B * W, E), zero=True); g_kcd = self.buf("dec.g_kc_acc", (B * H, E), zero=True)
         dqpos = self.buf("dqpos", (Q, E), zero=True); dqx = self.buf("dqx", (Q, E), zero=True); dqy = self.buf("dqy", (Q, E), zero=True)
         dtgt = self.buf("dtgt", (MQ, E)); have_dtgt = False
+        # hoisted decoder (see forward): every layer writes its dV / dK_r / dK_c into a column slice of decoder-wide tensors;
+        # the memory-side input gradients are three GEMMs over K = D*E after the loop instead of 3*D GEMMs + accumulations
+        hoisted = bool(sv.get("dec_hoist"))
+        D = cfg.dec_layers
+        if hoisted:
+            dv_all = self.sbuf("dec.dv_all", M, D * E)
+            dkr_all = self.sbuf("dec.dkr_all", B * W, D * E); dkc_all = self.sbuf("dec.dkc_all", B * H, D * E)
         # ---- decoder, last layer first
         for i in reversed(range(cfg.dec_layers)):
             q = f"transformer.decoder_layers.{i}"
@@ -902,13 +1007,18 @@ class Engine:
                 dy, dy2 = dtgt, None
             d2 = self._ffn_bwd(dy, dy2, q)                       # grad wrt t2 (post norm1)
             dz1, dz1s = self._ln_bwd(d2, None, q + ".ln1")       # -> ca (split) and t1 residual (fp32)
-            g_qr, g_qc, g_kr, g_kc, g_v = self._rcda_bwd(q, q + ".ca_in", q + ".ca_out", dz1s,
-                                                        dv_add=dmem if dmem_written else None)
-            # value input is the memory: accumulate over decoder layers
-            dmem = g_v              # this layer's buffer now holds the sum over the layers processed so far
-            dmem_written = True
-            L.call("cdetr_add_bcast", g_krd, g_kr, B * W, E, 0, 1, 1, 0, g_krd, None)
-            L.call("cdetr_add_bcast", g_kcd, g_kc, B * H, E, 0, 1, 1, 0, g_kcd, None)
+            if hoisted:
+                sl = slice(i * E, (i + 1) * E)
+                g_qr, g_qc, _, _, _ = self._rcda_bwd(q, q + ".ca_in", q + ".ca_out", dz1s,
+                                                     hoist=dict(dv=dv_all[:, :, sl], dkr=dkr_all[:, :, sl], dkc=dkc_all[:, :, sl]))
+            else:
+                g_qr, g_qc, g_kr, g_kc, g_v = self._rcda_bwd(q, q + ".ca_in", q + ".ca_out", dz1s,
+                                                            dv_add=dmem if dmem_written else None)
+                # value input is the memory: accumulate over decoder layers
+                dmem = g_v              # this layer's buffer now holds the sum over the layers processed so far
+                dmem_written = True
+                L.call("cdetr_add_bcast", g_krd, g_kr, B * W, E, 0, 1, 1, 0, g_krd, None)
+                L.call("cdetr_add_bcast", g_kcd, g_kc, B * H, E, 0, 1, 1, 0, g_kcd, None)
             # queries: q_row_in = t1 + qx, q_col_in = t1 + qy
             L.call("cdetr_reduce_axis", g_qr, 1, B, Q, E, 1, 1.0, None, 1, dqx, None)
             L.call("cdetr_reduce_axis", g_qc, 1, B, Q, E, 1, 1.0, None, 1, dqy, None)
@@ -935,6 +1045,15 @@ class Engine:
             lin.dgrad(dv_, MQ, rows=(2 * E, 3 * E), out_f32=g_t, add_f32=g_qk)
             L.call("cdetr_combine_bcast", dz2, g_t, None, None, 0.0, None, 0.0, MQ, E, 1, 1, dtgt)
             have_dtgt = True
+        if hoisted:
+            pm = self.policy_mask("attn", "dgrad")
+            dmem = self.buf("dec.dmem", (M, E))
+
+            def kgrads():
+                L.gemm(dkr_all, self.dec_wt["kr"], B * W, E, D * E, mode=0, out_f32=g_krd, pass_mask=pm)
+                L.gemm(dkc_all, self.dec_wt["kc"], B * H, E, D * E, mode=0, out_f32=g_kcd, pass_mask=pm)
+
+            self.fork_join([lambda: L.gemm(dv_all, self.dec_wt["v"], M, E, D * E, mode=0, out_f32=dmem, pass_mask=pm), kgrads])
         # ---- pattern embedding: tgt0[b, p*Qp + j] = pattern[p]
         gpat = self.grad_views[self._pattern_key()]
         dpat = self.buf("dpattern_tmp", (B * P, E))       # sum over the Qp queries of each (sample, pattern), then over b
