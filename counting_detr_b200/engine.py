@@ -199,7 +199,8 @@ class Engine:
         if os.environ.get("CDETR_NO_SIDE"):      # debugging / A-B measurements
             self.side_stream = None
         self.rcda_legacy = bool(int(os.environ.get("CDETR_RCDA_LEGACY", "0")))   # A/B + tests of the CUDA-core RCDA
-        self.aux_streams = [torch.cuda.Stream(device=device, priority=-1) for _ in range(2)] if device.type == "cuda" else []
+        self.aux_streams = [torch.cuda.Stream(device=device, priority=-1) for _ in range(4)] if device.type == "cuda" else []
+        self._aux_rr = 0        # round-robin start: nested / consecutive forks land on different streams
 
     # Precision policy: "<group>.<kind>=<mask>" entries, group in {backbone, proj, attn, ffn, pos,
     # heads, *}, kind in {fwd, dgrad, wgrad, *}, mask = cdetr_gemm_t.pass_mask (7 all three products, 5 second operand
@@ -241,11 +242,17 @@ class Engine:
         ev0 = torch.cuda.Event()
         ev0.record(main)
         used = []
+        n = len(self.aux_streams)
+        base = self._aux_rr
+        self._aux_rr = (self._aux_rr + len(fns) - 1) % n
         for i, fn in enumerate(fns):
             if i == 0:
                 fn()
                 continue
-            st = self.aux_streams[(i - 1) % len(self.aux_streams)]
+            st = self.aux_streams[(base + i - 1) % n]
+            if st.cuda_stream == main.cuda_stream:   # a nested fork wrapped around to the stream it runs on: stay in order
+                fn()
+                continue
             if st not in used:
                 st.wait_event(ev0)
                 used.append(st)
@@ -267,8 +274,11 @@ class Engine:
         ev0 = torch.cuda.Event()
         ev0.record(main)
         evs = []
+        n = len(self.aux_streams)
+        base = self._aux_rr
+        self._aux_rr = (self._aux_rr + len(fns)) % n
         for i, fn in enumerate(fns):
-            st = self.aux_streams[i % len(self.aux_streams)]
+            st = self.aux_streams[(base + i) % n]
             st.wait_event(ev0)
             with torch.cuda.stream(st):
                 fn()
@@ -639,12 +649,12 @@ class Engine:
             v = self.buf(q + ".v", (N, E))
             v_s = self.sbuf(q + ".v_s", N, E) if use_tc else None
 
-            def small():
+            def keys():
                 lin.fwd(kr_in, B * W, rows=(2 * E, 3 * E), out_f32=kr)
                 lin.fwd(kc_in, B * H, rows=(3 * E, 4 * E), out_f32=kc)
-                lin.fwd(qc_in, M, rows=(E, 2 * E), out_f32=qc)
 
-            self.fork_join([lambda: lin.fwd(qr_in, M, rows=(0, E), out_f32=qr), small,
+            self.fork_join([lambda: lin.fwd(qr_in, M, rows=(0, E), out_f32=qr),
+                            lambda: lin.fwd(qc_in, M, rows=(E, 2 * E), out_f32=qc), keys,
                             lambda: lin.fwd(v_in, N, rows=(4 * E, 5 * E), out_f32=v, out_split=v_s)])
         ar = self.buf(q + ".ar", (B, self.nh, W, Lq)); ac = self.buf(q + ".ac", (B, self.nh, H, Lq))
         o = self.sbuf(q + ".o", M, E)
@@ -687,16 +697,23 @@ class Engine:
             if hoist is None:
                 lin.dgrad(dv, N, rows=(4 * E, 5 * E), out_f32=g_v, add_f32=dv_add)
 
-        def qk_dgrads():
+        def qr_side():
             lin.wgrad(dqr, t["qr_in"], M, rows=(0, E))
+            lin.dgrad(dqr, M, rows=(0, E), out_f32=g_qr)
+
+        def qc_side():
             lin.wgrad(dqc, t["qc_in"], M, rows=(E, 2 * E))
+            lin.dgrad(dqc, M, rows=(E, 2 * E), out_f32=g_qc)
+
+        def k_side():
             lin.wgrad(dkr, t["kr_in"], B * W, rows=(2 * E, 3 * E))
             lin.wgrad(dkc, t["kc_in"], B * H, rows=(3 * E, 4 * E))
-            lin.dgrad(dqr, M, rows=(0, E), out_f32=g_qr)
-            lin.dgrad(dqc, M, rows=(E, 2 * E), out_f32=g_qc)
             if hoist is None:
                 lin.dgrad(dkr, B * W, rows=(2 * E, 3 * E), out_f32=g_kr)
                 lin.dgrad(dkc, B * H, rows=(3 * E, 4 * E), out_f32=g_kc)
+
+        def qk_dgrads():
+            qr_side(); qc_side(); k_side()
 
         if t["v_s"] is not None:
             # tcgen05 kernels.  The value side (dV, then the v-projection dgrad) only needs dO and the saved maps, so
@@ -704,8 +721,14 @@ class Engine:
             def query_key_side():
                 L.call("cdetr_rcda_bwd_q_tc", B, Lq, H, W, E, self.nh, t["kr"], t["kc"], t["v_s"], t["ar"], t["ac"], dO,
                        dsr, dsc, dqr, dqc)
-                L.call("cdetr_rcda_bwd_k", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], dsr, dsc, dkr, dkc)
-                qk_dgrads()
+                # the three input-projection gradients are independent once dS exists: the key side (dK from dS, then its
+                # projections) runs beside the two query-side dgrads instead of in front of them
+
+                def key_chain():
+                    L.call("cdetr_rcda_bwd_k", B, Lq, H, W, E, self.nh, t["qr"], t["qc"], dsr, dsc, dkr, dkc)
+                    k_side()
+
+                self.fork_join([qr_side, qc_side, key_chain])
 
             def value_side():
                 L.call("cdetr_rcda_bwd_v_tc", B, Lq, H, W, E, self.nh, t["ar"], t["ac"], dO_s, dv)
