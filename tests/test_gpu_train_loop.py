@@ -153,8 +153,11 @@ def test_captured_step_matches_the_eager_loop():
         sched_b.step()
         replayed.append(total.item())
     assert step._graph is not None and step.launches_per_step > 500
+    # same kernels in both loops; the first step agrees to fp32 rounding, later steps carry the AdamW-amplified noise of
+    # the fp32 atomics (split-K order differs from run to run; see the parameter bound below)
+    assert abs(replayed[0] - eager[0]) <= 2e-5 * abs(eager[0]), (replayed, eager)
     for a, b in zip(replayed, eager):
-        assert abs(a - b) <= 2e-5 * abs(b), (replayed, eager)   # same kernels; split-K atomics reorder fp32 sums
+        assert abs(a - b) <= 5e-4 * abs(b), (replayed, eager)
     for (n, p), q in zip(model_a.named_parameters(), model_b.parameters()):
         if p.requires_grad:
             # AdamW normalises every gradient element by its own magnitude, so an element whose gradient is at the
