@@ -201,6 +201,8 @@ class Engine:
         self.rcda_legacy = bool(int(os.environ.get("CDETR_RCDA_LEGACY", "0")))   # A/B + tests of the CUDA-core RCDA
         self.aux_streams = [torch.cuda.Stream(device=device, priority=-1) for _ in range(4)] if device.type == "cuda" else []
         self._aux_rr = 0        # round-robin start: nested / consecutive forks land on different streams
+        self.acc_stream = torch.cuda.Stream(device=device, priority=0) if device.type == "cuda" else None
+        self.acc_used = False
 
     # Precision policy: "<group>.<kind>=<mask>" entries, group in {backbone, proj, attn, ffn, pos,
     # heads, *}, kind in {fwd, dgrad, wgrad, *}, mask = cdetr_gemm_t.pass_mask (7 all three products, 5 second operand
@@ -291,6 +293,27 @@ class Engine:
         main = torch.cuda.current_stream()
         for ev in evs:
             main.wait_event(ev)
+
+    def on_acc(self, fn):
+        """Accumulations that nothing on the dgrad chain consumes (position-embedding / anchor-point gradients summed over
+        layers) leave the critical path: they run on a dedicated in-order stream, ordered after 'now', and are joined
+        once before their consumers (join_acc)."""
+        if self.acc_stream is None:
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.acc_stream.wait_event(ev)
+        with torch.cuda.stream(self.acc_stream):
+            fn()
+        self.acc_used = True
+
+    def join_acc(self):
+        if self.acc_stream is not None and self.acc_used:
+            ev = torch.cuda.Event()
+            ev.record(self.acc_stream)
+            torch.cuda.current_stream().wait_event(ev)
+            self.acc_used = False
 
     def join_side_stream(self):
         """main stream waits for every weight-gradient kernel issued on the side stream."""
@@ -929,71 +952,102 @@ class Engine:
         """cls / bbox / variance heads (shared weights, A2/models/transformer.py:193-211)."""
         tag = f"heads{i}"
         logits = self.buf(tag + ".logits", (MQ, 2))
-        self.lins["cls"].fwd(xs, MQ, out_f32=logits)
         h1 = self.sbuf(tag + ".b1", MQ, self.E); h2 = self.sbuf(tag + ".b2", MQ, self.E)
-        self.lins["bbox_embed.0"].fwd(xs, MQ, out_split=h1, relu=True)
-        self.lins["bbox_embed.1"].fwd(h1, MQ, out_split=h2, relu=True)
         t = self.buf(tag + ".t", (MQ, 4))
-        self.lins["bbox_embed.2"].fwd(h2, MQ, out_f32=t)
         boxes = self.buf(tag + ".boxes", (MQ, 4))
         # reference points are identical for every sample: index rows modulo Q via a repeated view
         ref_b = self.buf("ref_rep", (MQ, 2))
         ref_b.view(-1, Q, 2).copy_(self.saved["ref"].unsqueeze(0).expand(MQ // Q, Q, 2))
-        L.call("cdetr_box_head_fwd", t, ref_b, MQ, boxes)
         out = dict(logits=logits, boxes=boxes, xs=xs, h1=h1, h2=h2, ref_b=ref_b)
+
+        def box_head():
+            self.lins["bbox_embed.0"].fwd(xs, MQ, out_split=h1, relu=True)
+            self.lins["bbox_embed.1"].fwd(h1, MQ, out_split=h2, relu=True)
+            self.lins["bbox_embed.2"].fwd(h2, MQ, out_f32=t)
+            L.call("cdetr_box_head_fwd", t, ref_b, MQ, boxes)
+
+        branches = [box_head, lambda: self.lins["cls"].fwd(xs, MQ, out_f32=logits)]
         if self.cfg.stage == 2:
             v1 = self.sbuf(tag + ".v1", MQ, self.E); v2 = self.sbuf(tag + ".v2", MQ, self.E)
-            self.lins["bbox_variance.0"].fwd(xs, MQ, out_split=v1, relu=True)
-            self.lins["bbox_variance.1"].fwd(v1, MQ, out_split=v2, relu=True)
             vr = self.buf(tag + ".vars", (MQ, 2))
-            self.lins["bbox_variance.2"].fwd(v2, MQ, out_f32=vr)
+
+            def var_head():
+                self.lins["bbox_variance.0"].fwd(xs, MQ, out_split=v1, relu=True)
+                self.lins["bbox_variance.1"].fwd(v1, MQ, out_split=v2, relu=True)
+                self.lins["bbox_variance.2"].fwd(v2, MQ, out_f32=vr)
+
+            branches.append(var_head)
             out.update(vars=vr, v1=v1, v2=v2)
+        self.fork_join(branches)        # the three heads are independent chains of tiny (M = B*Q) GEMMs
         self.saved[tag] = out
         return out
 
     # ------------------------------------------------------------------ backward
     def _heads_bwd(self, i, MQ, d_logits, d_boxes, d_vars, dx, first):
-        """accumulates the heads' input gradient into fp32 dx [MQ,E] (written when `first`)."""
+        """writes (first) / accumulates the heads' input gradient into fp32 dx [MQ,E]: the heads are independent chains,
+        each leaves its input gradient in its own buffer and one kernel sums them."""
         h = self.saved[f"heads{i}"]
         tag = f"heads{i}"
         E = self.E
-        wrote = not first
-
-        def acc_dgrad(lin, dy, **kw):
-            nonlocal wrote
-            lin.dgrad(dy, MQ, out_f32=dx, add_f32=dx if wrote else None, **kw)
-            wrote = True
-
+        parts, branches = [], []
         if d_logits is not None and self.lins["cls"].trainable:
-            dl = self.sbuf(tag + ".dl", MQ, 8)
-            L.call("cdetr_to_split", d_logits, MQ, 2, 2, dl)
-            self.lins["cls"].wgrad(dl, h["xs"], MQ)
-            acc_dgrad(self.lins["cls"], dl)
+            g_cls = self.buf(tag + ".g_cls", (MQ, E))
+            parts.append(g_cls)
+
+            def cls_branch():
+                dl = self.sbuf(tag + ".dl", MQ, 8)
+                L.call("cdetr_to_split", d_logits, MQ, 2, 2, dl)
+                self.lins["cls"].wgrad(dl, h["xs"], MQ)
+                self.lins["cls"].dgrad(dl, MQ, out_f32=g_cls)
+
+            branches.append(cls_branch)
         if d_boxes is not None:
-            dt = self.sbuf(tag + ".dt", MQ, 8)
+            g_box = self.buf(tag + ".g_box", (MQ, E))
+            parts.append(g_box)
             dref = self.buf("dref_rep", (MQ, 2), zero=True) if self.cfg.spatial_prior == "learned" else None
-            L.call("cdetr_box_head_bwd", d_boxes, h["boxes"], h["ref_b"], MQ, None, dt, dref)
             if dref is not None:
                 self.saved.setdefault("dref_list", []).append(dref)
-            self.lins["bbox_embed.2"].wgrad(dt, h["h2"], MQ)
-            d2 = self.sbuf(tag + ".d2", MQ, E); d1 = self.sbuf(tag + ".d1", MQ, E)
-            self.lins["bbox_embed.2"].dgrad(dt, MQ, out_split=d2, mask=h["h2"])
-            self.lins["bbox_embed.1"].wgrad(d2, h["h1"], MQ)
-            self.lins["bbox_embed.1"].dgrad(d2, MQ, out_split=d1, mask=h["h1"])
-            self.lins["bbox_embed.0"].wgrad(d1, h["xs"], MQ)
-            acc_dgrad(self.lins["bbox_embed.0"], d1)
+
+            def box_branch():
+                dt = self.sbuf(tag + ".dt", MQ, 8)
+                L.call("cdetr_box_head_bwd", d_boxes, h["boxes"], h["ref_b"], MQ, None, dt, dref)
+                self.lins["bbox_embed.2"].wgrad(dt, h["h2"], MQ)
+                d2 = self.sbuf(tag + ".d2", MQ, E); d1 = self.sbuf(tag + ".d1", MQ, E)
+                self.lins["bbox_embed.2"].dgrad(dt, MQ, out_split=d2, mask=h["h2"])
+                self.lins["bbox_embed.1"].wgrad(d2, h["h1"], MQ)
+                self.lins["bbox_embed.1"].dgrad(d2, MQ, out_split=d1, mask=h["h1"])
+                self.lins["bbox_embed.0"].wgrad(d1, h["xs"], MQ)
+                self.lins["bbox_embed.0"].dgrad(d1, MQ, out_f32=g_box)
+
+            branches.insert(0, box_branch)          # the longest chain stays on the current stream
         if d_vars is not None and self.cfg.stage == 2:
-            dv = self.sbuf(tag + ".dvr", MQ, 8)
-            L.call("cdetr_to_split", d_vars, MQ, 2, 2, dv)
-            self.lins["bbox_variance.2"].wgrad(dv, h["v2"], MQ)
-            d2 = self.sbuf(tag + ".dv2", MQ, E); d1 = self.sbuf(tag + ".dv1", MQ, E)
-            self.lins["bbox_variance.2"].dgrad(dv, MQ, out_split=d2, mask=h["v2"])
-            self.lins["bbox_variance.1"].wgrad(d2, h["v1"], MQ)
-            self.lins["bbox_variance.1"].dgrad(d2, MQ, out_split=d1, mask=h["v1"])
-            self.lins["bbox_variance.0"].wgrad(d1, h["xs"], MQ)
-            acc_dgrad(self.lins["bbox_variance.0"], d1)
-        if not wrote:
-            dx.zero_()
+            g_var = self.buf(tag + ".g_var", (MQ, E))
+            parts.append(g_var)
+
+            def var_branch():
+                dv = self.sbuf(tag + ".dvr", MQ, 8)
+                L.call("cdetr_to_split", d_vars, MQ, 2, 2, dv)
+                self.lins["bbox_variance.2"].wgrad(dv, h["v2"], MQ)
+                d2 = self.sbuf(tag + ".dv2", MQ, E); d1 = self.sbuf(tag + ".dv1", MQ, E)
+                self.lins["bbox_variance.2"].dgrad(dv, MQ, out_split=d2, mask=h["v2"])
+                self.lins["bbox_variance.1"].wgrad(d2, h["v1"], MQ)
+                self.lins["bbox_variance.1"].dgrad(d2, MQ, out_split=d1, mask=h["v1"])
+                self.lins["bbox_variance.0"].wgrad(d1, h["xs"], MQ)
+                self.lins["bbox_variance.0"].dgrad(d1, MQ, out_f32=g_var)
+
+            branches.append(var_branch)
+        if not parts:
+            if first:
+                dx.zero_()
+            return
+        self.fork_join(branches)
+        if not first:
+            parts.append(dx)
+        while len(parts) > 3:                       # combine_bcast sums up to three tensors
+            L.call("cdetr_combine_bcast", parts[0], parts[1], parts[2], None, 0.0, None, 0.0, MQ, E, 1, 1, parts[0])
+            parts = [parts[0]] + parts[3:]
+        parts += [None] * (3 - len(parts))
+        L.call("cdetr_combine_bcast", parts[0], parts[1], parts[2], None, 0.0, None, 0.0, MQ, E, 1, 1, dx)
 
     def backward(self, grads):
         """grads: list (one entry per emitted decoder layer, last = final layer) of dicts with optional
@@ -1043,8 +1097,11 @@ class Engine:
                 L.call("cdetr_add_bcast", g_krd, g_kr, B * W, E, 0, 1, 1, 0, g_krd, None)
                 L.call("cdetr_add_bcast", g_kcd, g_kc, B * H, E, 0, 1, 1, 0, g_kcd, None)
             # queries: q_row_in = t1 + qx, q_col_in = t1 + qy
-            L.call("cdetr_reduce_axis", g_qr, 1, B, Q, E, 1, 1.0, None, 1, dqx, None)
-            L.call("cdetr_reduce_axis", g_qc, 1, B, Q, E, 1, 1.0, None, 1, dqy, None)
+            def acc_q(g_qr=g_qr, g_qc=g_qc):
+                L.call("cdetr_reduce_axis", g_qr, 1, B, Q, E, 1, 1.0, None, 1, dqx, None)
+                L.call("cdetr_reduce_axis", g_qc, 1, B, Q, E, 1, 1.0, None, 1, dqy, None)
+
+            self.on_acc(acc_q)
             dt1 = self.buf(q + ".dt1", (MQ, E))
             L.call("cdetr_combine_bcast", dz1, g_qr, g_qc, None, 0.0, None, 0.0, MQ, E, 1, 1, dt1)
             dz2, dz2s = self._ln_bwd(dt1, None, q + ".ln2")      # -> sa (split), tgt residual (fp32)
@@ -1061,12 +1118,11 @@ class Engine:
             lin = self.lins[q + ".sa_in"]
             lin.wgrad(dq_, t["qk"], MQ, rows=(0, 2 * E))
             lin.wgrad(dv_, t["tgt_s"], MQ, rows=(2 * E, 3 * E))
-            g_qk = self.buf(q + ".g_qk", (MQ, E))
-            lin.dgrad(dq_, MQ, rows=(0, 2 * E), out_f32=g_qk)
-            L.call("cdetr_reduce_axis", g_qk, 1, B, Q, E, 1, 1.0, None, 1, dqpos, None)
-            g_t = self.buf(q + ".g_t", (MQ, E))
-            lin.dgrad(dv_, MQ, rows=(2 * E, 3 * E), out_f32=g_t, add_f32=g_qk)
-            L.call("cdetr_combine_bcast", dz2, g_t, None, None, 0.0, None, 0.0, MQ, E, 1, 1, dtgt)
+            g_qk = self.buf(q + ".g_qk", (MQ, E)); g_t = self.buf(q + ".g_t", (MQ, E))
+            self.fork_join([lambda: lin.dgrad(dq_, MQ, rows=(0, 2 * E), out_f32=g_qk),
+                            lambda: lin.dgrad(dv_, MQ, rows=(2 * E, 3 * E), out_f32=g_t)])
+            self.on_acc(lambda g_qk=g_qk: L.call("cdetr_reduce_axis", g_qk, 1, B, Q, E, 1, 1.0, None, 1, dqpos, None))
+            L.call("cdetr_combine_bcast", dz2, g_qk, g_t, None, 0.0, None, 0.0, MQ, E, 1, 1, dtgt)
             have_dtgt = True
         if hoisted:
             pm = self.policy_mask("attn", "dgrad")
@@ -1095,11 +1151,15 @@ class Engine:
             d1 = self._ffn_bwd(dx, None, q)
             dz1, dz1s = self._ln_bwd(d1, None, q + ".ln1")
             g_qr, g_qc, g_kr, g_kc, g_v = self._rcda_bwd(q, q + ".in", q + ".out", dz1s, dv_add=dz1)
-            L.call("cdetr_reduce_axis", g_qr, B, H, W, E, 1, 1.0, g_kr, 1, dpe_row, None)
-            L.call("cdetr_reduce_axis", g_qc, B, H, W, E, 2, 1.0, g_kc, 1, dpe_col, None)
+            def acc_pe(g_qr=g_qr, g_qc=g_qc, g_kr=g_kr, g_kc=g_kc):
+                L.call("cdetr_reduce_axis", g_qr, B, H, W, E, 1, 1.0, g_kr, 1, dpe_row, None)
+                L.call("cdetr_reduce_axis", g_qc, B, H, W, E, 2, 1.0, g_kc, 1, dpe_col, None)
+
+            self.on_acc(acc_pe)
             dx = self.buf(q + ".dx", (M, E))
             L.call("cdetr_combine_bcast", g_qr, g_qc, g_v, g_kr, 1.0 / H, g_kc, 1.0 / W, M, E, H, W, dx)
-        # ---- position MLPs
+        # ---- position MLPs (consumers of everything that was accumulated off the chain)
+        self.join_acc()
         L.call("cdetr_add_bcast", dpe[B * W + B * H: B * W + B * H + Q], dqx, Q, E, 0, 1, 1, 0,
                dpe[B * W + B * H: B * W + B * H + Q], None)
         L.call("cdetr_add_bcast", dpe[B * W + B * H + Q:], dqy, Q, E, 0, 1, 1, 0, dpe[B * W + B * H + Q:], None)
