@@ -913,8 +913,8 @@ class Engine:
             L.call("cdetr_add_bcast", tgt, qpos, MQ, E, 3, 1, 1, Q, None, qk)
             qkv = self.buf(q + ".qkv", (MQ, 3 * E))
             lin = self.lins[q + ".sa_in"]
-            lin.fwd(qk, MQ, rows=(0, 2 * E), out_f32=qkv[:, : 2 * E])
-            lin.fwd(tgt_s, MQ, rows=(2 * E, 3 * E), out_f32=qkv[:, 2 * E:])
+            self.fork_join([lambda: lin.fwd(qk, MQ, rows=(0, 2 * E), out_f32=qkv[:, : 2 * E]),
+                            lambda: lin.fwd(tgt_s, MQ, rows=(2 * E, 3 * E), out_f32=qkv[:, 2 * E:])])
             o = self.sbuf(q + ".sa_o", MQ, E); lse = self.buf(q + ".lse", (B, self.nh, Q))
             L.call("cdetr_mha_fwd", B, Q, E, self.nh, qkv, qkv[:, E:], qkv[:, 2 * E:], 3 * E, o, lse)
             sa = self.buf(q + ".sa", (MQ, E))
@@ -922,8 +922,8 @@ class Engine:
             sv[q + ".sa"] = dict(qk=qk, tgt_s=tgt_s, qkv=qkv, o=o, lse=lse)
             t1, t1s = self._ln_fwd(sa, tgt, MQ, q + ".norm2", q + ".ln2")
             qr_in = self.sbuf(q + ".qr_in", MQ, E); qc_in = self.sbuf(q + ".qc_in", MQ, E)
-            L.call("cdetr_add_bcast", t1, qx, MQ, E, 3, 1, 1, Q, None, qr_in)
-            L.call("cdetr_add_bcast", t1, qy, MQ, E, 3, 1, 1, Q, None, qc_in)
+            self.fork_join([lambda: L.call("cdetr_add_bcast", t1, qx, MQ, E, 3, 1, 1, Q, None, qr_in),
+                            lambda: L.call("cdetr_add_bcast", t1, qy, MQ, E, 3, 1, 1, Q, None, qc_in)])
             if hoist_join is not None:
                 self.join(hoist_join)
                 hoist_join = None
