@@ -861,11 +861,15 @@ class Engine:
         for i in range(cfg.enc_layers):
             q = f"transformer.encoder_layers.{i}"
             xr = self.sbuf(q + ".xr", M, E); xc = self.sbuf(q + ".xc", M, E)
-            L.call("cdetr_add_bcast", x, pe_row, M, E, 1, H, W, 0, None, xr)
-            L.call("cdetr_add_bcast", x, pe_col, M, E, 2, H, W, 0, None, xc)
             krin = self.sbuf(q + ".krin", B * W, E); kcin = self.sbuf(q + ".kcin", B * H, E)
-            L.call("cdetr_reduce_axis", x, B, H, W, E, 1, 1.0 / H, pe_row, 0, None, krin)
-            L.call("cdetr_reduce_axis", x, B, H, W, E, 2, 1.0 / W, pe_col, 0, None, kcin)
+
+            def key_means(x=x, krin=krin, kcin=kcin):
+                L.call("cdetr_reduce_axis", x, B, H, W, E, 1, 1.0 / H, pe_row, 0, None, krin)
+                L.call("cdetr_reduce_axis", x, B, H, W, E, 2, 1.0 / W, pe_col, 0, None, kcin)
+
+            # four independent small kernels over the same x: three branches instead of a chain
+            self.fork_join([lambda x=x, xr=xr: L.call("cdetr_add_bcast", x, pe_row, M, E, 1, H, W, 0, None, xr),
+                            lambda x=x, xc=xc: L.call("cdetr_add_bcast", x, pe_col, M, E, 2, H, W, 0, None, xc), key_means])
             attn = self._rcda_fwd(q, q + ".in", q + ".out", B, N, H, W, xr, xc, krin, kcin, xs, masks)
             x1, x1s = self._ln_fwd(attn, x, M, q + ".norm1", q + ".ln1")
             x, xs = self._ffn_fwd(x1, x1s, M, q)
