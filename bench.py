@@ -17,6 +17,7 @@ cpu_baseline = the oracle port (CPU PyTorch restatement of the reference) on the
 `--impl reference` prints the CPU arm alone (the reference itself cannot travel to the GPU box).
 """
 import argparse
+import itertools
 import json
 import os
 import statistics
@@ -337,54 +338,62 @@ def run_ours(args):
     loss_pin = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_run(stepper, n, lagged=False):
-        """lagged=False: loss.item() right after every step (the reference's loop, A2/engine.py:44).  lagged=True: the loss
-        of step i leaves through an async copy into pinned memory and is read while step i+1 runs (still one read per
-        step, the last one inside the timed region): the host never leaves the device idle."""
-        pf = DevicePrefetcher((host[i & 1] for i in range(n)), dev, defer=not lagged)
-        last = None
-        for k, b in enumerate(pf):
-            _, total = call(stepper, b)
-            if not lagged:
-                pf.kick()            # next batch's H2D is issued after this step's launch, before the blocking read
-                last = total.item()
-                continue
-            slot = k & 1
-            loss_pin[slot].copy_(total, non_blocking=True)
-            loss_ev[slot].record()
-            if k >= 1:
-                loss_ev[slot ^ 1].synchronize()
-                last = float(loss_pin[slot ^ 1])
-        if lagged and n >= 1:
-            loss_ev[(n - 1) & 1].synchronize()
-            last = float(loss_pin[(n - 1) & 1])
-        return last, pf.h2d_bytes
+    class E2ELoop:
+        """The reference's iteration over a data loader, through the public API.  One DevicePrefetcher over an endless
+        stream of pinned host batches (a real epoch builds it once for hundreds of iterations: its construction - pinned
+        staging buffers, copy stream - is outside the timed region, every step's H2D copy and result read are inside).
+        lagged=False: loss.item() right after every step (A2/engine.py:44).  lagged=True: the loss of step i leaves through
+        an async copy into pinned memory and is read while step i+1 runs (still one read per step, the last one inside the
+        timed region): the host never leaves the device idle."""
 
-    e2e_run(step_fb, 3)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    _, h2d_total = e2e_run(step_fb, steps)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1) / steps
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t)
-    e2e_run(step_fb, 2, lagged=True)
-    barrier()
-    e0.record()
-    e2e_run(step_fb, steps, lagged=True)
-    e1.record()
-    barrier()
-    ms_e2e_lag = e0.elapsed_time(e1) / steps
-    if world > 1:
-        t = torch.tensor([ms_e2e_lag], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e_lag = float(t)
+        def __init__(self, stepper, lagged):
+            self.stepper, self.lagged, self.k = stepper, lagged, 0
+            self.pf = DevicePrefetcher((host[i & 1] for i in itertools.count()), dev, defer=not lagged)
+            self.it = iter(self.pf)
+
+        def run(self, n):
+            last = None
+            for _ in range(n):
+                b = next(self.it)
+                _, total = call(self.stepper, b)
+                if not self.lagged:
+                    self.pf.kick()       # next batch's H2D is issued after this step's launch, before the blocking read
+                    last = total.item()
+                    continue
+                slot = self.k & 1
+                loss_pin[slot].copy_(total, non_blocking=True)
+                loss_ev[slot].record()
+                if self.k >= 1:
+                    loss_ev[slot ^ 1].synchronize()
+                    last = float(loss_pin[slot ^ 1])
+                self.k += 1
+            if self.lagged and n >= 1:
+                loss_ev[(self.k - 1) & 1].synchronize()
+                last = float(loss_pin[(self.k - 1) & 1])
+            return last
+
+        def timed(self, n):
+            self.run(3)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0 = self.pf.h2d_bytes
+            e0.record()
+            self.run(n)
+            e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1) / n
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t)
+            h2d = (self.pf.h2d_bytes - h0) // n
+            self.it.close()
+            return ms, h2d
+
+    ms_e2e, h2d_step = E2ELoop(step_fb, lagged=False).timed(steps)
+    ms_e2e_lag, _ = E2ELoop(step_fb, lagged=True).timed(steps)
     e2e = {"value": B * world / ms_e2e * 1e3, "unit": "images/s", "ms_per_step": ms_e2e,
-           "h2d_bytes_per_step": int(h2d_total // steps), "d2h_bytes_per_step": 4,
+           "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": 4,
            "path": "DevicePrefetcher(pinned host batches) -> CapturedStep(model, criterion) -> loss.item() every step",
            "value_async_loss_read": B * world / ms_e2e_lag * 1e3,
            "async_note": "same path, but the loss of step i is read (from pinned memory) while step i+1 runs"}
@@ -403,13 +412,7 @@ def run_ours(args):
         eng2 = model2.engine()
         ms_opt = timed(lambda i: opt.step(max_norm=0.1), 10)
         ms_pack = timed(lambda i: eng2.pack_weights(), 10)
-        e2e_run(step_full, 2)
-        barrier()
-        e0.record()
-        e2e_run(step_full, steps)
-        e1.record()
-        barrier()
-        ms_full_e2e = e0.elapsed_time(e1) / steps
+        ms_full_e2e, _ = E2ELoop(step_full, lagged=False).timed(steps)
         full = {"ms_per_step": ms_full, "value": B * world / ms_full * 1e3, "e2e_value": B * world / ms_full_e2e * 1e3,
                 "optimizer_plus_repack_ms_in_graph": ms_full - ms_step,
                 "optimizer_ms_eager": ms_opt, "repack_ms_eager": ms_pack, "launches_per_step": step_full.launches_per_step,

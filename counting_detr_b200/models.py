@@ -188,6 +188,7 @@ class AnchorDETR(nn.Module):
                 p.requires_grad_(False)
         self._maybe_load_pretrained()
         self._engine = None
+        self._plist = None
         self._param_version = None
         self._grad_group = None
         self._alias_grads = False
@@ -246,7 +247,7 @@ class AnchorDETR(nn.Module):
     def _pack_weights_graphed(self, eng):
         """The re-pack of the weights an optimizer step changed (125 pack + 53 FrozenBN-fold launches) as one graph
         replay; parameter storages are fixed (load_state_dict copies in place), checked by their pointers."""
-        key = tuple(p.data_ptr() for p in self.parameters())
+        key = tuple(p.data_ptr() for p in self._param_list())
         if self._pack_graph is None or self._pack_graph[0] != key:
             eng.pack_weights()                       # eager once: allocates the packed buffers
             torch.cuda.synchronize(eng.dev)
@@ -257,8 +258,27 @@ class AnchorDETR(nn.Module):
         self._pack_graph[1].replay()
         eng.packed = True
 
+    def _param_list(self):
+        """The parameters in registration order, cached: walking the module tree costs ~0.3 ms, and the version check
+        below sits between a step's result and the next launch.  _apply (.to / .cuda / .float) drops the cache."""
+        if self._plist is None:
+            self._plist = list(self.parameters())
+        return self._plist
+
+    def _apply(self, fn, *a, **k):
+        self._plist = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._plist = None                  # assign=True swaps the Parameter objects
+        try:
+            return super().load_state_dict(*a, **k)
+        finally:
+            self._plist = None
+
     def _current_version(self):
-        return tuple(p._version for p in self.parameters())
+        # tensor version counters only ever grow, so their sum changes iff some parameter was written
+        return sum(p._version for p in self._param_list())
 
     def forward(self, samples, points=None, rects=None):
         """stage 2: model(samples, points=None, rects=[B,3,4]) -> (dict, reference_points)
@@ -283,7 +303,7 @@ class AnchorDETR(nn.Module):
             if rects is None:
                 raise ValueError("stage-2 forward needs exemplar rects")
             rects0 = rects[0]                 # the rects of SAMPLE 0 serve the whole batch (A2/models/backbone.py:122)
-        params = [p for p in self.parameters()]
+        params = self._param_list()
         outs = _ModelFn.apply(self, samples, rects0, points, mask, *params)
         return self._pack_outputs(outs)
 

@@ -15,15 +15,17 @@ dev = torch.device("cuda", 0)
 model, crit, _ = build_model(SY.default_args(st, num_query_position=Q, device="cuda"))
 model.load_state_dict(SY.make_state_dict(SY.SynthCfg(stage=st, num_query_position=Q), 0), strict=True)
 model.to(dev).train()
+model._auto_graph = False                      # this tool captures the step itself (per-GEMM device timestamps)
 inp = SY.make_inputs(B, S, T=T, stage=st, Q=Q)
 img = inp["image"].to(dev)
+rects = inp["rects"].to(dev) if "rects" in inp else None
 targets = [{k: v.to(dev) for k, v in t.items()} for t in inp["targets"]] if st == 2 else {"points": inp["points"].to(dev), "whs": inp["whs"].to(dev)}
 
 
 def step():
     model.zero_grad(set_to_none=True)
     if st == 2:
-        out, _ = model(img, None, inp["rects"])
+        out, _ = model(img, None, rects)
     else:
         out = model(img, targets["points"])
     ld = crit(out, targets)
