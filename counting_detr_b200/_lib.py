@@ -86,6 +86,7 @@ COUNTER = {"launches": 0}
 _LAUNCHES = {"cdetr_exemplar_concat": 2, "cdetr_exemplar_concat_bwd": 2, "cdetr_rcda_bwd": 3, "cdetr_rcda_bwd_kv": 2, "cdetr_mha_bwd": 2,
              "cdetr_mt_grad_norm": 2, "cdetr_mt_adamw": 2}
 GEMM_TRACE = None
+SKIP = None            # tools/criticality.py only: set of entry points NOT launched (timing experiments, wrong results)
 CALL_TRACE = None      # when a list: (name, leading int args, start event, end event) of every attention-core call
 
 
@@ -222,6 +223,8 @@ def call(name, *args):
             conv.append(float(a))
         else:
             conv.append(int(a))
+    if SKIP is not None and name in SKIP:
+        return
     COUNTER["launches"] += _LAUNCHES.get(name, 1)
     if CALL_TRACE is not None and name.startswith(("cdetr_rcda", "cdetr_mha")):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -651,16 +651,20 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
 
 // ---------------------------------------------------------------------------------------------
 // Backward (value side) on tensor cores:  dV[(h,w), c] = sum_q A_c[q,h] A_r[q,w] dO[q,c]
-// One CTA per (sample, head).  Per block of 64 queries: dO tile by TMA (split planes, SWIZZLE_64B, MN-major B
-// operand), the attention maps of those queries staged in shared memory, and for each 128-row tile of key
-// positions the compute warps build P[(h,w), q] = A_c A_r as a split-bf16 K-major A operand (SWIZZLE_128B,
-// double buffered) which one thread multiplies into the tile's 32 TMEM columns: the [L, H*W] outer-product
-// matrix exists only 32 KB at a time.  The accumulators of a CTA's slice of key positions (<= 8 tiles = 256 TMEM
-// columns) stay resident; H, W <= 64 (the staged maps take max(H,W) rows: two CTAs per SM up to ~52 x 52).
+// One CTA per (sample, head, slice of key positions).  Per block of 64 queries: dO tile by TMA (split planes,
+// SWIZZLE_64B, MN-major B operand), the attention maps of those queries staged in shared memory (cp.async, one block
+// ahead), and for each 128-row tile of key positions the compute warps build P[(h,w), q] = A_c A_r as a split-bf16
+// A operand IN TENSOR MEMORY (tcgen05.st, one key position per TMEM lane = per thread, two bf16 per column), which one
+// thread multiplies (tcgen05.mma with the A operand read from TMEM) into the tile's 32 accumulator columns.  The
+// [L, H*W] outer-product matrix never touches shared memory: round 1 wrote every P tile to shared memory and had the
+// tensor core read it back three times (hi twice, lo once), and ncu showed that kernel bound by the shared-memory
+// pipe (l1tex data-pipe wavefronts 74 % of peak while active, tensor pipe 9 %); per tile that was 32 KB of stores +
+// 48 KB of operand reads beside 64 KB of map loads, now only the map loads (and 12 KB of dO operand reads) remain.
+// TMEM plan: tiles_per_cta * 32 accumulator columns + p_bufs * 64 operand columns (hi plane | lo plane, 32 columns
+// = 64 queries each); 256 columns per CTA keep two CTAs per SM.  H, W <= 64.
 constexpr int VK = 64;                                   // queries per k block
-constexpr uint32_t P_TILE_BYTES = 128 * VK * 2;          // one plane of the P tile: 16 KB
 constexpr uint32_t DO_PLANE_BYTES = VK * HD * 2;         // 4 KB
-constexpr int MAP_LD = 72;                               // map row = two 32-query halves at +0 / +36: conflict-free float4 reads
+constexpr int MAP_LD = 68;                               // map row = 64 queries + 4: conflict-free float4 reads of 8 rows
 
 struct TcBwdVArgs {
   int B, L, H, W, E, nh;
@@ -669,19 +673,27 @@ struct TcBwdVArgs {
   __nv_bfloat16 *dv_hi, *dv_lo;
   int64_t ld_g;
   uint32_t idesc;
-  int tiles_per_cta;   // key-position tiles (of 128) per CTA: blockIdx.z selects the slice of positions (<= 8)
+  int tiles_per_cta;   // key-position tiles (of 128) per CTA: blockIdx.z selects the slice of positions
   int kp;              // rows of the staged attention maps: max(H, W) rounded up to 8 (<= 64)
   int map_bufs;        // 2: the next query block's maps are prefetched (cp.async) while this block's tiles are built
-  int d_bufs;          // dO stages (2 when shared memory allows two CTAs per SM with it)
+  int d_bufs;          // dO stages
+  int p_bufs;          // P operand buffers in TMEM (2 when the accumulators leave 128 columns free)
+  int tmem_cols;       // allocation: 256 (two CTAs per SM) or 512
+  int vec4;            // L % 4 == 0 and 16-byte aligned maps: stage them with 16-byte cp.async
 };
+
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 
 __global__ void __launch_bounds__(320, 2)
 rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a) {
   pdl_trigger();   // light successors (launch_light) may pre-launch; they wait for this grid to finish
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Ps = smem;                                    // [2 bufs][2 planes][128][64] bf16, SW128 K-major
-  uint8_t* Ds = Ps + 4 * P_TILE_BYTES;                   // [d_bufs][2 planes][64 q][32 c] bf16, SW64
+  uint8_t* Ds = smem;                                    // [d_bufs][2 planes][64 q][32 c] bf16, SW64
   float* maps = reinterpret_cast<float*>(Ds + a.d_bufs * 2 * DO_PLANE_BYTES);   // [map_bufs][A_r | A_c][kp][MAP_LD]
   const int map_stride = 2 * a.kp * MAP_LD;
   uint64_t* bars = reinterpret_cast<uint64_t*>(maps + a.map_bufs * map_stride);
@@ -698,6 +710,7 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
   const int mt_begin = blockIdx.z * a.tiles_per_cta;
   const int mt_end = min((HW + 127) / 128, mt_begin + a.tiles_per_cta);
   const int nkb = (a.L + VK - 1) / VK;
+  const uint32_t p_col0 = (uint32_t)a.tiles_per_cta * 32u;   // first operand column behind the accumulators
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmD);
     for (int i = 0; i < 2; ++i) {
@@ -710,7 +723,7 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_holder, 256);
+    tmem_alloc(tmem_holder, (uint32_t)a.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -722,7 +735,7 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % a.d_bufs;
-        if (kb >= a.d_bufs) mbar_wait(&d_empty[s], (uint32_t)(kb / a.d_bufs - 1) & 1u);
+        if (kb >= a.d_bufs) mbar_wait_sleep(&d_empty[s], (uint32_t)(kb / a.d_bufs - 1) & 1u);
         mbar_arrive_expect_tx(&d_full[s], 2 * DO_PLANE_BYTES);
         tma_load_3d(Ds + s * 2 * DO_PLANE_BYTES, &tmD, &d_full[s], head * HD, b * a.L + kb * VK, 0);
         tma_load_3d(Ds + s * 2 * DO_PLANE_BYTES + DO_PLANE_BYTES, &tmD, &d_full[s], head * HD, b * a.L + kb * VK, 1);
@@ -733,23 +746,23 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
       int u = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % a.d_bufs;
-        mbar_wait(&d_full[s], (uint32_t)(kb / a.d_bufs) & 1u);
+        mbar_wait_sleep(&d_full[s], (uint32_t)(kb / a.d_bufs) & 1u);
         const uint32_t d_base = smem_u32(Ds) + (uint32_t)s * 2u * DO_PLANE_BYTES;
         for (int mt = mt_begin; mt < mt_end; ++mt, ++u) {
-          const int pb = u & 1;
-          mbar_wait(&p_full[pb], (uint32_t)(u >> 1) & 1u);
+          const int pb = u % a.p_bufs;
+          mbar_wait_sleep(&p_full[pb], (uint32_t)(u / a.p_bufs) & 1u);
           tc_fence_after();
-          const uint32_t p_base = smem_u32(Ps) + (uint32_t)pb * 2u * P_TILE_BYTES;
+          const uint32_t p_base = tmem_base + p_col0 + (uint32_t)pb * 64u;   // hi plane; lo plane 32 columns further
           const uint32_t d = tmem_base + (uint32_t)(mt - mt_begin) * 32u;
 #pragma unroll
           for (int ks = 0; ks < VK / 16; ++ks) {
-            const uint64_t a_hi = make_smem_desc(p_base + ks * 32, 16, 1024, 2);                 // K-major SW128
-            const uint64_t a_lo = make_smem_desc(p_base + P_TILE_BYTES + ks * 32, 16, 1024, 2);
+            const uint32_t a_hi = p_base + (uint32_t)ks * 8u;                // 16 queries = 8 packed columns
+            const uint32_t a_lo = a_hi + 32u;
             const uint64_t b_hi = make_smem_desc(d_base + ks * 1024, 4096, 512, 4);              // MN-major SW64
             const uint64_t b_lo = make_smem_desc(d_base + DO_PLANE_BYTES + ks * 1024, 4096, 512, 4);
-            umma_bf16_ss(d, a_hi, b_lo, a.idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-            umma_bf16_ss(d, a_lo, b_hi, a.idesc, 1);
-            umma_bf16_ss(d, a_hi, b_hi, a.idesc, 1);
+            umma_bf16_ts(d, a_hi, b_lo, a.idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16_ts(d, a_lo, b_hi, a.idesc, 1);
+            umma_bf16_ts(d, a_hi, b_hi, a.idesc, 1);
           }
           umma_commit(&p_empty[pb]);
         }
@@ -759,18 +772,32 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
     }
   } else {
     const int ct = threadIdx.x - 64;        // 0..255
-    const int ml = ct >> 1;                 // row of the P tile built by this thread
-    const int qh = ct & 1;                  // which half (32 queries) of the k block
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const int ml = quarter * 32 + lane;     // row of the P tile (= TMEM lane) built by this thread
+    const int qh = (warp - 2) >> 2;         // which half (32 queries) of the k block
     const int64_t bh = (int64_t)b * a.nh + head;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int u = 0;
     // maps of one block of 64 queries -> shared memory, asynchronously (cp.async, 4 bytes each: rows of the transposed
     // maps are only 4-byte aligned for odd L); out-of-range entries are zeros
     auto stage_maps = [&](int kb2, float* dst) {
       const int q0 = kb2 * VK;
+      if (a.vec4) {     // L % 4 == 0: 16-byte chunks (4 queries), each entirely inside or outside the sequence
+        const int c4 = (ct & 15) * 4, q = q0 + c4;
+        const uint32_t nb = q < a.L ? 16u : 0u;
+        const float* sr = a.ar + bh * a.W * a.L + min(q, a.L - 4);
+        const float* sc = a.ac + bh * a.H * a.L + min(q, a.L - 4);
+        float* d = dst + c4;
+        for (int k = ct >> 4; k < a.kp; k += 16) {
+          cp_async_16_zfill(d + k * MAP_LD, sr + (int64_t)min(k, a.W - 1) * a.L, k < a.W ? nb : 0u);
+          cp_async_16_zfill(d + (a.kp + k) * MAP_LD, sc + (int64_t)min(k, a.H - 1) * a.L, k < a.H ? nb : 0u);
+        }
+        return;
+      }
       for (int i = ct; i < a.kp * VK; i += 256) {
         const int k = i / VK, qq = i % VK;
         const bool qok = q0 + qq < a.L;
-        const int mo = k * MAP_LD + (qq >> 5) * 36 + (qq & 31);
+        const int mo = k * MAP_LD + qq;
         if (qok && k < a.W) cp_async_4(dst + mo, a.ar + (bh * a.W + k) * a.L + q0 + qq); else dst[mo] = 0.0f;
         if (qok && k < a.H) cp_async_4(dst + a.kp * MAP_LD + mo, a.ac + (bh * a.H + k) * a.L + q0 + qq);
         else dst[a.kp * MAP_LD + mo] = 0.0f;
@@ -793,37 +820,34 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
         stage_maps(kb + 1, maps + ((kb + 1) & 1) * map_stride);   // in flight while this block's tiles are built
       }
       for (int mt = mt_begin; mt < mt_end; ++mt, ++u) {
-        const int pb = u & 1;
-        if (u >= 2) mbar_wait(&p_empty[pb], (uint32_t)((u >> 1) - 1) & 1u);
+        const int pb = u % a.p_bufs;
+        if (u >= a.p_bufs) {
+          mbar_wait_sleep(&p_empty[pb], (uint32_t)(u / a.p_bufs - 1) & 1u);   // the MMAs that read this buffer are done
+          tc_fence_after();
+        }
+        // rows past H*W only feed accumulator rows that are never stored: any in-range map row will do
         const int m = mt * 128 + ml;
-        const bool mok = m < HW;
-        const int h = mok ? m / a.W : 0, w = mok ? m % a.W : 0;
-        const uint32_t cr = smem_u32(acs + h * MAP_LD + qh * 36);     // explicit LDS / STS: see lds128()
-        const uint32_t rr = smem_u32(ars + w * MAP_LD + qh * 36);
-        const uint32_t Pb = smem_u32(Ps) + (uint32_t)pb * 2u * P_TILE_BYTES;
+        const int h = min(m / a.W, a.kp - 1), w = m % a.W;
+        const uint32_t cr = smem_u32(acs + h * MAP_LD + qh * 32);     // explicit LDS: see lds128()
+        const uint32_t rr = smem_u32(ars + w * MAP_LD + qh * 32);
+        const uint32_t pt = lane_addr + p_col0 + (uint32_t)pb * 64u + (uint32_t)qh * 16u;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {        // 4 chunks of 8 queries
-          float pv[8];
-          const float4 c0 = lds128(cr + 32 * j), c1 = lds128(cr + 32 * j + 16);
-          const float4 r0 = lds128(rr + 32 * j), r1 = lds128(rr + 32 * j + 16);
-          {
-            const float2 p01 = __fmul2_rn(make_float2(c0.x, c0.y), make_float2(r0.x, r0.y));
-            const float2 p23 = __fmul2_rn(make_float2(c0.z, c0.w), make_float2(r0.z, r0.w));
-            const float2 p45 = __fmul2_rn(make_float2(c1.x, c1.y), make_float2(r1.x, r1.y));
-            const float2 p67 = __fmul2_rn(make_float2(c1.z, c1.w), make_float2(r1.z, r1.w));
-            pv[0] = p01.x; pv[1] = p01.y; pv[2] = p23.x; pv[3] = p23.y;
-            pv[4] = p45.x; pv[5] = p45.y; pv[6] = p67.x; pv[7] = p67.y;
-          }
-          uint32_t hw[4], lw[4];
+        for (int j = 0; j < 2; ++j) {        // 2 groups of 16 queries = 8 packed columns per plane
+          uint32_t hw[8], lw[8];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            split_bf16_pair(mok ? pv[2 * i] : 0.0f, mok ? pv[2 * i + 1] : 0.0f, hw[i], lw[i]);
+            const float4 c = lds128(cr + 64 * j + 16 * i);
+            const float4 r = lds128(rr + 64 * j + 16 * i);
+            const float2 p01 = __fmul2_rn(make_float2(c.x, c.y), make_float2(r.x, r.y));
+            const float2 p23 = __fmul2_rn(make_float2(c.z, c.w), make_float2(r.z, r.w));
+            split_bf16_pair(p01.x, p01.y, hw[2 * i], lw[2 * i]);
+            split_bf16_pair(p23.x, p23.y, hw[2 * i + 1], lw[2 * i + 1]);
           }
-          const uint32_t off = (uint32_t)ml * 128u + (uint32_t)(((qh * 4 + j) ^ (ml & 7)) << 4);
-          sts128(Pb + off, hw[0], hw[1], hw[2], hw[3]);
-          sts128(Pb + P_TILE_BYTES + off, lw[0], lw[1], lw[2], lw[3]);
+          tmem_st_32x32b_x8(pt + 8u * j, hw);
+          tmem_st_32x32b_x8(pt + 32u + 8u * j, lw);
         }
-        fence_proxy_async();
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[pb]);
       }
@@ -833,13 +857,12 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
       }
     }
     // ---- epilogue: accumulators -> dV (split)
-    mbar_wait(acc_full, 0);
+    mbar_wait_sleep(acc_full, 0);
     tc_fence_after();
-    const int quarter = warp & 3;
     const int grp = (warp - 2) >> 2;
     for (int mt = mt_begin + grp; mt < mt_end; mt += 2) {
       uint32_t t[32];
-      tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt - mt_begin) * 32u, t);
+      tmem_ld_32x32b_x32(lane_addr + (uint32_t)(mt - mt_begin) * 32u, t);
       tmem_ld_wait();
       const int m = mt * 128 + quarter * 32 + lane;
       if (m < HW) {
@@ -861,7 +884,7 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
 }
 
@@ -1000,26 +1023,27 @@ extern "C" int cdetr_rcda_bwd_v_tc(int B, int L, int H, int W, int E, int nh, co
   a.dv_hi = reinterpret_cast<__nv_bfloat16*>(dv.base); a.dv_lo = a.dv_hi + dv.plane; a.ld_g = dv.ld;
   a.idesc = make_idesc_bf16_f32(128, HD, 0, 1);
   a.kp = ((H > W ? H : W) + 7) / 8 * 8;
-  // shared-memory plan: keep two CTAs per SM (<= ~112 KB each); spend what is left on prefetching the next query
-  // block's maps (double-buffered maps) and on a second dO stage
-  const size_t map_bytes = 2 * (size_t)a.kp * MAP_LD * sizeof(float);
-  const size_t fixed = 4 * P_TILE_BYTES + 128 + 1024;
-  const size_t budget = 112 * 1024;
-  a.map_bufs = fixed + 2 * DO_PLANE_BYTES + 2 * map_bytes <= budget ? 2 : 1;
-  a.d_bufs = fixed + 4 * DO_PLANE_BYTES + a.map_bufs * map_bytes <= budget ? 2 : 1;
-  const size_t smem = fixed + (size_t)a.d_bufs * 2 * DO_PLANE_BYTES + a.map_bufs * map_bytes;
-  static DevAttrCache cfg = {};
-  CDETR_CHECK_CUDA(cdetr_ensure_smem(rcda_bwd_v_tc_kernel, 4 * P_TILE_BYTES + 4 * DO_PLANE_BYTES + 2 * 2 * 64 * MAP_LD * 4 + 128 + 1024, &cfg));
-  // split the key positions over enough CTAs to fill the machine at two CTAs per SM (one wave); a CTA keeps at most
-  // 8 position tiles (256 TMEM columns, two CTAs per SM) resident
+  a.vec4 = (L % 4 == 0 && L >= 4 && ((reinterpret_cast<uintptr_t>(ar) | reinterpret_cast<uintptr_t>(ac)) & 15) == 0) ? 1 : 0;
+  // split the key positions over enough CTAs to fill the machine at two CTAs per SM (one wave).  TMEM: 32 accumulator
+  // columns per tile + 64 per P operand buffer; 256 columns per CTA keep two CTAs per SM (<= 4 tiles with two operand
+  // buffers, <= 6 with one), else one CTA takes all 512 (<= 12 tiles)
   int num_sms = 0;
   CDETR_CHECK_CUDA(cdetr_num_sms(&num_sms));
   const int ntile = (H * W + 127) / 128;
   int nsplit = 1;
   while (nsplit * 2 <= ntile && nh * B * nsplit * 2 <= 2 * num_sms) nsplit *= 2;
-  while ((ntile + nsplit - 1) / nsplit > 8) ++nsplit;
+  while ((ntile + nsplit - 1) / nsplit > 12) ++nsplit;
   a.tiles_per_cta = (ntile + nsplit - 1) / nsplit;
   nsplit = (ntile + a.tiles_per_cta - 1) / a.tiles_per_cta;
+  a.p_bufs = (a.tiles_per_cta <= 4 || a.tiles_per_cta > 6) ? 2 : 1;
+  a.tmem_cols = a.tiles_per_cta * 32 + a.p_bufs * 64 <= 256 ? 256 : 512;
+  // shared memory: dO stages + the staged maps (double-buffered: the next query block's maps are prefetched)
+  const size_t map_bytes = 2 * (size_t)a.kp * MAP_LD * sizeof(float);
+  a.map_bufs = 2;
+  a.d_bufs = 2;
+  const size_t smem = (size_t)a.d_bufs * 2 * DO_PLANE_BYTES + a.map_bufs * map_bytes + 128 + 1024;
+  static DevAttrCache cfg = {};
+  CDETR_CHECK_CUDA(cdetr_ensure_smem(rcda_bwd_v_tc_kernel, 4 * DO_PLANE_BYTES + 2 * 2 * 64 * MAP_LD * 4 + 128 + 1024, &cfg));
   rcda_bwd_v_tc_kernel<<<dim3(nh, B, nsplit), 320, smem, reinterpret_cast<cudaStream_t>(s)>>>(tm, a);
   CDETR_CHECK_LAUNCH();
   return 0;
