@@ -147,6 +147,7 @@ _SIGS = {
     "cdetr_to_split": "plilS",
     "cdetr_from_split": "Slipl",
     "cdetr_stem_im2col": "piiiS",
+    "cdetr_stem_conv": "piiiSpS",
     "cdetr_im2col3x3": "SiiiiiiS",
     "cdetr_col2im3x3": "SiiiiiiSS",
     "cdetr_maxpool3x3s2": "SiiiiS",

@@ -682,11 +682,6 @@ struct TcBwdVArgs {
   int vec4;            // L % 4 == 0 and 16-byte aligned maps: stage them with 16-byte cp.async
 };
 
-__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
 
 __global__ void __launch_bounds__(320, 2)
 rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a) {

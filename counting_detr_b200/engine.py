@@ -177,6 +177,7 @@ class Engine:
         self.dec_bv = torch.zeros(D * E_, device=device)
         self.dec_wt = {k: torch.zeros(2, E_, D * E_, device=device, dtype=bf) for k in ("kr", "kc", "v")}
         self.hoist_dec = not os.environ.get("CDETR_NO_DEC_HOIST")
+        self.stem_fused = not os.environ.get("CDETR_NO_STEM_FUSED")      # A/B + tests of the im2col + GEMM lowering
         stage_sizes = [(l, l.n_out * l.k) for l in self.lins.values() if l.trainable and l.taps > 1]
         total = sum(_r8(s) for s in sizes) + sum(_r8(s) for _, s in stage_sizes)
         self.grad_flat = torch.zeros(total, device=device)
@@ -493,10 +494,14 @@ class Engine:
         B, _, S1, S2 = image.shape
         sv = self.saved
         H0, W0 = (S1 + 6 - 7) // 2 + 1, (S2 + 6 - 7) // 2 + 1
-        col = self.sbuf("stem_col", B * H0 * W0, 152)
-        L.call("cdetr_stem_im2col", image, B, S1, S2, col)
         a0 = self.sbuf("stem_out", B * H0 * W0, 64)
-        self.lins["stem"].fwd(col, B * H0 * W0, out_split=a0, relu=True)
+        stem = self.lins["stem"]
+        if self.stem_fused:      # conv 7x7 s2 + FrozenBN + ReLU in one kernel: the 637 MB im2col matrix never exists
+            L.call("cdetr_stem_conv", image, B, S1, S2, stem.w, stem.bias, a0)
+        else:
+            col = self.sbuf("stem_col", B * H0 * W0, 152)
+            L.call("cdetr_stem_im2col", image, B, S1, S2, col)
+            stem.fwd(col, B * H0 * W0, out_split=a0, relu=True)
         H, W = (H0 + 2 - 3) // 2 + 1, (W0 + 2 - 3) // 2 + 1
         x = self.sbuf("pool_out", B * H * W, 64)
         L.call("cdetr_maxpool3x3s2", a0, B, H0, W0, 64, x)

@@ -124,6 +124,11 @@ int cdetr_unpack_conv_grad(const float* g, int cout, int cin, int taps, float* g
 int cdetr_to_split(const float* x, int64_t rows, int cols, int64_t ld_x, cdetr_split_t dst, cdetr_stream_t s);
 int cdetr_from_split(cdetr_split_t src, int64_t rows, int cols, float* y, int64_t ld_y, cdetr_stream_t s);
 int cdetr_stem_im2col(const float* img_nchw, int B, int H, int W, cdetr_split_t col, cdetr_stream_t s);
+/* the whole stem in one kernel, no im2col matrix: out[(b,oy,ox), 0:64] = relu(conv7x7 s2 p3(img) + shift); w = FrozenBN-
+   scaled conv1 weights [64, ld >= 152] split bf16 with k = (r*7 + s)*3 + c, shift = FrozenBN shift [64]
+   (A2/models/resnet.py:263-271, A2/models/backbone.py:22-60) */
+int cdetr_stem_conv(const float* img_nchw, int B, int H, int W, cdetr_split_t w, const float* shift, cdetr_split_t out,
+                    cdetr_stream_t s);
 int cdetr_im2col3x3(cdetr_split_t x, int B, int H, int W, int C, int stride, int dil, cdetr_split_t col,
                     cdetr_stream_t s);
 int cdetr_col2im3x3(cdetr_split_t dcol, int B, int H, int W, int C, int stride, int dil, cdetr_split_t mask,

@@ -52,6 +52,21 @@ for stride, dil in [(1, 1), (2, 1), (1, 2)]:
                    dilation=dil, padding=dil, stride=stride).permute(0, 2, 3, 1)
     refdx = refdx * (L.from_split(xs_mask).reshape(B, H, W, C) > 0)
     report(f"col2im s{stride} d{dil}", L.from_split(dx).reshape(B, H, W, C), refdx, 1e-5)
+# fused stem (conv 7x7 s2 p3 + FrozenBN + ReLU, no im2col matrix) vs torch conv2d in fp64, odd sizes / partial patches
+for (Bs, Hs, Ws) in [(2, 64, 96), (1, 70, 90), (3, 33, 47), (1, 256, 256)]:
+    img = torch.randn(Bs, 3, Hs, Ws, device=dev)
+    w7 = torch.randn(64, 3, 7, 7, device=dev) * 0.1
+    sc = torch.rand(64, device=dev) + 0.5
+    sh = torch.randn(64, device=dev)
+    wp = torch.zeros(64, 152, device=dev)
+    wp[:, :147] = (w7 * sc[:, None, None, None]).permute(0, 2, 3, 1).reshape(64, 147)      # k = (r*7 + s)*3 + c
+    wps = L.to_split(wp)
+    Hs0, Ws0 = (Hs + 6 - 7) // 2 + 1, (Ws + 6 - 7) // 2 + 1
+    o = zs(Bs * Hs0 * Ws0, 64)
+    L.call("cdetr_stem_conv", img, Bs, Hs, Ws, wps, sh, o)
+    wn = L.from_split(wps)[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2)
+    ref = torch.relu(F.conv2d(img.double(), wn.double(), stride=2, padding=3) + sh.double()[None, :, None, None])
+    report(f"stem_conv B{Bs} {Hs}x{Ws}", L.from_split(o).reshape(Bs, Hs0, Ws0, 64), ref.permute(0, 2, 3, 1), 2e-5)
 y = zs(B * 6 * 5, C)
 L.call("cdetr_maxpool3x3s2", xs, B, H, W, C, y)
 report("maxpool", L.from_split(y).reshape(B, 6, 5, C), F.max_pool2d(xn.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1), 1e-7)
