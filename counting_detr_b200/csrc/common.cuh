@@ -85,6 +85,7 @@ struct CdetrTuning {
   int pdl;            // CDETR_PDL=1: programmatic dependent launch of the GEMM
   int pdl_light;      // CDETR_PDL_LIGHT=1: ... of the light kernels
   int mha_legacy;     // CDETR_MHA_LEGACY=1: CUDA-core decoder self-attention
+  int rcda_stream;    // CDETR_RCDA_STREAM: 1 = streamed-V RCDA kernels (rcda_tc64.cu) also for maps <= 32x32, 0 = resident V
 };
 static inline const CdetrTuning& cdetr_tuning() {
   static const CdetrTuning t = [] {
@@ -93,6 +94,7 @@ static inline const CdetrTuning& cdetr_tuning() {
     x.gemm_pair = geti("CDETR_GEMM_PAIR", -1);
     x.gemm_tma_epi = geti("CDETR_GEMM_TMA_EPI", 1);
     x.gemm_resident = geti("CDETR_GEMM_RESIDENT", 0);
+    x.rcda_stream = geti("CDETR_RCDA_STREAM", 0);
     x.gemm_stages = geti("CDETR_GEMM_STAGES", 0);
     x.gemm_epi_debug = geti("CDETR_GEMM_EPI_DEBUG", 0);
     x.pdl = geti("CDETR_PDL", 0);

@@ -918,7 +918,7 @@ extern "C" int cdetr_rcda_fwd_tc(int B, int L, int H, int W, int E, int nh, cons
   CDETR_CHECK_ARG(qr && qc && kr && kc && v.base && ar && ac && o.base, "rcda_fwd_tc: null pointer");
   CDETR_CHECK_ARG(v.ld % 8 == 0 && v.plane % 8 == 0 && (reinterpret_cast<uintptr_t>(v.base) & 15) == 0,
                   "rcda_fwd_tc: V must be 16-byte aligned with ld/plane multiples of 8");
-  if (H > HP || W > WP)
+  if (H > HP || W > WP || (cdetr_tuning().rcda_stream & 1))
     return rcda_fwd_tc64_launch(B, L, H, W, E, nh, qr, qc, kr, kc, v, mask_row, mask_col, ar, ac, o,
                                 reinterpret_cast<cudaStream_t>(s));
   EncodeTiledFn fn = encode_fn();
@@ -972,7 +972,7 @@ extern "C" int cdetr_rcda_bwd_q_tc(int B, int L, int H, int W, int E, int nh, co
   CDETR_CHECK_ARG(H >= 1 && W >= 1 && H <= 64 && W <= 64, "rcda_bwd_q_tc: H, W must be <= 64");
   CDETR_CHECK_ARG(kr && kc && v.base && ar && ac && d_o && dsr && dsc && dqr.base && dqc.base, "rcda_bwd_q_tc: null pointer");
   CDETR_CHECK_ARG(dqr.ld == dqc.ld, "rcda_bwd_q_tc: gradient tensors must share ld");
-  if (H > HP || W > WP)
+  if (H > HP || W > WP || (cdetr_tuning().rcda_stream & 2))
     return rcda_bwd_q_tc64_launch(B, L, H, W, E, nh, kr, kc, v, ar, ac, d_o, dsr, dsc, dqr, dqc,
                                   reinterpret_cast<cudaStream_t>(s));
   CUtensorMap tm;
