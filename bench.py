@@ -488,10 +488,12 @@ def run_ours(args):
         traffic, traffic_note = None, None
         if args.workload == "c3" and world == 1:
             try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic_c3.json")))
+                tpath = next(p for p in (os.path.join(ROOT, "profiles", f) for f in ("r02_gemm_traffic_c3.json", "r01_gemm_traffic_c3.json"))
+                             if os.path.exists(p))
+                tj = json.load(open(tpath))
                 traffic = tj["dram_bytes"] / max(tj["launches"], 1)
                 traffic_note = (f"dram__bytes_read+write summed over the {tj['launches']} GEMM launches of one step "
-                                f"= {tj['dram_bytes'] / 1e9:.2f} GB per step (ncu, cold cache); value = mean bytes per launch")
+                                f"= {tj['dram_bytes'] / 1e9:.2f} GB per step (ncu, cold cache, {os.path.basename(tpath)}); value = mean bytes per launch")
             except Exception:
                 pass
         roofline = {"bound": "tensor", "kernel": "gemm_split_kernel (tcgen05 split-bf16 GEMM family: conv/linear fwd, dgrad, wgrad)",

@@ -11,7 +11,11 @@
 // K-major SWIZZLE_128B in shared memory, staged once per CTA) by tcgen05.mma with the A operand read from TMEM (three
 // bf16 products hi*lo + lo*hi + hi*hi, fp32 accumulation); the epilogue adds the FrozenBN shift, applies the ReLU and
 // writes split-bf16 NHWC rows.  HBM traffic: the image once (+ halo re-reads from L2) and the activation once.
-// TMEM per CTA: 64 accumulator + 80 + 80 operand columns (256 allocated: two CTAs per SM overlap build / MMA / store).
+// One CTA per SM, 16 builder warps (4 per TMEM lane quarter, a quarter of the window values each) + the MMA warp; the
+// operand rows and the accumulator are double-buffered in TMEM (2 x 160 + 2 x 64 of the 512 columns), so the tensor core
+// works on tile t while the builders store tile t-1 and build tile t+1: nobody waits for an MMA in steady state
+// (the first version - 8 builder warps, single buffers, two CTAs per SM - spent 23 % of its stall samples and 20 % of
+// its issued instructions in barrier spins: 207 us; profiles/r02_final_ncu_attn_stem_summary.txt).
 #include "common.cuh"
 #include "../../include/cdetr.h"
 
@@ -21,11 +25,13 @@ constexpr int PH = 8, PW = 16;                 // output patch = 128 pixels
 constexpr int IH = 2 * PH + 5;                 // 21 input rows
 constexpr int IWH = PW + 3;                    // 19 columns per parity (37 input columns de-interleaved: even | odd)
 constexpr int ROW_LD = 40;                     // floats per staged input row: [even 19 | pad | odd 18 at +20]; 2*40 = 16 mod 32
-constexpr int PATCH_FLOATS = 3 * IH * ROW_LD;  // 2520
+constexpr int PATCH_FLOATS = 2528;              // 3 * 21 * 40 = 2520 floats, padded to a 128-byte multiple
 constexpr int KP = 160;                        // 147 window values padded to 10 k-steps of 16
 constexpr int KSTEPS = KP / 16;
 constexpr uint32_t W_PLANE_BYTES = 3 * 64 * 128;   // 3 k-blocks of [64 rows x 64 k] bf16, SW128 K-major
-constexpr uint32_t COL_ACC = 0, COL_AHI = 64, COL_ALO = 64 + KP / 2;
+constexpr uint32_t COL_ACC = 0, COL_A = 128, A_COLS = KP;   // acc buffer i at 64 i; operand buffer i at 128 + 160 i: hi 80 | lo 80
+constexpr int NPATCH = 3;                                   // input-window buffers: two tiles of cp.async lead
+constexpr int NBUILD = 16;                                  // builder warps
 
 struct StemArgs {
   const float* img;
@@ -38,7 +44,11 @@ struct StemArgs {
   uint32_t idesc;
 };
 
-// window value k of the pixel whose de-interleaved window starts at `base` (float index in the staged patch)
+// Staged window layouts (floats).  The 37 input columns a patch touches are de-interleaved by parity so that the 16
+// pixels of a patch row read consecutive words (the two patch rows of a warp land 16 banks apart).
+//   [c][r][ROW_LD = 40]: even columns at +0, odd at +20.  (A TMA box cannot do this: the TMA unit has no element stride
+//   along the innermost dimension; the window is staged with 4-byte cp.async, two tiles ahead.)
+// window value k of the pixel whose de-interleaved window starts at `base` (byte address in the staged patch)
 template <int K>
 __device__ __forceinline__ float window_value(uint32_t base) {
   if (K >= 147) return 0.0f;
@@ -47,44 +57,54 @@ __device__ __forceinline__ float window_value(uint32_t base) {
 }
 
 template <int K0>
-__device__ __forceinline__ void build_k16(uint32_t base, uint32_t taddr_hi, uint32_t taddr_lo) {
-  uint32_t hw[8], lw[8];
-  float v[16];
-  // template recursion by hand: 16 consecutive k
-  v[0] = window_value<K0 + 0>(base);   v[1] = window_value<K0 + 1>(base);
-  v[2] = window_value<K0 + 2>(base);   v[3] = window_value<K0 + 3>(base);
-  v[4] = window_value<K0 + 4>(base);   v[5] = window_value<K0 + 5>(base);
-  v[6] = window_value<K0 + 6>(base);   v[7] = window_value<K0 + 7>(base);
-  v[8] = window_value<K0 + 8>(base);   v[9] = window_value<K0 + 9>(base);
-  v[10] = window_value<K0 + 10>(base); v[11] = window_value<K0 + 11>(base);
-  v[12] = window_value<K0 + 12>(base); v[13] = window_value<K0 + 13>(base);
-  v[14] = window_value<K0 + 14>(base); v[15] = window_value<K0 + 15>(base);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) split_bf16_pair(v[2 * i], v[2 * i + 1], hw[i], lw[i]);
-  tmem_st_32x32b_x8(taddr_hi + (uint32_t)(K0 / 2), hw);
-  tmem_st_32x32b_x8(taddr_lo + (uint32_t)(K0 / 2), lw);
+__device__ __forceinline__ void build_k8(uint32_t base, uint32_t taddr_hi, uint32_t taddr_lo) {
+  uint32_t hw[4], lw[4];
+  split_bf16_pair(window_value<K0 + 0>(base), window_value<K0 + 1>(base), hw[0], lw[0]);
+  split_bf16_pair(window_value<K0 + 2>(base), window_value<K0 + 3>(base), hw[1], lw[1]);
+  split_bf16_pair(window_value<K0 + 4>(base), window_value<K0 + 5>(base), hw[2], lw[2]);
+  split_bf16_pair(window_value<K0 + 6>(base), window_value<K0 + 7>(base), hw[3], lw[3]);
+  tmem_st_32x32b_x4(taddr_hi + (uint32_t)(K0 / 2), hw);
+  tmem_st_32x32b_x4(taddr_lo + (uint32_t)(K0 / 2), lw);
+}
+template <int K0>
+__device__ __forceinline__ void build_k40(uint32_t base, uint32_t t_hi, uint32_t t_lo) {
+  build_k8<K0>(base, t_hi, t_lo);      build_k8<K0 + 8>(base, t_hi, t_lo);  build_k8<K0 + 16>(base, t_hi, t_lo);
+  build_k8<K0 + 24>(base, t_hi, t_lo); build_k8<K0 + 32>(base, t_hi, t_lo);
 }
 
-__global__ void __launch_bounds__(288, 2)
+__global__ void __launch_bounds__(32 * NBUILD + 32, 1)
 stem_conv_kernel(const StemArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Ws = smem;                                               // [2 planes][3 k-blocks][64][64] bf16 SW128
-  float* patch = reinterpret_cast<float*>(Ws + 2 * W_PLANE_BYTES);  // [2 buffers][3][IH][ROW_LD]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(patch + 2 * PATCH_FLOATS);
-  uint64_t* a_full = bars;        // operand rows of the tile are in TMEM (8 builder warps)
-  uint64_t* mma_done = bars + 1;  // accumulator complete, operand columns free
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2);
+  float* patch = reinterpret_cast<float*>(Ws + 2 * W_PLANE_BYTES);  // [NPATCH buffers][3][IH][ROW_LD]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(patch + NPATCH * PATCH_FLOATS);
+  uint64_t* a_full = bars;        // [2] operand rows of the tile are in TMEM buffer i (16 builder warps)
+  uint64_t* mma_done = bars + 2;  // [2] accumulator i complete, operand buffer i free
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 4);
+  float* shift_s = reinterpret_cast<float*>(bars + 6);    // FrozenBN shift, read back as warp-wide broadcasts
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    mbar_init(a_full, 8);
-    mbar_init(mma_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], NBUILD);
+      mbar_init(&mma_done[i], 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 8) {
-    tmem_alloc(tmem_holder, 256);
+  if (warp == NBUILD) {
+    tmem_alloc(tmem_holder, 512);
     tmem_relinquish();
+  }
+  if (threadIdx.x < 64) shift_s[threadIdx.x] = __ldg(a.shift + threadIdx.x);
+  // tiles of this CTA (blockIdx.x, + gridDim.x, ...), decoded once
+  int2* tiles = reinterpret_cast<int2*>(shift_s + 64);
+  const int n_my = a.ntiles > (int)blockIdx.x ? (a.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  for (int i = threadIdx.x; i < n_my; i += blockDim.x) {
+    const int tile = blockIdx.x + i * gridDim.x;
+    const int tpi = a.tiles_y * a.tiles_x;
+    const int b = tile / tpi, tr = tile % tpi;
+    tiles[i] = make_int2(b, ((tr / a.tiles_x) << 16) | (tr % a.tiles_x));
   }
   // weights -> shared memory in the K-major SWIZZLE_128B operand layout (16-byte chunks; k >= ld_w is zero padding)
   for (int i = threadIdx.x; i < 2 * 64 * 24; i += blockDim.x) {
@@ -101,87 +121,84 @@ stem_conv_kernel(const StemArgs a) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  const int t_begin = blockIdx.x, t_step = gridDim.x;
-  if (warp == 8) {
+  if (warp == NBUILD) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       const uint32_t w_base = smem_u32(Ws);
-      int it = 0;
-      for (int tile = t_begin; tile < a.ntiles; tile += t_step, ++it) {
-        mbar_wait_sleep(a_full, (uint32_t)it & 1u);
+      for (int it = 0; it < n_my; ++it) {
+        const uint32_t buf = (uint32_t)it & 1u;
+        mbar_wait_sleep(&a_full[buf], (uint32_t)(it >> 1) & 1u);
         tc_fence_after();
+        const uint32_t acc = tmem_base + COL_ACC + 64u * buf;
+        const uint32_t a0 = tmem_base + COL_A + A_COLS * buf;
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
           const uint32_t boff = (uint32_t)(ks >> 2) * 8192u + (uint32_t)(ks & 3) * 32u;
           const uint64_t b_hi = make_smem_desc_sw128(w_base + boff, 16, 1024);
           const uint64_t b_lo = make_smem_desc_sw128(w_base + W_PLANE_BYTES + boff, 16, 1024);
-          const uint32_t a_hi = tmem_base + COL_AHI + (uint32_t)ks * 8u;
-          const uint32_t a_lo = tmem_base + COL_ALO + (uint32_t)ks * 8u;
-          umma_bf16_ts(tmem_base + COL_ACC, a_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u);
-          umma_bf16_ts(tmem_base + COL_ACC, a_lo, b_hi, a.idesc, 1);
-          umma_bf16_ts(tmem_base + COL_ACC, a_hi, b_hi, a.idesc, 1);
+          const uint32_t a_hi = a0 + (uint32_t)ks * 8u;
+          const uint32_t a_lo = a_hi + KP / 2;
+          umma_bf16_ts(acc, a_hi, b_lo, a.idesc, ks > 0 ? 1u : 0u);
+          umma_bf16_ts(acc, a_lo, b_hi, a.idesc, 1);
+          umma_bf16_ts(acc, a_hi, b_hi, a.idesc, 1);
         }
-        umma_commit(mma_done);
+        umma_commit(&mma_done[buf]);
       }
     }
   } else {
-    // ------------------------------ builders / epilogue (8 warps) ------------------------------
-    const int ct = threadIdx.x;             // 0..255
+    // ------------------------------ builders / epilogue (16 warps) ------------------------------
     const int quarter = warp & 3;           // TMEM lane quarter of this warp
-    const int khalf = warp >> 2;            // k 0..79 / 80..159 (build), output channels 0..31 / 32..63 (epilogue)
+    const int kq = warp >> 2;               // k 40 kq .. 40 kq + 39 (build), output channels 16 kq .. 16 kq + 15 (epilogue)
     const int ml = quarter * 32 + lane;     // pixel of the patch = TMEM lane
     const int py = ml / PW, px = ml % PW;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int tiles_per_img = a.tiles_y * a.tiles_x;
+    // this CTA's tiles, decoded once: {sample b, (ty << 16) | tx}; no divisions in the tile loop
+    auto tile_info = [&](int i) -> int2 { return tiles[i]; };
 
-    auto stage = [&](int tile, float* dst) {     // input window of one patch -> shared memory (zeros outside the image)
-      const int b = tile / tiles_per_img, tr = tile % tiles_per_img;
-      const int iy0 = (tr / a.tiles_x) * PH * 2 - 3, ix0 = (tr % a.tiles_x) * PW * 2 - 3;
-      for (int i = ct; i < 3 * IH * 37; i += 256) {
-        const int x = i % 37, r = (i / 37) % IH, c = i / (37 * IH);
-        const int iy = iy0 + r, ix = ix0 + x;
-        float* d = dst + (c * IH + r) * ROW_LD + (x & 1) * 20 + (x >> 1);
-        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) cp_async_4(d, a.img + (((int64_t)b * 3 + c) * a.H + iy) * a.W + ix);
-        else *d = 0.0f;
+    // input window of one patch -> shared memory (zeros outside the image).  Warp w takes the (channel, row) pairs
+    // w, w + 16, ... of the 63; lane l the columns l and l + 32.  Everything that does not depend on the tile is hoisted.
+    const int sx0 = lane, sx1 = lane + 32;
+    const uint32_t so0 = 4u * (uint32_t)((sx0 & 1) * 20 + (sx0 >> 1)), so1 = 4u * (uint32_t)((sx1 & 1) * 20 + (sx1 >> 1));
+    int prow[4], pimg[4];                      // window row r and c * H * W of this warp's pairs
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pr = warp + NBUILD * j;
+      prow[j] = pr % IH;
+      pimg[j] = (pr / IH) * a.H * a.W;
+    }
+    auto stage = [&](int i, uint32_t dst) {    // dst: shared-memory address of the patch buffer
+      const int2 ti = tile_info(i);
+      const int iy0 = (ti.y >> 16) * (PH * 2) - 3, ix0 = (ti.y & 0xffff) * (PW * 2) - 3;
+      const bool ok0 = ix0 + sx0 >= 0 && ix0 + sx0 < a.W;
+      const bool ok1 = sx1 < 37 && ix0 + sx1 >= 0 && ix0 + sx1 < a.W;
+      const float* img_b = a.img + ti.x * (3 * a.H * a.W) + ix0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pr = warp + NBUILD * j;
+        if (pr < 3 * IH) {
+          const int iy = iy0 + prow[j];
+          const bool rok = iy >= 0 && iy < a.H;
+          const float* src = img_b + (pimg[j] + iy * a.W);
+          const uint32_t d = dst + (uint32_t)pr * (ROW_LD * 4u);
+          if (rok && ok0) cp_async_4s(d + so0, src + sx0); else sts32(d + so0, 0.0f);
+          if (sx1 < 37) { if (rok && ok1) cp_async_4s(d + so1, src + sx1); else sts32(d + so1, 0.0f); }
+        }
       }
     };
-
-    if (t_begin < a.ntiles) stage(t_begin, patch);
-    int it = 0;
-    for (int tile = t_begin; tile < a.ntiles; tile += t_step, ++it) {
-      float* cur = patch + (it & 1) * PATCH_FLOATS;
-      cp_async_wait_all();
-      asm volatile("bar.sync 1, 256;" ::: "memory");       // this patch has landed; the other buffer is no longer read
-      if (tile + t_step < a.ntiles) stage(tile + t_step, patch + ((it + 1) & 1) * PATCH_FLOATS);
-      // ---- build this pixel's operand row: window value k = patch[c][2 py + r][2 px + s]
-      const uint32_t base = smem_u32(cur) + 4u * (uint32_t)(2 * py * ROW_LD + px);
-      const uint32_t t_hi = lane_addr + COL_AHI, t_lo = lane_addr + COL_ALO;
-      if (khalf == 0) {
-        build_k16<0>(base, t_hi, t_lo);  build_k16<16>(base, t_hi, t_lo); build_k16<32>(base, t_hi, t_lo);
-        build_k16<48>(base, t_hi, t_lo); build_k16<64>(base, t_hi, t_lo);
-      } else {
-        build_k16<80>(base, t_hi, t_lo);  build_k16<96>(base, t_hi, t_lo); build_k16<112>(base, t_hi, t_lo);
-        build_k16<128>(base, t_hi, t_lo); build_k16<144>(base, t_hi, t_lo);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(a_full);
-      // ---- epilogue: accumulator row of this pixel, 32 channels per thread
-      mbar_wait_sleep(mma_done, (uint32_t)it & 1u);
-      tc_fence_after();
-      uint32_t t[32];
-      tmem_ld_32x32b_x32(lane_addr + COL_ACC + (uint32_t)khalf * 32u, t);
+    // accumulator row of this pixel (16 channels per thread) of tile `tile` from accumulator buffer `buf` -> output
+    auto store_tile = [&](int i, uint32_t buf) {
+      uint32_t t[16];
+      tmem_ld_32x32b_x16(lane_addr + COL_ACC + 64u * buf + (uint32_t)kq * 16u, t);
       tmem_ld_wait();
-      tc_fence_before();      // the next tile's MMAs (ordered behind our a_full arrival) overwrite these columns
-      const int b = tile / tiles_per_img, tr = tile % tiles_per_img;
-      const int oy = (tr / a.tiles_x) * PH + py, ox = (tr % a.tiles_x) * PW + px;
+      tc_fence_before();      // a later tile's MMAs (ordered behind an a_full arrival of this warp) overwrite these columns
+      const int2 ti = tile_info(i);
+      const int oy = (ti.y >> 16) * PH + py, ox = (ti.y & 0xffff) * PW + px;
       if (oy < a.Ho && ox < a.Wo) {
-        const int64_t off = (((int64_t)b * a.Ho + oy) * a.Wo + ox) * a.ld_o + khalf * 32;
+        const int64_t off = ((int64_t)ti.x * a.Ho * a.Wo + oy * a.Wo + ox) * a.ld_o + kq * 16;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.shift + khalf * 32 + g * 8));
-          const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.shift + khalf * 32 + g * 8 + 4));
+        for (int g = 0; g < 2; ++g) {
+          const float4 s0 = lds128(smem_u32(shift_s + kq * 16 + g * 8));
+          const float4 s1 = lds128(smem_u32(shift_s + kq * 16 + g * 8 + 4));
           const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
           uint32_t hw[4], lw[4];
 #pragma unroll
@@ -194,17 +211,55 @@ stem_conv_kernel(const StemArgs a) {
           reinterpret_cast<uint4*>(a.o_lo + off)[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
       }
+    };
+
+    const uint32_t patch_s = smem_u32(patch);
+    // windows travel two tiles ahead (cp.async path: one group per tile, empty groups past the end keep the count uniform)
+    if (n_my > 0) stage(0, patch_s);
+    cp_async_commit();
+    if (n_my > 1) stage(1, patch_s + PATCH_FLOATS * 4u);
+    cp_async_commit();
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t buf = (uint32_t)it & 1u;
+      const uint32_t pbuf = (uint32_t)(it % NPATCH);
+      cp_async_wait_group<1>();                            // this tile's window has landed (the next one may be in flight)
+      asm volatile("bar.sync 1, 512;" ::: "memory");       // ... for every thread; buffer (it+2) % 3 is no longer read
+      // operand buffer `buf` was read by the MMAs of tile it-2: this thread saw them complete before it stored tile it-2
+      // ---- build this pixel's operand row: window value k = patch[c][2 py + r][2 px + s]
+      const uint32_t base = patch_s + pbuf * (PATCH_FLOATS * 4u) + 4u * (uint32_t)(2 * py * ROW_LD + px);
+      const uint32_t t_hi = lane_addr + COL_A + A_COLS * buf, t_lo = t_hi + KP / 2;
+      if (kq == 0) build_k40<0>(base, t_hi, t_lo);
+      else if (kq == 1) build_k40<40>(base, t_hi, t_lo);
+      else if (kq == 2) build_k40<80>(base, t_hi, t_lo);
+      else build_k40<120>(base, t_hi, t_lo);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[buf]);
+      if (it + 2 < n_my) stage(it + 2, patch_s + (uint32_t)((it + 2) % NPATCH) * (PATCH_FLOATS * 4u));
+      cp_async_commit();
+      // ---- store the PREVIOUS tile: its MMAs ran while this one was built
+      if (it > 0) {
+        mbar_wait_sleep(&mma_done[buf ^ 1u], (uint32_t)((it - 1) >> 1) & 1u);
+        tc_fence_after();
+        store_tile(it - 1, buf ^ 1u);
+      }
+    }
+    if (n_my > 0) {
+      const uint32_t buf = (uint32_t)(n_my - 1) & 1u;
+      mbar_wait_sleep(&mma_done[buf], (uint32_t)((n_my - 1) >> 1) & 1u);
+      tc_fence_after();
+      store_tile(n_my - 1, buf);
     }
     cp_async_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == NBUILD) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
-
 
 }  // namespace
 
@@ -228,13 +283,16 @@ extern "C" int cdetr_stem_conv(const float* img, int B, int H, int W, cdetr_spli
   a.tiles_y = (a.Ho + PH - 1) / PH; a.tiles_x = (a.Wo + PW - 1) / PW;
   a.ntiles = B * a.tiles_y * a.tiles_x;
   a.idesc = make_idesc_bf16_f32(128, 64, 0, 0);
-  const size_t smem = 2 * W_PLANE_BYTES + 2 * PATCH_FLOATS * sizeof(float) + 64 + 1024;
-  static DevAttrCache cfg = {};
-  CDETR_CHECK_CUDA(cdetr_ensure_smem(stem_conv_kernel, smem, &cfg));
+  CDETR_CHECK_ARG((int64_t)B * 3 * H * W < (int64_t)1 << 31 && a.tiles_y < 65536 && a.tiles_x < 65536, "stem_conv: batch too large for 32-bit image offsets");
   int num_sms = 0;
   CDETR_CHECK_CUDA(cdetr_num_sms(&num_sms));
-  const int grid = a.ntiles < 2 * num_sms ? a.ntiles : 2 * num_sms;
-  stem_conv_kernel<<<grid, 288, smem, reinterpret_cast<cudaStream_t>(s)>>>(a);
+  const int grid = a.ntiles < num_sms ? a.ntiles : num_sms;
+  const int n_my_max = (a.ntiles + grid - 1) / grid;
+  const size_t smem = 2 * W_PLANE_BYTES + NPATCH * PATCH_FLOATS * sizeof(float) + 96 + 256 + (size_t)n_my_max * 8 + 1024;
+  CDETR_CHECK_ARG(smem <= 200 * 1024, "stem_conv: too many tiles per CTA (%d)", n_my_max);
+  static DevAttrCache cfg = {};
+  CDETR_CHECK_CUDA(cdetr_ensure_smem(stem_conv_kernel, 200 * 1024, &cfg));
+  stem_conv_kernel<<<grid, 32 * NBUILD + 32, smem, reinterpret_cast<cudaStream_t>(s)>>>(a);
   CDETR_CHECK_LAUNCH();
   return 0;
 }
