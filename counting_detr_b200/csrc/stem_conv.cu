@@ -10,7 +10,10 @@
 // in tensor memory (tcgen05.st); one thread multiplies it with the FrozenBN-folded weights ([64 x 160] split bf16,
 // K-major SWIZZLE_128B in shared memory, staged once per CTA) by tcgen05.mma with the A operand read from TMEM (three
 // bf16 products hi*lo + lo*hi + hi*hi, fp32 accumulation); the epilogue adds the FrozenBN shift, applies the ReLU and
-// writes split-bf16 NHWC rows.  HBM traffic: the image once (+ halo re-reads from L2) and the activation once.
+// leaves through a swizzled shared-memory staging tile and ONE TMA store per plane and patch (box {64 c, 16 x, 8 y}, edges
+// clipped by the TMA unit): per-thread 16-byte global stores (32 rows per warp instruction) kept the L1TEX pipe busy
+// enough to delay the window loads behind them.  HBM traffic: the image once (+ halo re-reads from L2) and the
+// activation once.
 // One CTA per SM, 16 builder warps (4 per TMEM lane quarter, a quarter of the window values each) + the MMA warp; the
 // operand rows and the accumulator are double-buffered in TMEM (2 x 160 + 2 x 64 of the 512 columns), so the tensor core
 // works on tile t while the builders store tile t-1 and build tile t+1: nobody waits for an MMA in steady state
@@ -23,13 +26,13 @@ namespace {
 
 constexpr int PH = 8, PW = 16;                 // output patch = 128 pixels
 constexpr int IH = 2 * PH + 5;                 // 21 input rows
-constexpr int IWH = PW + 3;                    // 19 columns per parity (37 input columns de-interleaved: even | odd)
 constexpr int ROW_LD = 40;                     // floats per staged input row: [even 19 | pad | odd 18 at +20]; 2*40 = 16 mod 32
 constexpr int PATCH_FLOATS = 2528;              // 3 * 21 * 40 = 2520 floats, padded to a 128-byte multiple
 constexpr int KP = 160;                        // 147 window values padded to 10 k-steps of 16
 constexpr int KSTEPS = KP / 16;
 constexpr uint32_t W_PLANE_BYTES = 3 * 64 * 128;   // 3 k-blocks of [64 rows x 64 k] bf16, SW128 K-major
 constexpr uint32_t COL_ACC = 0, COL_A = 128, A_COLS = KP;   // acc buffer i at 64 i; operand buffer i at 128 + 160 i: hi 80 | lo 80
+constexpr uint32_t OUT_PLANE_BYTES = 128 * 64 * 2;          // one plane of a patch's output tile: 16 KB
 constexpr int NPATCH = 3;                                   // input-window buffers: two tiles of cp.async lead
 constexpr int NBUILD = 16;                                  // builder warps
 
@@ -73,10 +76,11 @@ __device__ __forceinline__ void build_k40(uint32_t base, uint32_t t_hi, uint32_t
 }
 
 __global__ void __launch_bounds__(32 * NBUILD + 32, 1)
-stem_conv_kernel(const StemArgs a) {
+stem_conv_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Ws = smem;                                               // [2 planes][3 k-blocks][64][64] bf16 SW128
+  uint8_t* Os = smem;                                               // [2 buffers][2 planes][128 pixels][64 c] bf16, SW128: output staging
+  uint8_t* Ws = Os + 4 * OUT_PLANE_BYTES;                           // [2 planes][3 k-blocks][64][64] bf16 SW128
   float* patch = reinterpret_cast<float*>(Ws + 2 * W_PLANE_BYTES);  // [NPATCH buffers][3][IH][ROW_LD]
   uint64_t* bars = reinterpret_cast<uint64_t*>(patch + NPATCH * PATCH_FLOATS);
   uint64_t* a_full = bars;        // [2] operand rows of the tile are in TMEM buffer i (16 builder warps)
@@ -185,34 +189,41 @@ stem_conv_kernel(const StemArgs a) {
         }
       }
     };
-    // accumulator row of this pixel (16 channels per thread) of tile `tile` from accumulator buffer `buf` -> output
-    auto store_tile = [&](int i, uint32_t buf) {
+    // accumulator row of this pixel (16 channels per thread) of tile i from accumulator buffer `buf` -> staging tile `buf`
+    // (row = pixel, 128 bytes per plane, 16-byte chunks XOR-swizzled by the row as the TMA store's SWIZZLE_128B expects)
+    const uint32_t os = smem_u32(Os);
+    auto store_tile = [&](uint32_t buf) {
       uint32_t t[16];
       tmem_ld_32x32b_x16(lane_addr + COL_ACC + 64u * buf + (uint32_t)kq * 16u, t);
       tmem_ld_wait();
       tc_fence_before();      // a later tile's MMAs (ordered behind an a_full arrival of this warp) overwrite these columns
-      const int2 ti = tile_info(i);
-      const int oy = (ti.y >> 16) * PH + py, ox = (ti.y & 0xffff) * PW + px;
-      if (oy < a.Ho && ox < a.Wo) {
-        const int64_t off = ((int64_t)ti.x * a.Ho * a.Wo + oy * a.Wo + ox) * a.ld_o + kq * 16;
+      const uint32_t row = os + buf * (2u * OUT_PLANE_BYTES) + (uint32_t)ml * 128u;
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const float4 s0 = lds128(smem_u32(shift_s + kq * 16 + g * 8));
-          const float4 s1 = lds128(smem_u32(shift_s + kq * 16 + g * 8 + 4));
-          const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          uint32_t hw[4], lw[4];
+      for (int g = 0; g < 2; ++g) {
+        const float4 s0 = lds128(smem_u32(shift_s + kq * 16 + g * 8));
+        const float4 s1 = lds128(smem_u32(shift_s + kq * 16 + g * 8 + 4));
+        const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        uint32_t hw[4], lw[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float v0 = fmaxf(__uint_as_float(t[g * 8 + 2 * j]) + sh[2 * j], 0.0f);
-            const float v1 = fmaxf(__uint_as_float(t[g * 8 + 2 * j + 1]) + sh[2 * j + 1], 0.0f);
-            split_bf16_pair(v0, v1, hw[j], lw[j]);
-          }
-          reinterpret_cast<uint4*>(a.o_hi + off)[g] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          reinterpret_cast<uint4*>(a.o_lo + off)[g] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        for (int j = 0; j < 4; ++j) {
+          const float v0 = fmaxf(__uint_as_float(t[g * 8 + 2 * j]) + sh[2 * j], 0.0f);
+          const float v1 = fmaxf(__uint_as_float(t[g * 8 + 2 * j + 1]) + sh[2 * j + 1], 0.0f);
+          split_bf16_pair(v0, v1, hw[j], lw[j]);
         }
+        const uint32_t off = (uint32_t)(((2 * kq + g) ^ (ml & 7)) << 4);
+        sts128(row + off, hw[0], hw[1], hw[2], hw[3]);
+        sts128(row + OUT_PLANE_BYTES + off, lw[0], lw[1], lw[2], lw[3]);
       }
+      fence_proxy_async();    // generic-proxy writes -> visible to the TMA unit (after the CTA barrier that follows)
     };
-
+    // one thread: TMA stores of tile i's staging tile (both planes); coordinates {c, x, y, sample, plane}
+    auto issue_store = [&](int i) {
+      const int2 ti = tile_info(i);
+      const uint32_t src = os + (uint32_t)(i & 1) * (2u * OUT_PLANE_BYTES);
+      tma_store_5d(&tmOut, src, 0, (ti.y & 0xffff) * PW, (ti.y >> 16) * PH, ti.x, 0);
+      tma_store_5d(&tmOut, src + OUT_PLANE_BYTES, 0, (ti.y & 0xffff) * PW, (ti.y >> 16) * PH, ti.x, 1);
+      bulk_commit_group();
+    };
     const uint32_t patch_s = smem_u32(patch);
     // windows travel two tiles ahead (cp.async path: one group per tile, empty groups past the end keep the count uniform)
     if (n_my > 0) stage(0, patch_s);
@@ -222,9 +233,12 @@ stem_conv_kernel(const StemArgs a) {
     for (int it = 0; it < n_my; ++it) {
       const uint32_t buf = (uint32_t)it & 1u;
       const uint32_t pbuf = (uint32_t)(it % NPATCH);
+      if (threadIdx.x == 0) bulk_wait_group_read<0>();     // the stores issued one iteration ago have left their staging tile
       cp_async_wait_group<1>();                            // this tile's window has landed (the next one may be in flight)
-      asm volatile("bar.sync 1, 512;" ::: "memory");       // ... for every thread; buffer (it+2) % 3 is no longer read
-      // operand buffer `buf` was read by the MMAs of tile it-2: this thread saw them complete before it stored tile it-2
+      asm volatile("bar.sync 1, 512;" ::: "memory");       // ... for every thread; window buffer (it+2) % 3 is no longer read;
+                                                           // the staging tile of tile it-2 is complete
+      if (threadIdx.x == 0 && it >= 2) issue_store(it - 2);
+      // operand buffer `buf` was read by the MMAs of tile it-2: this thread saw them complete before it staged tile it-2
       // ---- build this pixel's operand row: window value k = patch[c][2 py + r][2 px + s]
       const uint32_t base = patch_s + pbuf * (PATCH_FLOATS * 4u) + 4u * (uint32_t)(2 * py * ROW_LD + px);
       const uint32_t t_hi = lane_addr + COL_A + A_COLS * buf, t_lo = t_hi + KP / 2;
@@ -238,19 +252,27 @@ stem_conv_kernel(const StemArgs a) {
       if (lane == 0) mbar_arrive(&a_full[buf]);
       if (it + 2 < n_my) stage(it + 2, patch_s + (uint32_t)((it + 2) % NPATCH) * (PATCH_FLOATS * 4u));
       cp_async_commit();
-      // ---- store the PREVIOUS tile: its MMAs ran while this one was built
+      // ---- stage the PREVIOUS tile's output: its MMAs ran while this one was built; its staging tile (buf ^ 1) was last
+      // read by the TMA stores of tile it-3, drained before this iteration's barrier
       if (it > 0) {
         mbar_wait_sleep(&mma_done[buf ^ 1u], (uint32_t)((it - 1) >> 1) & 1u);
         tc_fence_after();
-        store_tile(it - 1, buf ^ 1u);
+        store_tile(buf ^ 1u);
       }
     }
+    // drain: tiles n_my-2 (staged, not yet stored) and n_my-1 (MMAs in flight)
+    if (threadIdx.x == 0) bulk_wait_group_read<0>();
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    if (threadIdx.x == 0 && n_my >= 2) issue_store(n_my - 2);
     if (n_my > 0) {
       const uint32_t buf = (uint32_t)(n_my - 1) & 1u;
       mbar_wait_sleep(&mma_done[buf], (uint32_t)((n_my - 1) >> 1) & 1u);
       tc_fence_after();
-      store_tile(n_my - 1, buf);
+      store_tile(buf);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (threadIdx.x == 0) issue_store(n_my - 1);
     }
+    if (threadIdx.x == 0) bulk_wait_group<0>();            // every store has been performed before the CTA retires
     cp_async_wait_all();
   }
   tc_fence_before();
@@ -259,6 +281,21 @@ stem_conv_kernel(const StemArgs a) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+typedef CUresult (*StemEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+StemEncodeFn stem_encode_fn() {
+  static StemEncodeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<StemEncodeFn>(p);
+  }
+  return fn;
 }
 
 }  // namespace
@@ -288,11 +325,26 @@ extern "C" int cdetr_stem_conv(const float* img, int B, int H, int W, cdetr_spli
   CDETR_CHECK_CUDA(cdetr_num_sms(&num_sms));
   const int grid = a.ntiles < num_sms ? a.ntiles : num_sms;
   const int n_my_max = (a.ntiles + grid - 1) / grid;
-  const size_t smem = 2 * W_PLANE_BYTES + NPATCH * PATCH_FLOATS * sizeof(float) + 96 + 256 + (size_t)n_my_max * 8 + 1024;
+  const size_t smem = 4 * OUT_PLANE_BYTES + 2 * W_PLANE_BYTES + NPATCH * PATCH_FLOATS * sizeof(float) + 96 + 256 + (size_t)n_my_max * 8 + 1024;
   CDETR_CHECK_ARG(smem <= 200 * 1024, "stem_conv: too many tiles per CTA (%d)", n_my_max);
+  // output map {64 c, Wo, Ho, B, 2 planes}: one box {64, 16, 8, 1, 1} = a patch's tile of one plane, edges clipped
+  StemEncodeFn enc = stem_encode_fn();
+  if (!enc) { cdetr_set_error("cuTensorMapEncodeTiled entry point unavailable"); return CDETR_ERR_CUDA; }
+  CDETR_CHECK_ARG(out.ld == 64, "stem_conv: output rows must be dense (ld == 64)");
+  CUtensorMap tm;
+  {
+    cuuint64_t gdim[5] = {64, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)B, 2};
+    cuuint64_t gstr[4] = {(cuuint64_t)out.ld * 2, (cuuint64_t)a.Wo * out.ld * 2, (cuuint64_t)a.Ho * a.Wo * out.ld * 2,
+                          (cuuint64_t)out.plane * 2};
+    cuuint32_t box[5] = {64, PW, PH, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, out.base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { cdetr_set_error("stem_conv: cuTensorMapEncodeTiled failed (%d) Ho=%d Wo=%d", (int)r, a.Ho, a.Wo); return CDETR_ERR_CUDA; }
+  }
   static DevAttrCache cfg = {};
   CDETR_CHECK_CUDA(cdetr_ensure_smem(stem_conv_kernel, 200 * 1024, &cfg));
-  stem_conv_kernel<<<grid, 32 * NBUILD + 32, smem, reinterpret_cast<cudaStream_t>(s)>>>(a);
+  stem_conv_kernel<<<grid, 32 * NBUILD + 32, smem, reinterpret_cast<cudaStream_t>(s)>>>(tm, a);
   CDETR_CHECK_LAUNCH();
   return 0;
 }
