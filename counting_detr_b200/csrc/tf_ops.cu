@@ -130,6 +130,42 @@ __global__ void reduce_axis_kernel(const float* __restrict__ x, int B, int H, in
   }
 }
 
+// reduce_axis, four channels per thread (E % 4 == 0, 16-byte aligned fp32 operands, no split output): the reduced axis is
+// walked with independent 16-byte loads, 8 in flight
+__global__ void reduce_axis4_kernel(const float4* __restrict__ x, int B, int H, int W, int E4, int axis, float scale,
+                                    const float4* __restrict__ add, int accumulate, float4* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const int R = axis == 1 ? W : H, n = axis == 1 ? H : W;
+  const int64_t total = (int64_t)B * R * E4;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(t % E4);
+    const int r = (int)((t / E4) % R);
+    const int b = (int)(t / ((int64_t)E4 * R));
+    // element i of the walk: axis 1 -> (h = i, w = r), axis 2 -> (h = r, w = i)
+    const float4* p = x + (axis == 1 ? ((int64_t)b * H * W + r) : ((int64_t)b * H + r) * W) * E4 + e;
+    const int64_t step = (int64_t)(axis == 1 ? W : 1) * E4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int i = 0;
+    for (; i + 8 <= n; i += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(p + (i + j) * step);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
+    }
+    for (; i < n; ++i) {
+      const float4 v = __ldg(p + i * step);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    s.x *= scale; s.y *= scale; s.z *= scale; s.w *= scale;
+    if (add) { const float4 v = __ldg(add + t); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+    if (accumulate) { const float4 o = out[t]; s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w; }
+    out[t] = s;
+  }
+}
+
 // out[m,:] = a[m,:] + b[m,:] + c[m,:] + sr * row[(b, w),:] + sc * col[(b, h),:]   ([B,H,W,E] fp32; any may be null)
 __global__ void combine_bcast_kernel(const float* __restrict__ a, const float* __restrict__ b2,
                                      const float* __restrict__ c, const float* __restrict__ row, float sr,
@@ -324,6 +360,15 @@ extern "C" int cdetr_reduce_axis(const float* x, int B, int H, int W, int E, int
                                  cdetr_stream_t s) {
   CDETR_CHECK_ARG(x && (axis == 1 || axis == 2) && (out || out_split.base), "reduce_axis: bad args");
   const int R = axis == 1 ? W : H;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(add) | reinterpret_cast<uintptr_t>(out);
+  static const int scalar_light = getenv("CDETR_SCALAR_LIGHT") ? atoi(getenv("CDETR_SCALAR_LIGHT")) : 0;   // A/B: 2 = scalar reduce_axis
+  if (!(scalar_light & 2) && out && !out_split.base && E % 4 == 0 && (al & 15) == 0) {
+    launch_light(reduce_axis4_kernel, dim3(grid_for((int64_t)B * R * (E / 4), 128)), dim3(128), 0, STREAM(s),
+                 reinterpret_cast<const float4*>(x), B, H, W, E / 4, axis, scale, reinterpret_cast<const float4*>(add), accumulate,
+                 reinterpret_cast<float4*>(out));
+    CDETR_CHECK_LAUNCH();
+    return 0;
+  }
   launch_light(reduce_axis_kernel, dim3(grid_for((int64_t)B * R * E)), dim3(256), 0, STREAM(s), 
       x, B, H, W, E, axis, scale, add, accumulate, out, SPLIT_HI(out_split), SPLIT_LO(out_split), out_split.ld);
   CDETR_CHECK_LAUNCH();
@@ -336,7 +381,8 @@ extern "C" int cdetr_combine_bcast(const float* a, const float* b, const float* 
   CDETR_CHECK_ARG(out && M > 0, "combine_bcast: bad args");
   const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
                        reinterpret_cast<uintptr_t>(row) | reinterpret_cast<uintptr_t>(col) | reinterpret_cast<uintptr_t>(out);
-  if (E % 4 == 0 && (al & 15) == 0) {
+  static const int scalar_light = getenv("CDETR_SCALAR_LIGHT") ? atoi(getenv("CDETR_SCALAR_LIGHT")) : 0;   // A/B: 1 = scalar combine_bcast
+  if (!(scalar_light & 1) && E % 4 == 0 && (al & 15) == 0) {
     launch_light(combine_bcast4_kernel, dim3(grid_for(M * (E / 4))), dim3(256), 0, STREAM(s), reinterpret_cast<const float4*>(a),
                  reinterpret_cast<const float4*>(b), reinterpret_cast<const float4*>(c), reinterpret_cast<const float4*>(row), sr,
                  reinterpret_cast<const float4*>(col), sc, M, E / 4, H, W, reinterpret_cast<float4*>(out));

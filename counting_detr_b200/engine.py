@@ -564,9 +564,11 @@ class Engine:
             da = self.sbuf(n + ".da", Min, p_)
             if blk["c2"].implicit:
                 blk["c2"].wgrad(db, t["a"], Mo, conv=(H, W, p_, d, 1))
+                blk["c2"].finish_grad()      # staging -> [cout, cin, 3, 3] on the side stream, right behind the wgrad
                 blk["c2"].dgrad_conv(db, Mo, H, W, d, out_split=da, mask=t["a"])
             else:
                 blk["c2"].wgrad(db, t["col"], Mo)
+                blk["c2"].finish_grad()
                 dcol = col2buf[:, : Mo * 9 * p_].view(2, Mo, 9 * p_)
                 blk["c2"].dgrad(db, Mo, out_split=dcol)
                 L.call("cdetr_col2im3x3", dcol, B, H, W, p_, s, d, t["a"], da)
@@ -588,11 +590,6 @@ class Engine:
             dx = self.sbuf(n + ".dx", Min, blk["cin"])
             blk["c1"].dgrad(da, Min, out_split=dx, add_split=didt, mask=t["x"])
             g = dx
-        for blk in self.blocks:
-            if blk["train"]:
-                for k in ("c1", "c2", "c3", "ds"):
-                    if blk[k] is not None:
-                        blk[k].finish_grad()
 
     # ------------------------------------------------------------------ small helpers
     def _mlp2_fwd(self, key, e0, n, tag):
