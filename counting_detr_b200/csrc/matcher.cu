@@ -255,6 +255,180 @@ __global__ void lsap_kernel(const float* __restrict__ cost_all, const int* __res
   if (tid == 0) out_n[b] = nr;
 }
 
+// Single-warp solver with the per-column state in REGISTERS (problems up to 384 columns: lane l owns columns l, l + 32, ...).
+// Same algorithm, same arithmetic order and the same tie rule as lsap_kernel (= scipy's _lsap): the scan position of a
+// column in scipy's `remaining` array is tracked per column (`pos`, updated for the one column the swap-with-last
+// removal moves), so the lexicographic (value, assigned?, +-position) arg-min sees exactly scipy's keys.  What changes is
+// where the state lives: lsap_kernel re-reads remaining / cost / v / spc / row4col from shared memory in a dependent
+// chain per column and serialises the bookkeeping of every step on lane 0 (1.7 us per augmentation step at 300 x 50:
+// 188 us per call, all of it on the critical path between the forward and the backward); here a step is ten register
+// updates per lane, one warp arg-min and three uniform shared-memory reads.
+constexpr int LSAP_CPL = 12;   // columns per lane
+__global__ void __launch_bounds__(128)
+lsap_warp_kernel(const float* __restrict__ cost_all, const int* __restrict__ tgt_off, int Q, int Tmax,
+                 int64_t* __restrict__ out_q, int64_t* __restrict__ out_t, int* __restrict__ out_n,
+                 int* __restrict__ status, int stage_cost, int stage_off) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int b = blockIdx.x;
+  const int T = tgt_off[b + 1] - tgt_off[b];
+  const bool transposed = T < Q;  // rows = targets (scipy transposes iff nr > nc)
+  const int nr = transposed ? T : Q, nc = transposed ? Q : T;
+  const int ncap = max(Q, Tmax);
+  const float* cost = cost_all + (int64_t)b * Q * Tmax;  // [nr, nc] row-major
+  float* cost_s = reinterpret_cast<float*>(smraw + stage_off);
+  double* u = reinterpret_cast<double*>(smraw);
+  int* path = reinterpret_cast<int*>(u + ncap);
+  int* col4row = path + ncap;
+  int* row4col = col4row + ncap;
+  int* remaining = row4col + ncap;
+  const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x, nt = blockDim.x;   // warps 1.. only help to stage the cost slab
+  int64_t* oq = out_q + (int64_t)b * min(Q, Tmax);
+  int64_t* ot = out_t + (int64_t)b * min(Q, Tmax);
+  if (nr == 0) {
+    if (tid == 0) out_n[b] = 0;
+    return;
+  }
+  for (int i = tid; i < nr; i += nt) { u[i] = 0.0; col4row[i] = -1; }
+  for (int j = tid; j < nc; j += nt) row4col[j] = -1;
+  if (stage_cost) {
+    const int n4 = (nr * nc) >> 2;
+    if ((reinterpret_cast<uintptr_t>(cost) & 15) == 0) {
+      for (int i = tid; i < n4; i += nt) reinterpret_cast<float4*>(cost_s)[i] = __ldg(reinterpret_cast<const float4*>(cost) + i);
+      for (int i = 4 * n4 + tid; i < nr * nc; i += nt) cost_s[i] = __ldg(cost + i);
+    } else {
+      for (int i = tid; i < nr * nc; i += nt) cost_s[i] = __ldg(cost + i);
+    }
+  }
+  __syncthreads();
+  if (tid >= 32) return;
+  const float* cbase = stage_cost ? cost_s : cost;
+  double v[LSAP_CPL], spc[LSAP_CPL];
+  int pos[LSAP_CPL], r4c[LSAP_CPL];
+#pragma unroll
+  for (int k = 0; k < LSAP_CPL; ++k) { v[k] = 0.0; r4c[k] = -1; }
+  __syncwarp();
+  bool fail = false;
+
+  for (int cur = 0; cur < nr && !fail; ++cur) {
+    uint32_t open = 0;   // bit k: column lane + 32 k is still in `remaining`
+#pragma unroll
+    for (int k = 0; k < LSAP_CPL; ++k) {
+      const int j = lane + 32 * k;
+      if (j < nc) {
+        open |= 1u << k;
+        remaining[nc - j - 1] = j;   // reverse fill, as scipy: remaining[it] = nc - it - 1
+        pos[k] = nc - j - 1;
+      }
+      spc[k] = INFINITY;
+    }
+    __syncwarp();
+    int i = cur, sink = -1, nrem = nc;
+    double minval = 0.0;
+    while (true) {
+      const double ui = u[i];
+      const float* crow = cbase + (int64_t)i * nc;
+      Key best;
+      best.val = INFINITY; best.pri = 2; best.pos = 0x7fffffff;
+      int best_j = -1;
+#pragma unroll
+      for (int k = 0; k < LSAP_CPL; ++k) {
+        if (open & (1u << k)) {
+          const int j = lane + 32 * k;
+          const double r = __dsub_rn(__dsub_rn(__dadd_rn(minval, (double)crow[j]), ui), v[k]);
+          if (r < spc[k]) {
+            spc[k] = r;
+            path[j] = i;
+          }
+          Key key;
+          key.val = spc[k];
+          const bool unassigned = r4c[k] == -1;
+          key.pri = unassigned ? 0 : 1;
+          key.pos = unassigned ? -pos[k] : pos[k];
+          if (key_less(key, best)) { best = key; best_j = j; }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const Key other = key_shfl_xor(best, o);
+        const int other_j = __shfl_xor_sync(0xffffffffu, best_j, o);
+        if (key_less(other, best)) { best = other; best_j = other_j; }
+      }
+      if (best.val == INFINITY) {  // infeasible (cannot happen for finite costs)
+        fail = true;
+        break;
+      }
+      const int index = best.pri == 0 ? -best.pos : best.pos;   // scan position of the chosen column
+      const int j = best_j;
+      minval = best.val;
+      const int j_last = remaining[nrem - 1];
+      const int r_j = row4col[j];
+      __syncwarp();
+      if (lane == 0) remaining[index] = j_last;
+      // owner lanes: the chosen column leaves `remaining`, the former last column takes its scan position
+#pragma unroll
+      for (int k = 0; k < LSAP_CPL; ++k) {
+        if (lane + 32 * k == j) open &= ~(1u << k);
+        if (lane + 32 * k == j_last) pos[k] = index;
+      }
+      --nrem;
+      __syncwarp();
+      if (r_j == -1) { sink = j; break; }
+      i = r_j;
+    }
+    if (fail) break;
+    // dual update (scipy order of arithmetic): visited columns are exactly those that left `remaining`; the rows scanned
+    // besides `cur` are the rows matched to the visited assigned columns
+    if (lane == 0) u[cur] = __dadd_rn(u[cur], minval);
+#pragma unroll
+    for (int k = 0; k < LSAP_CPL; ++k) {
+      const int j = lane + 32 * k;
+      if (j < nc && !(open & (1u << k))) {
+        const double d = __dsub_rn(minval, spc[k]);
+        if (r4c[k] != -1) u[r4c[k]] = __dadd_rn(u[r4c[k]], d);
+        v[k] = __dsub_rn(v[k], d);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {   // augment along the alternating path
+      int j = sink;
+      while (true) {
+        const int i2 = path[j];
+        row4col[j] = i2;
+        const int tmp = col4row[i2];
+        col4row[i2] = j;
+        j = tmp;
+        if (i2 == cur) break;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < LSAP_CPL; ++k) {
+      const int j = lane + 32 * k;
+      if (j < nc) r4c[k] = row4col[j];
+    }
+  }
+  if (fail) {
+    if (lane == 0) { out_n[b] = 0; atomicExch(status, 1); }
+    return;
+  }
+  // output: (query, target) pairs with query ascending (scipy ordering, incl. the transposed case)
+  if (!transposed) {
+    for (int i = lane; i < nr; i += 32) { oq[i] = i; ot[i] = col4row[i]; }
+  } else {
+    for (int t = lane; t < nr; t += 32) {
+      const int q = col4row[t];
+      int rank = 0;
+      for (int t2 = 0; t2 < nr; ++t2) rank += col4row[t2] < q;
+      oq[rank] = q;
+      ot[rank] = t;
+    }
+  }
+  if (lane == 0) out_n[b] = nr;
+}
+
+size_t lsap_warp_smem(int ncap) { return (sizeof(double) + 4 * sizeof(int)) * (size_t)ncap + 16; }
+
 size_t lsap_smem(int ncap, int nthreads) {
   size_t s = 3 * sizeof(double) * ncap + 4 * sizeof(int) * ncap + 2 * (size_t)ncap;
   s += (16 - (2 * ncap) % 16) % 16;
@@ -289,7 +463,14 @@ extern "C" int cdetr_lsap(const float* cost, const int* tgt_off, int B, int Q, i
   const size_t base = (lsap_smem(ncap, 32) + 15) / 16 * 16;
   const size_t slab = (size_t)Q * Tmax * sizeof(float);
   const int stage_cost = base + slab <= 200 * 1024 ? 1 : 0;
-  if (ncap <= 384) {
+  static const bool legacy = getenv("CDETR_LSAP_LEGACY") != nullptr;     // A/B: shared-memory-state single-warp kernel
+  if (ncap <= 32 * LSAP_CPL && !legacy) {
+    const size_t wbase = (lsap_warp_smem(ncap) + 15) / 16 * 16;
+    const int stage = wbase + slab <= 200 * 1024 ? 1 : 0;
+    const size_t smem = stage ? wbase + slab : wbase;
+    { static DevAttrCache cfg = {}; CDETR_CHECK_CUDA(cdetr_ensure_smem(lsap_warp_kernel, 200 * 1024, &cfg)); }
+    lsap_warp_kernel<<<B, stage ? 128 : 32, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status, stage, (int)wbase);
+  } else if (ncap <= 384) {
     const size_t smem = stage_cost ? base + slab : lsap_smem(ncap, 32);
     { static DevAttrCache cfg = {}; CDETR_CHECK_CUDA(cdetr_ensure_smem(lsap_kernel<true>, 200 * 1024, &cfg)); }
     lsap_kernel<true><<<B, 32, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status, stage_cost, (int)base);
