@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcdetr_sm100a.so")
+LIB_PATH = os.environ.get("CDETR_LIB_PATH") or os.path.join(_HERE, "lib", "libcdetr_sm100a.so")   # override: A/B builds
 _lib = None
 
 

@@ -214,6 +214,15 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
       : "memory");
 }
 
+// Waits of the single-lane producer / MMA-issuer warps.  -DCDETR_SINGLE_SLEEP=1 selects the sleeping form for an A/B build.
+__device__ __forceinline__ void mbar_wait_single(uint64_t* bar, uint32_t parity) {
+#if defined(CDETR_SINGLE_SLEEP) && CDETR_SINGLE_SLEEP
+  mbar_wait_sleep(bar, parity);
+#else
+  mbar_wait(bar, parity);
+#endif
+}
+
 // ------------------------------- TMA ---------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -199,7 +199,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const TileCoord tc = decode_tile(args, rank, tile);
         const int n0 = tc.n0, m0 = tc.m0, kb_begin = tc.kb_begin, kb_end = tc.kb_end;
         if (RB && n0 != cur_n0) {   // new n-tile: (re)load the weight slab once every MMA on the old one is done
-          if (slab_gen > 0) mbar_wait(slab_empty_bar, (slab_gen - 1) & 1u);
+          if (slab_gen > 0) mbar_wait_single(slab_empty_bar, (slab_gen - 1) & 1u);
           mbar_arrive_expect_tx(slab_full_bar, slab_bytes);
           for (int kb = 0; kb < args.num_kb; ++kb)
             tma_load_3d(smem + (size_t)kb * b_bytes, &tmB, slab_full_bar, kb * BK, n0, 0);
@@ -215,7 +215,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t ph = (uint32_t)(it / stages) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_wait_single(&empty_bar[s], ph ^ 1u);
           uint8_t* a_s = RB ? smem + slab_bytes + (size_t)s * a_bytes : smem + (size_t)s * stage_bytes;
           uint8_t* b_s = a_s + a_bytes;
           if (RB) {
@@ -280,14 +280,14 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const TileCoord tc = decode_tile(args, rank, tile);
         const int kb_begin = tc.kb_begin, kb_end = tc.kb_end;
         if (RB && tc.n0 != cur_n0) {
-          mbar_wait(slab_full_bar, slab_gen & 1u);
+          mbar_wait_single(slab_full_bar, slab_gen & 1u);
           tc_fence_after();
           cur_n0 = tc.n0;
           ++slab_gen;
         }
         const int ab = ti & 1;
         if (ti >= 2) {  // the epilogue must have drained this accumulator buffer (used by tile ti-2)
-          mbar_wait(&tmem_empty_bar[ab], (uint32_t)((ti >> 1) - 1) & 1u);
+          mbar_wait_single(&tmem_empty_bar[ab], (uint32_t)((ti >> 1) - 1) & 1u);
           tc_fence_after();
         }
         const uint32_t tmem_d = tmem_base + (uint32_t)ab * args.tmem_cols;
@@ -295,7 +295,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
           const int s = it % stages;
           const uint32_t ph = (uint32_t)(it / stages) & 1u;
-          mbar_wait(&full_bar[s], ph);
+          mbar_wait_single(&full_bar[s], ph);
           tc_fence_after();
           if (it == 0) DBG_T(2);
           const uint32_t a_base = smem_u32(RB ? smem + slab_bytes + (size_t)s * a_bytes : smem + (size_t)s * stage_bytes);

@@ -21,6 +21,12 @@
 #include "common.cuh"
 #include "../../include/cdetr.h"
 
+#if defined(CDETR_BWDV_SPIN) && CDETR_BWDV_SPIN
+#define BWDV_WAIT mbar_wait
+#else
+#define BWDV_WAIT mbar_wait_sleep
+#endif
+
 namespace {
 
 constexpr int HD = 32;    // head dim
@@ -135,7 +141,7 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
       // logits: S = q K^T per side and group, [128 x 32] x [32 x 32] into the first 32 columns of the group's buffer
       for (int side = 0; side < 2; ++side) {
         for (int g = 0; g < ngroups; ++g) {
-          mbar_wait(&q_ready[g], (uint32_t)side);
+          mbar_wait_single(&q_ready[g], (uint32_t)side);
           tc_fence_after();
           const uint32_t a_base = smem_u32(As) + (uint32_t)g * 2u * A_PLANE_BYTES;
           const uint32_t k_base = smem_u32(Kb) + (uint32_t)side * 2u * K_PLANE_BYTES;
@@ -153,12 +159,12 @@ rcda_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcArgs a) {
           umma_commit(&s_full[g]);
         }
       }
-      mbar_wait(v_full, 0);
+      mbar_wait_single(v_full, 0);
       const uint32_t v_base = smem_u32(Vs);
       for (int p = 0; p < nblk; ++p) {
         for (int g = 0; g < ngroups; ++g) {
-          if (p == 0) mbar_wait(&a_ready[g], 0);
-          else mbar_wait(&t_empty[g], (uint32_t)(p - 1) & 1u);
+          if (p == 0) mbar_wait_single(&a_ready[g], 0);
+          else mbar_wait_single(&t_empty[g], (uint32_t)(p - 1) & 1u);
           tc_fence_after();
           const uint32_t a_base = smem_u32(As) + (uint32_t)g * 2u * A_PLANE_BYTES;
           const uint32_t d = tmem_base + (uint32_t)g * 256u;
@@ -416,12 +422,12 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
   } else if (warp == 1) {
     if (lane == 0) {
       const int ngroups = (q_cta + TQ < a.L) ? 2 : 1;
-      mbar_wait(v_full, 0);
+      mbar_wait_single(v_full, 0);
       const uint32_t v_base = smem_u32(Vs);
       for (int p = 0; p < nblk; ++p) {
         for (int g = 0; g < ngroups; ++g) {
-          if (p == 0) mbar_wait(&a_ready[g], 0);
-          else mbar_wait(&t_empty[g], (uint32_t)(p - 1) & 1u);
+          if (p == 0) mbar_wait_single(&a_ready[g], 0);
+          else mbar_wait_single(&t_empty[g], (uint32_t)(p - 1) & 1u);
           tc_fence_after();
           const uint32_t a_base = smem_u32(As) + (uint32_t)g * 2u * A_PLANE_BYTES;
           const uint32_t d = tmem_base + (uint32_t)g * 256u;
@@ -444,7 +450,7 @@ rcda_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmV, const TcBwdArgs a)
       // an MN-major operand (row = key = k index, 64-byte rows of 32 channels), D = first 32 columns of the buffer
       for (int side = 0; side < 2; ++side) {
         for (int g = 0; g < ngroups; ++g) {
-          mbar_wait(&q_ready[g], (uint32_t)side);
+          mbar_wait_single(&q_ready[g], (uint32_t)side);
           tc_fence_after();
           const uint32_t a_base = smem_u32(As) + (uint32_t)g * 2u * A_PLANE_BYTES;
           const uint32_t k_base = smem_u32(Vs) + (uint32_t)side * 4096u;
@@ -730,7 +736,7 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % a.d_bufs;
-        if (kb >= a.d_bufs) mbar_wait_sleep(&d_empty[s], (uint32_t)(kb / a.d_bufs - 1) & 1u);
+        if (kb >= a.d_bufs) BWDV_WAIT(&d_empty[s], (uint32_t)(kb / a.d_bufs - 1) & 1u);
         mbar_arrive_expect_tx(&d_full[s], 2 * DO_PLANE_BYTES);
         tma_load_3d(Ds + s * 2 * DO_PLANE_BYTES, &tmD, &d_full[s], head * HD, b * a.L + kb * VK, 0);
         tma_load_3d(Ds + s * 2 * DO_PLANE_BYTES + DO_PLANE_BYTES, &tmD, &d_full[s], head * HD, b * a.L + kb * VK, 1);
@@ -741,11 +747,11 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
       int u = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % a.d_bufs;
-        mbar_wait_sleep(&d_full[s], (uint32_t)(kb / a.d_bufs) & 1u);
+        BWDV_WAIT(&d_full[s], (uint32_t)(kb / a.d_bufs) & 1u);
         const uint32_t d_base = smem_u32(Ds) + (uint32_t)s * 2u * DO_PLANE_BYTES;
         for (int mt = mt_begin; mt < mt_end; ++mt, ++u) {
           const int pb = u % a.p_bufs;
-          mbar_wait_sleep(&p_full[pb], (uint32_t)(u / a.p_bufs) & 1u);
+          BWDV_WAIT(&p_full[pb], (uint32_t)(u / a.p_bufs) & 1u);
           tc_fence_after();
           const uint32_t p_base = tmem_base + p_col0 + (uint32_t)pb * 64u;   // hi plane; lo plane 32 columns further
           const uint32_t d = tmem_base + (uint32_t)(mt - mt_begin) * 32u;
@@ -817,7 +823,7 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
       for (int mt = mt_begin; mt < mt_end; ++mt, ++u) {
         const int pb = u % a.p_bufs;
         if (u >= a.p_bufs) {
-          mbar_wait_sleep(&p_empty[pb], (uint32_t)(u / a.p_bufs - 1) & 1u);   // the MMAs that read this buffer are done
+          BWDV_WAIT(&p_empty[pb], (uint32_t)(u / a.p_bufs - 1) & 1u);   // the MMAs that read this buffer are done
           tc_fence_after();
         }
         // rows past H*W only feed accumulator rows that are never stored: any in-range map row will do
@@ -852,7 +858,7 @@ rcda_bwd_v_tc_kernel(const __grid_constant__ CUtensorMap tmD, const TcBwdVArgs a
       }
     }
     // ---- epilogue: accumulators -> dV (split)
-    mbar_wait_sleep(acc_full, 0);
+    BWDV_WAIT(acc_full, 0);
     tc_fence_after();
     const int grp = (warp - 2) >> 2;
     for (int mt = mt_begin + grp; mt < mt_end; mt += 2) {

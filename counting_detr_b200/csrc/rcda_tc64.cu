@@ -178,7 +178,7 @@ rcda_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmV, const Fwd64Args a)
     if (lane == 0) {
       for (int p = 0; p < nblk; ++p) {
         const int st = p % NSTAGE;
-        if (p >= NSTAGE) mbar_wait(&v_empty[st], (uint32_t)(p / NSTAGE - 1) & 1u);
+        if (p >= NSTAGE) mbar_wait_single(&v_empty[st], (uint32_t)(p / NSTAGE - 1) & 1u);
         mbar_arrive_expect_tx(&v_full[st], V_STAGE);
         tma_load_5d(Vs + st * V_STAGE, &tmV, &v_full[st], head * HD, 0, p * HB, b, 0);          // box {32 c, 64 w, 4 h, 1, 1}
         tma_load_5d(Vs + st * V_STAGE + V_PLANE, &tmV, &v_full[st], head * HD, 0, p * HB, b, 1);
@@ -189,7 +189,7 @@ rcda_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmV, const Fwd64Args a)
       // logits S = q K^T: [128 x 32] x [32 x 64 keys] into the first 64 columns of the tile's TMEM region
       for (int side = 0; side < 2; ++side) {
         for (int g = 0; g < ngroups; ++g) {
-          mbar_wait(&q_ready[g], (uint32_t)side);
+          mbar_wait_single(&q_ready[g], (uint32_t)side);
           tc_fence_after();
           const uint32_t a_base = smem_u32(Qs) + (uint32_t)g * 2u * Q_PLANE;
           const uint32_t k_base = smem_u32(Kb) + (uint32_t)side * 2u * K_PLANE;
@@ -210,12 +210,12 @@ rcda_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmV, const Fwd64Args a)
       // main contraction, V block by V block; two 128-column accumulator buffers per query tile
       for (int p = 0; p < nblk; ++p) {
         const int st = p % NSTAGE;
-        mbar_wait(&v_full[st], (uint32_t)(p / NSTAGE) & 1u);
+        mbar_wait_single(&v_full[st], (uint32_t)(p / NSTAGE) & 1u);
         const uint32_t v_base = smem_u32(Vs) + (uint32_t)st * V_STAGE;
         const int u = p & 1;
         for (int g = 0; g < ngroups; ++g) {
-          if (p == 0) mbar_wait(&a_ready[g], 0);                 // A_r operand written AND both logit rows read out
-          if (p >= 2) mbar_wait(&t_empty[g * 2 + u], (uint32_t)((p >> 1) - 1) & 1u);
+          if (p == 0) mbar_wait_single(&a_ready[g], 0);                 // A_r operand written AND both logit rows read out
+          if (p >= 2) mbar_wait_single(&t_empty[g * 2 + u], (uint32_t)((p >> 1) - 1) & 1u);
           tc_fence_after();
           const uint32_t a_base = smem_u32(Ar) + (uint32_t)g * 2u * AR_PLANE;
           const uint32_t d = tmem_base + (uint32_t)g * 256u + (uint32_t)u * 128u;
@@ -431,7 +431,7 @@ rcda_bwd_q_tc64_kernel(const __grid_constant__ CUtensorMap tmV, const Bwd64Args 
     if (lane == 0) {
       for (int p = 0; p < nblk; ++p) {
         const int st = p % NSTAGE;
-        if (p >= NSTAGE) mbar_wait(&v_empty[st], (uint32_t)(p / NSTAGE - 1) & 1u);
+        if (p >= NSTAGE) mbar_wait_single(&v_empty[st], (uint32_t)(p / NSTAGE - 1) & 1u);
         mbar_arrive_expect_tx(&v_full[st], V_STAGE);
         tma_load_5d(Vs + st * V_STAGE, &tmV, &v_full[st], head * HD, 0, p * HB, b, 0);
         tma_load_5d(Vs + st * V_STAGE + V_PLANE, &tmV, &v_full[st], head * HD, 0, p * HB, b, 1);
@@ -441,11 +441,11 @@ rcda_bwd_q_tc64_kernel(const __grid_constant__ CUtensorMap tmV, const Bwd64Args 
     if (lane == 0) {
       for (int p = 0; p < nblk; ++p) {
         const int st = p % NSTAGE;
-        mbar_wait(&v_full[st], (uint32_t)(p / NSTAGE) & 1u);
+        mbar_wait_single(&v_full[st], (uint32_t)(p / NSTAGE) & 1u);
         const uint32_t v_base = smem_u32(Vs) + (uint32_t)st * V_STAGE;
         for (int g = 0; g < ngroups; ++g) {
-          if (p == 0) mbar_wait(&a_ready[g], 0);
-          else mbar_wait(&t_empty[g], (uint32_t)(p - 1) & 1u);
+          if (p == 0) mbar_wait_single(&a_ready[g], 0);
+          else mbar_wait_single(&t_empty[g], (uint32_t)(p - 1) & 1u);
           tc_fence_after();
           const uint32_t a_base = smem_u32(As) + (uint32_t)g * 2u * Q_PLANE;
           const uint32_t d = tmem_base + (uint32_t)g * 256u;
@@ -469,7 +469,7 @@ rcda_bwd_q_tc64_kernel(const __grid_constant__ CUtensorMap tmV, const Bwd64Args 
       for (int side = 0; side < 2; ++side) {
         const int nks = ((side == 0 ? a.W : a.H) + 15) / 16;
         for (int g = 0; g < ngroups; ++g) {
-          mbar_wait(&q_ready[g], (uint32_t)side);
+          mbar_wait_single(&q_ready[g], (uint32_t)side);
           tc_fence_after();
           const uint32_t a_base = smem_u32(Ds) + (uint32_t)g * 2u * AR_PLANE;
           const uint32_t k_base = smem_u32(Kb) + (uint32_t)side * 2u * K_PLANE;

@@ -22,6 +22,12 @@
 #include "common.cuh"
 #include "../../include/cdetr.h"
 
+#if defined(CDETR_STEM_SPIN) && CDETR_STEM_SPIN
+#define STEM_WAIT mbar_wait
+#else
+#define STEM_WAIT mbar_wait_sleep
+#endif
+
 namespace {
 
 constexpr int PH = 8, PW = 16;                 // output patch = 128 pixels
@@ -131,7 +137,7 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a) {
       const uint32_t w_base = smem_u32(Ws);
       for (int it = 0; it < n_my; ++it) {
         const uint32_t buf = (uint32_t)it & 1u;
-        mbar_wait_sleep(&a_full[buf], (uint32_t)(it >> 1) & 1u);
+        STEM_WAIT(&a_full[buf], (uint32_t)(it >> 1) & 1u);
         tc_fence_after();
         const uint32_t acc = tmem_base + COL_ACC + 64u * buf;
         const uint32_t a0 = tmem_base + COL_A + A_COLS * buf;
@@ -255,7 +261,7 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a) {
       // ---- stage the PREVIOUS tile's output: its MMAs ran while this one was built; its staging tile (buf ^ 1) was last
       // read by the TMA stores of tile it-3, drained before this iteration's barrier
       if (it > 0) {
-        mbar_wait_sleep(&mma_done[buf ^ 1u], (uint32_t)((it - 1) >> 1) & 1u);
+        STEM_WAIT(&mma_done[buf ^ 1u], (uint32_t)((it - 1) >> 1) & 1u);
         tc_fence_after();
         store_tile(buf ^ 1u);
       }
@@ -266,7 +272,7 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap tmOut, const StemArgs a) {
     if (threadIdx.x == 0 && n_my >= 2) issue_store(n_my - 2);
     if (n_my > 0) {
       const uint32_t buf = (uint32_t)(n_my - 1) & 1u;
-      mbar_wait_sleep(&mma_done[buf], (uint32_t)((n_my - 1) >> 1) & 1u);
+      STEM_WAIT(&mma_done[buf], (uint32_t)((n_my - 1) >> 1) & 1u);
       tc_fence_after();
       store_tile(buf);
       asm volatile("bar.sync 1, 512;" ::: "memory");
