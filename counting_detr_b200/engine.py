@@ -93,10 +93,18 @@ class Lin:
             main = torch.cuda.current_stream()
             ev = torch.cuda.Event()
             ev.record(main)
-            eng.side_stream.wait_event(ev)
-            with torch.cuda.stream(eng.side_stream):
-                self._wgrad(dy, a, M, rows, bias_grad, conv)
+            side = eng.next_side_stream()
+            self._side = side        # finish_grad follows this layer's weight-gradient GEMM on the same stream
+            side.wait_event(ev)
+            split_bias = eng.bias_stream is not None and bias_grad and self.bname and self.bname in eng.grad_views
+            with torch.cuda.stream(side):
+                self._wgrad(dy, a, M, rows, bias_grad and not split_bias, conv)
             eng.side_used = True
+            if split_bias:      # the tiny column-sum kernels do not queue between the weight-gradient GEMMs
+                eng.bias_stream.wait_event(ev)
+                with torch.cuda.stream(eng.bias_stream):
+                    self._bias_grad(dy, M, rows)
+                eng.bias_used = True
         else:
             self._wgrad(dy, a, M, rows, bias_grad, conv)
 
@@ -118,16 +126,20 @@ class Lin:
                row_scale=self.scale[lo:hi] if self.scale is not None else None,
                block_n=bn, conv=conv, pass_mask=self.pm_wgrad)
         if bias_grad and self.bname and self.bname in self.eng.grad_views:
-            g = self.eng.grad_views[self.bname]
-            if g.numel() != self.n_out:
-                raise NotImplementedError("gradient of a broadcast (shape-[1]) bias")
-            L.call("cdetr_colsum", None, dy, 0, M, n, g[lo:hi])
+            self._bias_grad(dy, M, rows)
+
+    def _bias_grad(self, dy, M, rows):
+        lo, hi = rows if rows else (0, self.n_out)
+        g = self.eng.grad_views[self.bname]
+        if g.numel() != self.n_out:
+            raise NotImplementedError("gradient of a broadcast (shape-[1]) bias")
+        L.call("cdetr_colsum", None, dy, 0, M, hi - lo, g[lo:hi])
 
     def finish_grad(self):
         if self.trainable and self.taps > 1:
             eng = self.eng
             if eng.side_stream is not None:
-                with torch.cuda.stream(eng.side_stream):     # ordered after this conv's wgrad on the side stream
+                with torch.cuda.stream(getattr(self, "_side", None) or eng.side_stream):   # ordered after this conv's wgrad
                     L.call("cdetr_unpack_conv_grad", self.stage, self.n_out, self.cin, self.taps,
                            eng.grad_views[self.wname])
             else:
@@ -204,6 +216,17 @@ class Engine:
         self._aux_rr = 0        # round-robin start: nested / consecutive forks land on different streams
         self.acc_stream = torch.cuda.Stream(device=device, priority=0) if device.type == "cuda" else None
         self.acc_used = False
+        # weight-gradient GEMMs alternate over CDETR_SIDE_STREAMS streams: most of them are small (36-144 CTAs) and only
+        # depend on their own dy, so two can share the machine instead of queueing behind each other
+        self.side_streams = [self.side_stream] if self.side_stream is not None else []
+        for _ in range(max(int(os.environ.get("CDETR_SIDE_STREAMS", "1")), 1) - 1):
+            if self.side_stream is not None:
+                self.side_streams.append(torch.cuda.Stream(device=device, priority=0))
+        self._side_rr = 0
+        self.bias_stream = None     # bias-gradient column sums beside (not between) the weight-gradient GEMMs
+        if self.side_stream is not None and os.environ.get("CDETR_BIAS_STREAM", "1") != "0":
+            self.bias_stream = torch.cuda.Stream(device=device, priority=0)
+        self.bias_used = False
 
     # Precision policy: "<group>.<kind>=<mask>" entries, group in {backbone, proj, attn, ffn, pos,
     # heads, *}, kind in {fwd, dgrad, wgrad, *}, mask = cdetr_gemm_t.pass_mask (7 all three products, 5 second operand
@@ -316,13 +339,24 @@ class Engine:
             torch.cuda.current_stream().wait_event(ev)
             self.acc_used = False
 
+    def next_side_stream(self):
+        st = self.side_streams[self._side_rr % len(self.side_streams)]
+        self._side_rr += 1
+        return st
+
     def join_side_stream(self):
-        """main stream waits for every weight-gradient kernel issued on the side stream."""
+        """main stream waits for every weight-gradient kernel issued on the side streams."""
         if self.side_stream is not None and self.side_used:
-            ev = torch.cuda.Event()
-            ev.record(self.side_stream)
-            torch.cuda.current_stream().wait_event(ev)
+            for st in self.side_streams:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                torch.cuda.current_stream().wait_event(ev)
             self.side_used = False
+        if self.bias_stream is not None and self.bias_used:
+            ev = torch.cuda.Event()
+            ev.record(self.bias_stream)
+            torch.cuda.current_stream().wait_event(ev)
+            self.bias_used = False
 
     # ------------------------------------------------------------------ infrastructure
     def buf(self, name, shape, dtype=torch.float32, zero=False):
