@@ -263,7 +263,8 @@ __global__ void lsap_kernel(const float* __restrict__ cost_all, const int* __res
 // chain per column and serialises the bookkeeping of every step on lane 0 (1.7 us per augmentation step at 300 x 50:
 // 188 us per call, all of it on the critical path between the forward and the backward); here a step is ten register
 // updates per lane, one warp arg-min and three uniform shared-memory reads.
-constexpr int LSAP_CPL = 12;   // columns per lane
+constexpr int LSAP_CPL_MAX = 12;   // columns per lane (template parameter: the unrolled per-step work scales with it)
+template <int LSAP_CPL>
 __global__ void __launch_bounds__(128)
 lsap_warp_kernel(const float* __restrict__ cost_all, const int* __restrict__ tgt_off, int Q, int Tmax,
                  int64_t* __restrict__ out_q, int64_t* __restrict__ out_t, int* __restrict__ out_n,
@@ -464,12 +465,24 @@ extern "C" int cdetr_lsap(const float* cost, const int* tgt_off, int B, int Q, i
   const size_t slab = (size_t)Q * Tmax * sizeof(float);
   const int stage_cost = base + slab <= 200 * 1024 ? 1 : 0;
   static const bool legacy = getenv("CDETR_LSAP_LEGACY") != nullptr;     // A/B: shared-memory-state single-warp kernel
-  if (ncap <= 32 * LSAP_CPL && !legacy) {
+  if (ncap <= 32 * LSAP_CPL_MAX && !legacy) {
     const size_t wbase = (lsap_warp_smem(ncap) + 15) / 16 * 16;
     const int stage = wbase + slab <= 200 * 1024 ? 1 : 0;
     const size_t smem = stage ? wbase + slab : wbase;
-    { static DevAttrCache cfg = {}; CDETR_CHECK_CUDA(cdetr_ensure_smem(lsap_warp_kernel, 200 * 1024, &cfg)); }
-    lsap_warp_kernel<<<B, stage ? 128 : 32, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status, stage, (int)wbase);
+    const int cpl = (ncap + 31) / 32;
+#define CDETR_LSAP_LAUNCH(N)                                                                                              \
+  do {                                                                                                                    \
+    static DevAttrCache cfg = {};                                                                                         \
+    CDETR_CHECK_CUDA(cdetr_ensure_smem(lsap_warp_kernel<N>, 200 * 1024, &cfg));                                           \
+    lsap_warp_kernel<N><<<B, stage ? 128 : 32, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status, stage,     \
+                                                          (int)wbase);                                                    \
+  } while (0)
+    if (cpl <= 2) CDETR_LSAP_LAUNCH(2);
+    else if (cpl <= 4) CDETR_LSAP_LAUNCH(4);
+    else if (cpl <= 7) CDETR_LSAP_LAUNCH(7);
+    else if (cpl <= 10) CDETR_LSAP_LAUNCH(10);
+    else CDETR_LSAP_LAUNCH(12);
+#undef CDETR_LSAP_LAUNCH
   } else if (ncap <= 384) {
     const size_t smem = stage_cost ? base + slab : lsap_smem(ncap, 32);
     { static DevAttrCache cfg = {}; CDETR_CHECK_CUDA(cdetr_ensure_smem(lsap_kernel<true>, 200 * 1024, &cfg)); }
