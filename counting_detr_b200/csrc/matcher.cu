@@ -329,39 +329,46 @@ lsap_warp_kernel(const float* __restrict__ cost_all, const int* __restrict__ tgt
     while (true) {
       const double ui = u[i];
       const float* crow = cbase + (int64_t)i * nc;
-      Key best;
-      best.val = INFINITY; best.pri = 2; best.pos = 0x7fffffff;
-      int best_j = -1;
+      // (1) relax the open columns (branch-free) and take the lane's minimum shortest-path cost
+      double m = INFINITY;
 #pragma unroll
       for (int k = 0; k < LSAP_CPL; ++k) {
-        if (open & (1u << k)) {
-          const int j = lane + 32 * k;
-          const double r = __dsub_rn(__dsub_rn(__dadd_rn(minval, (double)crow[j]), ui), v[k]);
-          if (r < spc[k]) {
-            spc[k] = r;
-            path[j] = i;
-          }
-          Key key;
-          key.val = spc[k];
-          const bool unassigned = r4c[k] == -1;
-          key.pri = unassigned ? 0 : 1;
-          key.pos = unassigned ? -pos[k] : pos[k];
-          if (key_less(key, best)) { best = key; best_j = j; }
+        const int j = lane + 32 * k;
+        const bool op = (open >> k) & 1u;
+        const double r = __dsub_rn(__dsub_rn(__dadd_rn(minval, (double)crow[op ? j : 0]), ui), v[k]);
+        if (op && r < spc[k]) {
+          spc[k] = r;
+          path[j] = i;
         }
+        const double val = op ? spc[k] : INFINITY;
+        if (val < m) m = val;
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const Key other = key_shfl_xor(best, o);
-        const int other_j = __shfl_xor_sync(0xffffffffu, best_j, o);
-        if (key_less(other, best)) { best = other; best_j = other_j; }
-      }
-      if (best.val == INFINITY) {  // infeasible (cannot happen for finite costs)
+      // (2) warp minimum of a double through two 32-bit REDUX operations on its order-preserving bit pattern
+      //     (+0.0 first: -0.0 and +0.0 compare equal and must map to one pattern)
+      unsigned long long bits = (unsigned long long)__double_as_longlong(__dadd_rn(m, 0.0));
+      bits = (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
+      const unsigned hmin = __reduce_min_sync(0xffffffffu, (unsigned)(bits >> 32));
+      const unsigned lmin = __reduce_min_sync(0xffffffffu, (unsigned)(bits >> 32) == hmin ? (unsigned)bits : 0xffffffffu);
+      unsigned long long gb = ((unsigned long long)hmin << 32) | lmin;
+      gb = (gb >> 63) ? (gb & 0x7fffffffffffffffull) : ~gb;
+      const double gmin = __longlong_as_double((long long)gb);
+      if (gmin == INFINITY) {  // infeasible (cannot happen for finite costs)
         fail = true;
         break;
       }
-      const int index = best.pri == 0 ? -best.pos : best.pos;   // scan position of the chosen column
-      const int j = best_j;
-      minval = best.val;
+      // (3) scipy's tie rule among the columns at the minimum: unassigned columns first and of those the LAST in scan
+      //     order, else the first assigned one -- one integer per column, scan positions are unique
+      int tb = 0x7fffffff, bj = -1;
+#pragma unroll
+      for (int k = 0; k < LSAP_CPL; ++k) {
+        const bool cand = ((open >> k) & 1u) && spc[k] == gmin;
+        const int t = r4c[k] == -1 ? -pos[k] - (1 << 20) : pos[k];
+        if (cand && t < tb) { tb = t; bj = lane + 32 * k; }
+      }
+      const int tbmin = __reduce_min_sync(0xffffffffu, tb);
+      const int j = __reduce_max_sync(0xffffffffu, tb == tbmin ? bj : -1);
+      const int index = tbmin < 0 ? -(tbmin + (1 << 20)) : tbmin;   // scan position of the chosen column
+      minval = gmin;
       const int j_last = remaining[nrem - 1];
       const int r_j = row4col[j];
       __syncwarp();
