@@ -136,15 +136,25 @@ class Lin:
         L.call("cdetr_colsum", None, dy, 0, M, hi - lo, g[lo:hi])
 
     def finish_grad(self):
-        if self.trainable and self.taps > 1:
-            eng = self.eng
-            if eng.side_stream is not None:
-                with torch.cuda.stream(getattr(self, "_side", None) or eng.side_stream):   # ordered after this conv's wgrad
-                    L.call("cdetr_unpack_conv_grad", self.stage, self.n_out, self.cin, self.taps,
-                           eng.grad_views[self.wname])
-            else:
-                L.call("cdetr_unpack_conv_grad", self.stage, self.n_out, self.cin, self.taps,
-                       eng.grad_views[self.wname])
+        """3x3 convs: the weight-gradient GEMM wrote [cout, taps*cin] staging; add it into the [cout, cin, 3, 3] gradient.
+        Ordered behind this layer's weight-gradient GEMM; issued on the bias stream when there is one, so that the
+        small kernel does not queue in front of the next layers' weight-gradient GEMMs."""
+        if not (self.trainable and self.taps > 1):
+            return
+        eng = self.eng
+        side = getattr(self, "_side", None) or eng.side_stream
+        if side is None:
+            L.call("cdetr_unpack_conv_grad", self.stage, self.n_out, self.cin, self.taps, eng.grad_views[self.wname])
+            return
+        st = side
+        if eng.bias_stream is not None and eng.unpack_on_bias:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            eng.bias_stream.wait_event(ev)
+            st = eng.bias_stream
+            eng.bias_used = True
+        with torch.cuda.stream(st):
+            L.call("cdetr_unpack_conv_grad", self.stage, self.n_out, self.cin, self.taps, eng.grad_views[self.wname])
 
 
 class Engine:
@@ -227,6 +237,7 @@ class Engine:
         if self.side_stream is not None and os.environ.get("CDETR_BIAS_STREAM", "1") != "0":
             self.bias_stream = torch.cuda.Stream(device=device, priority=0)
         self.bias_used = False
+        self.unpack_on_bias = os.environ.get("CDETR_UNPACK_ON_BIAS", "1") != "0"
 
     # Precision policy: "<group>.<kind>=<mask>" entries, group in {backbone, proj, attn, ffn, pos,
     # heads, *}, kind in {fwd, dgrad, wgrad, *}, mask = cdetr_gemm_t.pass_mask (7 all three products, 5 second operand
