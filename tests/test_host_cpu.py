@@ -188,3 +188,43 @@ def test_buffer_cache_keeps_three_signatures():
     assert e.evictions == 1 and len(e._sig_keys) == 3
     shapes = sorted(k[1][0] for k in e._bufs if k[0] == "act")
     assert shapes == [96, 128, 160] and ("shared", (4,), torch.float32) in e._bufs
+
+
+def test_parameter_version_check_is_cached_and_sees_every_write():
+    """The per-step "did anyone change the weights" check (counting_detr_b200/models.py:_current_version) sums tensor
+    version counters over a CACHED parameter list (walking the module tree cost 0.3 ms between a step's result and the
+    next launch): it must change on any in-place write, on load_state_dict, and the cache must not survive .to()."""
+    import torch
+    from counting_detr_b200 import synthetic as SY
+    from counting_detr_b200.models import build_model
+    model, _, _ = build_model(SY.default_args(2, device="cpu", num_query_position=10))
+    v0 = model._current_version()
+    assert model._plist is not None and len(model._plist) == len(list(model.parameters()))
+    assert model._current_version() == v0                      # stable without writes
+    with torch.no_grad():
+        next(model.parameters()).add_(1.0)
+    v1 = model._current_version()
+    assert v1 != v0
+    with torch.no_grad():
+        list(model.parameters())[-1].mul_(0.5)                 # the last parameter counts too
+    v2 = model._current_version()
+    assert v2 != v1
+    model.load_state_dict(model.state_dict())
+    assert model._current_version() != v2
+    model.to(torch.float32)
+    assert model._plist is None                                # _apply drops the cache
+    assert all(a is b for a, b in zip(model._param_list(), model.parameters()))
+
+
+def test_sass_has_tmem_operand_kernels(built_lib):
+    """rcda_bwd_v_tc and the stem build their A operands in tensor memory: tcgen05.st (STTM) + MMAs whose A operand is a
+    TMEM address.  Guards against a silent fall back to the shared-memory formulation."""
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib.LIB_PATH], capture_output=True, text=True).stdout
+    for fn in ("rcda_bwd_v_tc_kernel", "stem_conv_kernel"):
+        i = sass.find(fn)
+        assert i >= 0, fn
+        j = sass.find("Function :", i + 1)
+        body = sass[i: j if j > 0 else len(sass)]
+        assert "STTM" in body, f"{fn}: no tcgen05.st"
+        # SS form: UTCHMMA gdesc[..], gdesc[..], tmem[acc], ...;  TS form: UTCHMMA tmem[a], gdesc[..], tmem[acc], ...
+        assert re.search(r"UTCHMMA\s+tmem\[", body), f"{fn}: no MMA with the A operand in tensor memory"
