@@ -435,6 +435,174 @@ lsap_warp_kernel(const float* __restrict__ cost_all, const int* __restrict__ tgt
   if (lane == 0) out_n[b] = nr;
 }
 
+// The same register-resident formulation for larger problems (up to 4096 columns): a whole CTA, thread t owns columns
+// t, t + blockDim, ...; the arg-min is a warp REDUX followed by a 32-entry cross-warp step that EVERY warp repeats from
+// shared memory (no broadcast barrier), three CTA barriers per augmentation step.  The cost row of the next step is read
+// from global memory / L2 (the matrix does not fit shared memory), which is now the longest link of the chain.
+template <int CPL>
+__global__ void __launch_bounds__(1024)
+lsap_block_kernel(const float* __restrict__ cost_all, const int* __restrict__ tgt_off, int Q, int Tmax,
+                  int64_t* __restrict__ out_q, int64_t* __restrict__ out_t, int* __restrict__ out_n,
+                  int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ unsigned long long red64[32];
+  __shared__ int red_tb[32];
+  __shared__ int s_j, s_rj;
+  const int b = blockIdx.x;
+  const int T = tgt_off[b + 1] - tgt_off[b];
+  const bool transposed = T < Q;
+  const int nr = transposed ? T : Q, nc = transposed ? Q : T;
+  const int ncap = max(Q, Tmax);
+  const float* cost = cost_all + (int64_t)b * Q * Tmax;  // [nr, nc] row-major
+  double* u = reinterpret_cast<double*>(smraw);
+  int* path = reinterpret_cast<int*>(u + ncap);
+  int* col4row = path + ncap;
+  int* row4col = col4row + ncap;
+  int* remaining = row4col + ncap;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  int64_t* oq = out_q + (int64_t)b * min(Q, Tmax);
+  int64_t* ot = out_t + (int64_t)b * min(Q, Tmax);
+  if (nr == 0) {
+    if (tid == 0) out_n[b] = 0;
+    return;
+  }
+  for (int i = tid; i < nr; i += nt) { u[i] = 0.0; col4row[i] = -1; }
+  for (int j = tid; j < nc; j += nt) row4col[j] = -1;
+  double v[CPL], spc[CPL];
+  int pos[CPL], r4c[CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) { v[k] = 0.0; r4c[k] = -1; }
+  __syncthreads();
+  bool fail = false;
+
+  for (int cur = 0; cur < nr && !fail; ++cur) {
+    uint32_t open = 0;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int j = tid + nt * k;
+      if (j < nc) {
+        open |= 1u << k;
+        remaining[nc - j - 1] = j;
+        pos[k] = nc - j - 1;
+      }
+      spc[k] = INFINITY;
+    }
+    __syncthreads();
+    int i = cur, sink = -1, nrem = nc;
+    double minval = 0.0;
+    while (true) {
+      const double ui = u[i];
+      const float* crow = cost + (int64_t)i * nc;
+      double m = INFINITY;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const int j = tid + nt * k;
+        const bool op = (open >> k) & 1u;
+        const double r = __dsub_rn(__dsub_rn(__dadd_rn(minval, (double)__ldg(crow + (op ? j : 0))), ui), v[k]);
+        if (op && r < spc[k]) {
+          spc[k] = r;
+          path[j] = i;
+        }
+        const double val = op ? spc[k] : INFINITY;
+        if (val < m) m = val;
+      }
+      // CTA minimum: warp REDUX on the order-preserving bit pattern, one entry per warp, every warp reduces the 32 entries
+      unsigned long long bits = (unsigned long long)__double_as_longlong(__dadd_rn(m, 0.0));
+      bits = (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
+      {
+        const unsigned hmin = __reduce_min_sync(0xffffffffu, (unsigned)(bits >> 32));
+        const unsigned lmin = __reduce_min_sync(0xffffffffu, (unsigned)(bits >> 32) == hmin ? (unsigned)bits : 0xffffffffu);
+        if (lane == 0) red64[warp] = ((unsigned long long)hmin << 32) | lmin;
+      }
+      __syncthreads();
+      unsigned long long wb = lane < nw ? red64[lane] : ~0ull;
+      const unsigned hmin = __reduce_min_sync(0xffffffffu, (unsigned)(wb >> 32));
+      const unsigned lmin = __reduce_min_sync(0xffffffffu, (unsigned)(wb >> 32) == hmin ? (unsigned)wb : 0xffffffffu);
+      unsigned long long gb = ((unsigned long long)hmin << 32) | lmin;
+      gb = (gb >> 63) ? (gb & 0x7fffffffffffffffull) : ~gb;
+      const double gmin = __longlong_as_double((long long)gb);
+      if (gmin == INFINITY) {  // infeasible (cannot happen for finite costs); uniform over the CTA
+        fail = true;
+        break;
+      }
+      int tb = 0x7fffffff, bj = -1, brj = -1;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const bool cand = ((open >> k) & 1u) && spc[k] == gmin;
+        const int t = r4c[k] == -1 ? -pos[k] - (1 << 20) : pos[k];
+        if (cand && t < tb) { tb = t; bj = tid + nt * k; brj = r4c[k]; }
+      }
+      {
+        const int wtb = __reduce_min_sync(0xffffffffu, tb);
+        if (lane == 0) red_tb[warp] = wtb;
+      }
+      __syncthreads();
+      const int tbmin = __reduce_min_sync(0xffffffffu, lane < nw ? red_tb[lane] : 0x7fffffff);
+      if (tb == tbmin) { s_j = bj; s_rj = brj; }     // scan positions are unique: exactly one thread
+      const int j_last = remaining[nrem - 1];
+      __syncthreads();
+      const int j = s_j, r_j = s_rj;
+      const int index = tbmin < 0 ? -(tbmin + (1 << 20)) : tbmin;
+      minval = gmin;
+      if (tid == 0) remaining[index] = j_last;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        if (tid + nt * k == j) open &= ~(1u << k);
+        if (tid + nt * k == j_last) pos[k] = index;
+      }
+      --nrem;
+      if (r_j == -1) { sink = j; break; }
+      i = r_j;
+    }
+    if (fail) break;
+    __syncthreads();
+    if (tid == 0) u[cur] = __dadd_rn(u[cur], minval);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int j = tid + nt * k;
+      if (j < nc && !((open >> k) & 1u)) {
+        const double d = __dsub_rn(minval, spc[k]);
+        if (r4c[k] != -1) u[r4c[k]] = __dadd_rn(u[r4c[k]], d);
+        v[k] = __dsub_rn(v[k], d);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {   // augment along the alternating path
+      int j = sink;
+      while (true) {
+        const int i2 = path[j];
+        row4col[j] = i2;
+        const int tmp = col4row[i2];
+        col4row[i2] = j;
+        j = tmp;
+        if (i2 == cur) break;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int j = tid + nt * k;
+      if (j < nc) r4c[k] = row4col[j];
+    }
+  }
+  if (fail) {
+    if (tid == 0) { out_n[b] = 0; atomicExch(status, 1); }
+    return;
+  }
+  if (!transposed) {
+    for (int i = tid; i < nr; i += nt) { oq[i] = i; ot[i] = col4row[i]; }
+  } else {
+    for (int t = tid; t < nr; t += nt) {
+      const int q = col4row[t];
+      int rank = 0;
+      for (int t2 = 0; t2 < nr; ++t2) rank += col4row[t2] < q;
+      oq[rank] = q;
+      ot[rank] = t;
+    }
+  }
+  if (tid == 0) out_n[b] = nr;
+}
+
 size_t lsap_warp_smem(int ncap) { return (sizeof(double) + 4 * sizeof(int)) * (size_t)ncap + 16; }
 
 size_t lsap_smem(int ncap, int nthreads) {
@@ -494,6 +662,22 @@ extern "C" int cdetr_lsap(const float* cost, const int* tgt_off, int B, int Q, i
     const size_t smem = stage_cost ? base + slab : lsap_smem(ncap, 32);
     { static DevAttrCache cfg = {}; CDETR_CHECK_CUDA(cdetr_ensure_smem(lsap_kernel<true>, 200 * 1024, &cfg)); }
     lsap_kernel<true><<<B, 32, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status, stage_cost, (int)base);
+  } else if (ncap <= 4096 && !legacy) {
+    // register-resident CTA solver: one column per thread up to 1024 columns, then 2 / 4 per thread
+    const int cpl = ncap <= 1024 ? 1 : (ncap <= 2048 ? 2 : 4);
+    int nt = ((ncap + cpl - 1) / cpl + 31) / 32 * 32;
+    if (nt < 64) nt = 64;
+    const size_t smem = lsap_warp_smem(ncap);
+#define CDETR_LSAP_BLOCK(N)                                                                              \
+  do {                                                                                                   \
+    static DevAttrCache cfg = {};                                                                        \
+    CDETR_CHECK_CUDA(cdetr_ensure_smem(lsap_block_kernel<N>, 128 * 1024, &cfg));                         \
+    lsap_block_kernel<N><<<B, nt, smem, s>>>(cost, tgt_off, Q, Tmax, out_q, out_t, out_n, status);       \
+  } while (0)
+    if (cpl == 1) CDETR_LSAP_BLOCK(1);
+    else if (cpl == 2) CDETR_LSAP_BLOCK(2);
+    else CDETR_LSAP_BLOCK(4);
+#undef CDETR_LSAP_BLOCK
   } else {
     int nt = 256;
     if (ncap > 768) nt = 512;
