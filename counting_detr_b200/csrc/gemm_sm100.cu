@@ -50,7 +50,10 @@ struct KernelArgs {
   int kb_per_split;  // k blocks (of 64) handled by one K-split
   int num_kb;
   int tiles_m, tiles_n, total_tiles;  // tile index = (split * tiles_m + mt) * tiles_n + nt
-  int tile_m;                         // output rows per tile: 128, or 256 for a CTA pair (cta_group::2)
+  int tile_m;                         // output rows per tile: 128, or 256 for a CTA pair (cta_group::2), or tile_rows
+  int tile_rows;                      // valid rows of a tile's 128 TMEM lanes (< 128: implicit conv on maps whose width does
+                                      // not divide 128 -- the tile is th image rows x tw pixels = tile_rows linear rows)
+  int conv_wblk;                      // mode-1 conv, widths not dividing 64: k blocks (64 pixels, zero-filled past W) per image row
   uint32_t idesc;
   uint32_t pass_mask;  // which of the three split-bf16 products are issued: 1 hi*hi, 2 hi_a*lo_b, 4 lo_a*hi_b (7 = all)
   uint32_t tx_a, tx_b; // bytes one k-block's TMA loads deliver per operand (a lo plane no product reads is not loaded)
@@ -207,10 +210,11 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ++slab_gen;
         }
         const int hw = args.cH * args.cW;
-        int cb = 0, ch0 = 0;             // mode 0 conv: image and first pixel row of this 128-pixel tile
+        int cb = 0, ch0 = 0, cw0 = 0;    // mode 0 conv: image, first pixel row and first pixel column of this tile
         if (!NT && args.conv) {
           cb = m0 / hw;
           ch0 = (m0 - cb * hw) / args.cW;
+          cw0 = m0 - cb * hw - ch0 * args.cW;   // != 0 only for tiles narrower than the image row (tile_rows < 128)
         }
         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
           const int s = it % stages;
@@ -230,7 +234,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const int k0 = kb * BK;
               const int tap = k0 / args.cC;
               const int dh = (tap / 3 - 1) * args.cdil * args.csign, dw = (tap % 3 - 1) * args.cdil * args.csign;
-              tma_load_5d_pair(a_s, &tmA, &full_bar[s], k0 - tap * args.cC, dw, ch0 + dh, cb, 0);
+              tma_load_5d_pair(a_s, &tmA, &full_bar[s], k0 - tap * args.cC, cw0 + dw, ch0 + dh, cb, 0);
             } else {
               tma_load_3d_pair(a_s, &tmA, &full_bar[s], kb * BK, m0, 0);           // box {64, 128, 2}
             }
@@ -243,18 +247,42 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const int k0 = kb * BK;
               const int tap = k0 / args.cC;
               const int dh = (tap / 3 - 1) * args.cdil * args.csign, dw = (tap % 3 - 1) * args.cdil * args.csign;
-              tma_load_5d(a_s, &tmA, &full_bar[s], k0 - tap * args.cC, dw, ch0 + dh, cb, 0);
+              if (args.tile_rows != BM) {   // narrow tile: one box per plane, the lo plane still lives 128 rows behind hi
+                tma_load_5d(a_s, &tmA, &full_bar[s], k0 - tap * args.cC, cw0 + dw, ch0 + dh, cb, 0);
+                if (args.pass_mask & 4u)
+                  tma_load_5d(a_s + BM * 128, &tmA, &full_bar[s], k0 - tap * args.cC, cw0 + dw, ch0 + dh, cb, 1);
+              } else {
+                tma_load_5d(a_s, &tmA, &full_bar[s], k0 - tap * args.cC, cw0 + dw, ch0 + dh, cb, 0);
+              }
             } else {
               tma_load_3d(a_s, &tmA, &full_bar[s], kb * BK, m0, 0);  // box {64, BM, 2}
             }
             tma_load_3d(b_s, &tmB, &full_bar[s], kb * BK, n0, 0);  // box {64, BN, 2}
           } else if (args.conv) {
-            for (int c = 0; c < BM / 64; ++c)                       // box {64(mn), 64(k), 2}
-              tma_load_3d(a_s + c * 16384, &tmA, &full_bar[s], m0 + 64 * c, kb * BK, 0);
+            const int krow = kb * BK;                               // first pixel (= k index) of this k block
+            if (args.conv_wblk > 0) {   // dy as {n_out, W, H, B}: the 64-pixel box is clipped (zero-filled) at the row end too
+              const int rowi = kb / args.conv_wblk;
+              const int ab_ = rowi / args.cH;
+              for (int c = 0; c < BM / 64; ++c)
+                tma_load_5d(a_s + c * 16384, &tmA, &full_bar[s], m0 + 64 * c, (kb - rowi * args.conv_wblk) * 64,
+                            rowi - ab_ * args.cH, ab_, 0);
+            } else {
+              for (int c = 0; c < BM / 64; ++c)                       // box {64(mn), 64(k), 2}
+                tma_load_3d(a_s + c * 16384, &tmA, &full_bar[s], m0 + 64 * c, krow, 0);
+            }
             // k block = 64 consecutive pixels of one image: box {64 c, min(W,64), 64/min(W,64), 1, 2}
-            const int p0 = kb * BK;
-            const int pb = p0 / hw, rem = p0 - pb * hw;
-            const int ph0 = rem / args.cW, pw0 = rem - ph0 * args.cW;
+            int pb, ph0, pw0;
+            if (args.conv_wblk > 0) {   // k block = 64 pixels of ONE image row starting at 64 * wb; past W the box is zeros
+              const int rowi = kb / args.conv_wblk;
+              pw0 = (kb - rowi * args.conv_wblk) * 64;
+              pb = rowi / args.cH;
+              ph0 = rowi - pb * args.cH;
+            } else {
+              const int p0 = kb * BK;
+              pb = p0 / hw;
+              const int rem = p0 - pb * hw;
+              ph0 = rem / args.cW; pw0 = rem - ph0 * args.cW;
+            }
             for (int c = 0; c < (BN + 63) / 64; ++c) {
               const int nn = n0 + 64 * c;
               const int tap = nn / args.cC;
@@ -602,7 +630,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     if (ti == 0 && warp == 2 && lane == 0) DBG_T(4);
     const int row_t = m0 + q * 32 + lane;  // row held by this thread in the TMEM phase
-    const float rs = (ep.row_scale != nullptr && row_t < args.M) ? ep.row_scale[row_t] : 1.0f;
+    const float rs = (ep.row_scale != nullptr && row_t < args.M && q * 32 + lane < args.tile_rows) ? ep.row_scale[row_t] : 1.0f;
     const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * args.tmem_cols;
     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
       const int cl = c0 + g8;     // tile-local first column of this lane's 8-vector in the coalesced phase
@@ -619,7 +647,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int i = 0; i < 4; ++i) {
         const int row = m0 + q * 32 + rr + 8 * i;
         pa0[i] = make_uint4(0, 0, 0, 0); pa1[i] = pa0[i]; pm[i] = pa0[i];
-        if (row < args.M) {
+        if (row < args.M && q * 32 + rr + 8 * i < args.tile_rows) {
           if (pre_add) {
             if (ep.add_hi != nullptr) {
               pa0[i] = __ldg(reinterpret_cast<const uint4*>(ep.add_hi + (int64_t)row * ep.ld_add + nb));
@@ -652,7 +680,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int i = 0; i < 4; ++i) {
           const int rl = rr + 8 * i;
           const int row = m0 + q * 32 + rl;
-          if (row >= args.M) continue;
+          if (row >= args.M || q * 32 + rl >= args.tile_rows) continue;
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = stg[rl * STG_LD + g8 + j] + bias8[j];
@@ -946,7 +974,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   CDETR_CHECK_ARG(bn >= 16 && bn <= 256 && bn % 16 == 0, "gemm: bad block_n %d", bn);
   CDETR_CHECK_ARG(!nt || bn % 64 == 0, "gemm: mode 1 needs block_n multiple of 64");
 
-  const int num_kb = cdiv(g->K, BK);
+  int num_kb = cdiv(g->K, BK);
   int splits = g->split_k > 1 ? g->split_k : 1;
   if (splits > num_kb) splits = num_kb;
   int kb_per_split = cdiv(num_kb, splits);
@@ -960,7 +988,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   if (g->accumulate) CDETR_CHECK_ARG(g->out_f32 != nullptr, "gemm: accumulate needs out_f32");
 
   const bool conv = g->conv_taps != 0;
-  int conv_B = 0;
+  int conv_B = 0, conv_tw = 0, conv_th = 0, conv_wblk = 0;
   if (conv) {
     const int H = g->conv_H, W = g->conv_W, C = g->conv_C;
     CDETR_CHECK_ARG(g->conv_taps == 9 && H > 0 && W > 0 && C > 0 && C % 64 == 0 && g->conv_dil >= 1,
@@ -972,15 +1000,36 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
     conv_B = (int)(pixels / ((int64_t)H * W));
     if (!nt) {
       CDETR_CHECK_ARG(g->K == 9 * C, "gemm: conv mode 0 needs K == 9*C");
-      CDETR_CHECK_ARG(W <= BM && BM % W == 0 && (H * W) % BM == 0,
-                      "gemm: implicit conv needs W | 128 and 128 | H*W (H=%d W=%d)", H, W);
+      // An M tile is th image rows x tw pixels = th * tw LINEAR rows of the [pixels, C] matrix.  Whole 128-row tiles when
+      // W | 128 and 128 | H*W; otherwise the largest (tw, th) with tw | W, th | H (th > 1 only when tw == W) and
+      // tw * th <= 128: the tile's remaining TMEM lanes are never stored (50 x 50 / 100 x 100 / 200 x 200 maps: 100 rows).
+      if (W <= BM && BM % W == 0 && (H * W) % BM == 0) {
+        conv_tw = W; conv_th = BM / W;
+      } else if (W <= BM) {
+        conv_tw = W; conv_th = 1;
+        for (int t = BM / W; t >= 1; --t) if (H % t == 0) { conv_th = t; break; }
+      } else {
+        conv_th = 1; conv_tw = 0;
+        for (int t = BM; t >= 1; --t) if (W % t == 0) { conv_tw = t; break; }
+      }
+      CDETR_CHECK_ARG(conv_tw * conv_th >= 64, "gemm: implicit conv finds no tile of >= 64 rows for a %d x %d map", H, W);
     } else {
       CDETR_CHECK_ARG(g->N == 9 * C && g->conv_sign == 1, "gemm: conv mode 1 needs N == 9*C, conv_sign == 1");
       const int bw = W < 64 ? W : 64;
-      CDETR_CHECK_ARG(64 % bw == 0 && W % bw == 0 && (H * W) % 64 == 0,
-                      "gemm: implicit conv wgrad needs W | 64 or 64 | W (H=%d W=%d)", H, W);
+      // k blocks of 64 consecutive pixels when W | 64 or 64 | W; otherwise 64-pixel blocks per image ROW, the part past W
+      // zero-filled by the TMA unit (the matching dy rows then multiply zeros)
+      if (!(64 % bw == 0 && W % bw == 0 && (H * W) % 64 == 0)) conv_wblk = (W + 63) / 64;
       CDETR_CHECK_ARG((9 * C) % bn == 0 && C % (bn < 64 ? bn : 64) == 0, "gemm: conv mode 1 needs block_n | 9*C");
     }
+  }
+  const int tile_rows = (conv && !nt) ? conv_tw * conv_th : BM;
+  if (tile_rows != BM) pair = false;          // narrow tiles: single CTA, generic epilogue (long-K GEMMs: the main loop dominates)
+  if (conv_wblk > 0) {                        // mode 1, padded k blocks: the contraction runs over B * H * wblk blocks
+    num_kb = conv_B * g->conv_H * conv_wblk;
+    splits = g->split_k > 1 ? g->split_k : 1;
+    if (splits > num_kb) splits = num_kb;
+    kb_per_split = cdiv(num_kb, splits);
+    splits = cdiv(num_kb, kb_per_split);
   }
 
   CUtensorMap tmA, tmB;
@@ -990,14 +1039,18 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   const int pl_a = (pmask & 4u) ? 2 : 1, pl_b = (pmask & 2u) ? 2 : 1;
   if (!nt) {
     if (conv) {
-      if ((rc = make_conv_map(&tmA, g->a, g->conv_C, g->conv_W, g->conv_H, conv_B, g->conv_W, BM / g->conv_W, pl_a)) != 0)
+      if ((rc = make_conv_map(&tmA, g->a, g->conv_C, g->conv_W, g->conv_H, conv_B, conv_tw, conv_th,
+                              conv_tw * conv_th != BM ? 1 : pl_a)) != 0)
         return rc;
     } else if ((rc = make_split_map(&tmA, g->a, g->K, g->M, BK, BM, pl_a)) != 0) return rc;
     if ((rc = make_split_map(&tmB, g->b, g->K, g->N, BK, pair ? bn / 2 : bn, pl_b)) != 0) return rc;
   } else {
-    if ((rc = make_split_map(&tmA, g->a, g->M, g->K, 64, BK, pl_a)) != 0) return rc;
+    if (conv && conv_wblk > 0) {   // dy [pixels, n_out] seen as {n_out, W, H, B}: boxes of 64 pixels clipped at the row end
+      CDETR_CHECK_ARG(g->M % 64 == 0, "gemm: conv mode 1 on narrow maps needs n_out %% 64 == 0 (%d)", g->M);
+      if ((rc = make_conv_map(&tmA, g->a, g->M, g->conv_W, g->conv_H, conv_B, 64, 1, pl_a)) != 0) return rc;
+    } else if ((rc = make_split_map(&tmA, g->a, g->M, g->K, 64, BK, pl_a)) != 0) return rc;
     if (conv) {
-      const int bw = g->conv_W < 64 ? g->conv_W : 64;
+      const int bw = conv_wblk > 0 ? 64 : (g->conv_W < 64 ? g->conv_W : 64);
       if ((rc = make_conv_map(&tmB, g->b, g->conv_C, g->conv_W, g->conv_H, conv_B, bw, 64 / bw, pl_b)) != 0) return rc;
     } else if ((rc = make_split_map(&tmB, g->b, g->N, g->K, 64, BK, pl_b)) != 0) return rc;
   }
@@ -1012,7 +1065,9 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   ka.cdil = g->conv_dil; ka.csign = g->conv_sign;
   ka.idesc = make_idesc_bf16_f32(pair ? 2 * BM : BM, bn, nt ? 1 : 0, nt ? 1 : 0);
   ka.pass_mask = pmask;
-  ka.tile_m = pair ? 2 * BM : BM;
+  ka.tile_m = pair ? 2 * BM : tile_rows;
+  ka.tile_rows = tile_rows;
+  ka.conv_wblk = conv_wblk;
   uint32_t cols = 32;
   while ((int)cols < bn) cols <<= 1;
   ka.tmem_cols = cols;
@@ -1020,6 +1075,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
   const uint32_t b_bytes = nt ? (uint32_t)((bn + 63) / 64) * 16384u : 2u * (uint32_t)(pair ? bn / 2 : bn) * 128u;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   ka.tx_a = a_bytes / 2u * (uint32_t)pl_a;     // both operands are laid out [hi | lo] per tile / per 64-wide chunk
+  if (tile_rows != BM) ka.tx_a = (uint32_t)tile_rows * 128u * (uint32_t)pl_a;   // the box delivers tile_rows rows per plane
   ka.tx_b = b_bytes / 2u * (uint32_t)pl_b;
   const uint32_t tail_bytes = (2 * MAX_STAGES + 6 + 16) * 8 + 16;
   const uint32_t smem_max = 227u * 1024u - 1024u - tail_bytes;   // dynamic smem minus alignment slack and barriers
@@ -1036,7 +1092,7 @@ extern "C" int cdetr_gemm(const cdetr_gemm_t* g, cdetr_stream_t stream_) {
                  (!has_os || tma_ok_split(g->out_split)) && (!has_as || tma_ok_split(g->add_split)) &&
                  (!has_af || tma_ok_f32(g->add_f32, g->ld_add_f32)) &&
                  (!has_mk || ((reinterpret_cast<uintptr_t>(g->mask.base) & 15) == 0 && g->mask.ld % 8 == 0));
-  if (tune.gemm_tma_epi == 0) tma_epi = false;
+  if (tune.gemm_tma_epi == 0 || tile_rows != BM) tma_epi = false;
   const uint32_t old_staging = 8u * 32u * 33u * 4u;
   uint32_t epi_buf = 4096u + (has_mk ? 2048u : 0u) + ((has_of && has_os) ? 4096u : 0u);
   int epi_nb = 2;

@@ -26,6 +26,15 @@ def _r8(n):
     return (n + 7) // 8 * 8
 
 
+def _conv_tile_rows(H, W):
+    """rows of the implicit-conv M tile cdetr_gemm picks for an H x W map (th image rows x tw pixels, tw | W, th | H,
+    th > 1 only for whole rows, tw * th <= 128): csrc/gemm_sm100.cu, conv geometry."""
+    if W <= 128:
+        th = next((t for t in range(128 // W, 0, -1) if H % t == 0), 1)
+        return W * th
+    return next((t for t in range(128, 0, -1) if W % t == 0), 1)
+
+
 class Lin:
     """A packed linear / conv-as-GEMM weight: split-bf16 [N, K] for forward, [K, N] for dgrad."""
 
@@ -527,9 +536,12 @@ class Engine:
         H, W = ((S1 + 6 - 7) // 2 + 1 + 2 - 3) // 2 + 1, ((S2 + 6 - 7) // 2 + 1 + 2 - 3) // 2 + 1
         import os
         off = bool(os.environ.get("CDETR_NO_IMPLICIT_CONV"))
+        tiled = os.environ.get("CDETR_TILED_CONV", "1") != "0"
         for blk in self.blocks:
             s = blk["stride"]
             ok = (not off and s == 1 and W in (16, 32, 64, 128) and (H * W) % 128 == 0 and blk["planes"] % 64 == 0)
+            if not ok and not off and tiled and s == 1 and blk["planes"] % 64 == 0:
+                ok = _conv_tile_rows(H, W) >= 64          # narrower tiles (e.g. 100 of 128 rows on 50 / 100 / 200-wide maps)
             if blk["c2"].implicit != ok:
                 blk["c2"].implicit = ok
                 self.packed = False

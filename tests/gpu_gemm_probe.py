@@ -9,12 +9,12 @@ dev = "cuda"
 fails = 0
 
 
-def report(name, got, ref):
+def report(name, got, ref, tol=2e-5):
     global fails
     err = (got.double() - ref).abs().max().item()
     scale = ref.abs().max().item() + 1e-30
     rel = err / scale
-    ok = rel < 2e-5
+    ok = rel < tol
     fails += (not ok)
     print(f"{'OK  ' if ok else 'FAIL'} {name}: max_abs_err={err:.3e} rel={rel:.3e}", flush=True)
     return ok
@@ -186,7 +186,8 @@ def run_conv(Bn, H, W, C, Co, dil):
     torch.cuda.synchronize()
     # staged layout [Co, (tap, c)]; reference grad is wrt the scaled weight -> multiply by scale for the raw weight
     ref_dw = (wd_.grad * scale.double()[:, None, None, None]).permute(0, 2, 3, 1).reshape(Co, 9 * C)
-    report(tag + " wgrad", dw, ref_dw)
+    # fp32 split-K accumulation over Mn pixels: the noise floor grows with the contraction length (1.3e-5 at 16 k pixels)
+    report(tag + " wgrad", dw, ref_dw, 2e-5 if Mn <= 20000 else 6e-5)
 
 
 run_conv(2, 32, 32, 64, 64, 1)
@@ -195,6 +196,47 @@ run_conv(2, 32, 32, 256, 256, 2)
 run_conv(1, 64, 64, 128, 128, 1)
 run_conv(1, 128, 128, 64, 64, 1)
 run_conv(3, 32, 32, 512, 512, 2)
+# maps whose width does not divide 128 (800 x 800 inputs: 200 / 100 / 50): narrower M tiles (100 of the 128 TMEM lanes),
+# generic epilogue; weight gradient with 64-pixel k blocks per image row, zero-filled past W
+run_conv(2, 50, 50, 64, 64, 1)
+run_conv(1, 50, 50, 256, 256, 2)
+run_conv(1, 100, 100, 128, 128, 1)
+run_conv(1, 200, 200, 64, 64, 1)
+run_conv(2, 12, 20, 64, 128, 1)
+
+
+def run_conv_fused(Bn, H, W, C, Co, dil):
+    """the engine's epilogues on a narrow-tile map: forward split output + ReLU, dgrad split output + ReLU mask"""
+    x = torch.randn(Bn, C, H, W, device=dev)
+    w = torch.randn(Co, C, 3, 3, device=dev) / (3.0 * C ** 0.5)
+    scale = torch.rand(Co, device=dev) + 0.5
+    bias = torch.randn(Co, device=dev)
+    Mn = Bn * H * W
+    xs = L.to_split(x.permute(0, 2, 3, 1).reshape(Mn, C).contiguous())
+    wf = torch.zeros(2, Co, 9 * C, device=dev, dtype=torch.bfloat16)
+    wdg = torch.zeros(2, C, 9 * Co, device=dev, dtype=torch.bfloat16)
+    L.call("cdetr_pack_weight", w.reshape(Co, C, 9).contiguous(), Co, C, 9, scale, wf, None)
+    L.call("cdetr_pack_weight_dgrad", w.reshape(Co, C, 9).contiguous(), Co, C, 9, scale, wdg)
+    y_ref = torch.relu(F.conv2d(x.double(), w.double() * scale.double()[:, None, None, None], padding=dil, dilation=dil)
+                       + bias.double()[None, :, None, None]).permute(0, 2, 3, 1).reshape(Mn, Co)
+    ys = torch.zeros(2, Mn, Co, device=dev, dtype=torch.bfloat16)
+    L.gemm(xs, wf, Mn, Co, 9 * C, mode=0, out_split=ys, bias=bias, relu=True, conv=(H, W, C, dil, 1))
+    torch.cuda.synchronize()
+    report(f"conv fused B={Bn} {H}x{W} C={C}->{Co} fwd split+relu", L.from_split(ys), y_ref)
+    dy = torch.randn(Mn, Co, device=dev)
+    dys = L.to_split(dy)
+    mask = L.to_split(torch.randn(Mn, C, device=dev))
+    dxs = torch.zeros(2, Mn, C, device=dev, dtype=torch.bfloat16)
+    L.gemm(dys, wdg, Mn, C, 9 * Co, mode=0, out_split=dxs, mask=mask, conv=(H, W, Co, dil, -1))
+    torch.cuda.synchronize()
+    dyn = L.from_split(dys).double().reshape(Bn, H, W, Co).permute(0, 3, 1, 2)
+    dx_ref = F.conv_transpose2d(dyn, w.double() * scale.double()[:, None, None, None], padding=dil, dilation=dil)
+    dx_ref = dx_ref.permute(0, 2, 3, 1).reshape(Mn, C) * (L.from_split(mask)[:, :C].double() > 0)
+    report(f"conv fused B={Bn} {H}x{W} C={C}->{Co} dgrad split+mask", L.from_split(dxs), dx_ref)
+
+
+run_conv_fused(2, 50, 50, 128, 128, 1)
+run_conv_fused(1, 100, 100, 64, 64, 1)
 
 # timing of the epilogue-bound shapes of the C3 step (split output unless noted)
 def timeit(fn, reps=20):
