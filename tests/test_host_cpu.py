@@ -228,3 +228,15 @@ def test_sass_has_tmem_operand_kernels(built_lib):
         assert "STTM" in body, f"{fn}: no tcgen05.st"
         # SS form: UTCHMMA gdesc[..], gdesc[..], tmem[acc], ...;  TS form: UTCHMMA tmem[a], gdesc[..], tmem[acc], ...
         assert re.search(r"UTCHMMA\s+tmem\[", body), f"{fn}: no MMA with the A operand in tensor memory"
+
+
+def test_implicit_conv_tile_geometry():
+    """Engine._plan_backbone mirrors cdetr_gemm's choice of the implicit-conv M tile (th image rows x tw pixels, tw | W,
+    th | H, th > 1 only for whole rows, tw * th <= 128): whole 128-row tiles at 512 x 512 inputs, 100-row tiles on the
+    200 / 100 / 50-wide maps of 800 x 800 inputs, and a refusal (explicit im2col) when no tile reaches 64 rows."""
+    from counting_detr_b200.engine import _conv_tile_rows
+    assert _conv_tile_rows(128, 128) == 128 and _conv_tile_rows(64, 64) == 128 and _conv_tile_rows(32, 32) == 128
+    assert _conv_tile_rows(200, 200) == 100 and _conv_tile_rows(100, 100) == 100 and _conv_tile_rows(50, 50) == 100
+    assert _conv_tile_rows(12, 20) == 120          # 6 rows of 20
+    assert _conv_tile_rows(7, 131) == 1            # prime width > 128: no usable tile -> explicit lowering
+    assert _conv_tile_rows(13, 37) == 37           # one row of 37 (< 64 -> explicit lowering)
